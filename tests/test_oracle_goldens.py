@@ -1,0 +1,226 @@
+"""Pins the CPU oracle against every golden the reference publishes for the hot path
+(BASELINE.md "Exact known answers") and against the
+reference's inline unit vectors.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+
+def f5(v):
+    return "%.5f" % v
+
+
+# ---- G1..G6: published known answers -------------------------------------------------
+
+def test_G1_nn_berlin52(berlin52):  # bench/baseline-solvers.tsv:2-6
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    assert f5(O.tour_length(P, O.nn_tour(P, 3))) == "8980.91797"
+
+
+def test_G2_nn_att532(att532):  # bench/baseline-solvers.tsv:12-16 (ATT header => EUC_2D, tsplib.rs:199-202)
+    _, x, y = att532
+    P = O.Problem(x, y)
+    assert f5(O.tour_length(P, O.nn_tour(P, 3))) == "112099.42188"
+
+
+def test_G3_opt_tour_length(berlin52, golden_dir):  # README.md:365
+    ids, x, y = berlin52
+    opt = O.read_opt_tour(os.path.join(golden_dir, "berlin52.opt.tour"))
+    pos = {int(c): k for k, c in enumerate(ids)}
+    P = O.Problem(x, y)
+    assert f5(O.tour_length(P, [pos[int(c)] for c in opt])) == "7544.36572"
+
+
+def test_G4_two_opt_from_identity(berlin52):  # docs/benchmarks.md:28
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    t, st, _ = O.two_opt_ref(P, np.arange(52))
+    assert f5(O.tour_length(P, t)) == "9368.31836"
+    assert (st.moves, st.passes, st.evals) == (87, 5, 6125)
+
+
+def test_G5_nn_then_two_opt(berlin52):  # README.md:385
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    t, st, _ = O.two_opt_ref(P, O.nn_tour(P, 3))
+    assert f5(O.tour_length(P, t)) == "8384.18848"
+    assert (st.moves, st.passes, st.evals) == (8, 3, 3675)
+
+
+def test_G6_nn_then_or_opt(berlin52):  # docs/benchmarks.md:48
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    t, st, _ = O.or_opt(P, O.nn_tour(P, 3))
+    assert f5(O.tour_length(P, t)) == "8097.47607"
+    assert (st.moves, st.passes, st.evals) == (10, 11, 136378)
+
+
+def test_matrix_and_recompute_are_bit_identical(berlin52):
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    Pm = O.Problem(tri=O.matrix_packed_f32(x, y), n=52)
+    nn = O.nn_tour(P, 3)
+    assert (O.nn_tour(Pm, 3) == nn).all()
+    for fn in (O.two_opt_ref, O.two_opt_best, O.or_opt):
+        a, sa, ma = fn(P, nn, log_cap=256)
+        b, sb, mb = fn(Pm, nn, log_cap=256)
+        assert (a == b).all() and ma == mb and sa.evals == sb.evals
+
+
+# ---- survey-time synthetic probes -----
+
+def test_synthetic_1k_probe():
+    x, y = O.gen_uniform(1000, 1000)
+    P = O.Problem(x, y)
+    nn = O.nn_tour(P, 3)
+    assert f5(O.tour_length(P, nn)) == "29890.67773"
+    t, st, _ = O.two_opt_ref(P, nn)
+    assert f5(O.tour_length(P, t)) == "25436.69336"
+    assert (st.passes, st.moves, st.evals) == (6, 331, 2985018)
+
+
+@pytest.mark.slow
+def test_synthetic_1k_mode_b_probe():
+    x, y = O.gen_uniform(1000, 1000)
+    P = O.Problem(x, y)
+    t, st, _ = O.two_opt_best(P, O.nn_tour(P, 3), nthreads=4)
+    assert f5(O.tour_length(P, t)) == "25282.04297"
+    assert (st.passes, st.moves, st.evals) == (171, 170, 85073013)
+
+
+# ---- reference inline unit vectors ---------------------------------------------------
+
+def test_swap_2opt_vectors():  # two_opt.rs:86-98
+    assert O.swap_2opt([1, 2, 3, 4], 1, 2).tolist() == [1, 3, 2, 4]
+    assert O.swap_2opt([1, 2, 3, 4], 1, 1).tolist() == [1, 2, 3, 4]
+    assert O.swap_2opt([1, 2, 3, 4], 2, 1).tolist() == [1, 2, 3, 4]  # from >= to: no-op
+
+
+TSP5 = ([0.0, 0.0, 0.0, 1.0, 1.0], [0.0, 0.5, 1.0, 1.0, 0.0])
+
+
+def test_two_opt_tsp5():  # two_opt.rs:100-131
+    P = O.Problem(*TSP5)
+    t, _, _ = O.two_opt_ref(P, np.arange(5))
+    assert t.tolist() == [0, 1, 2, 3, 4]
+    assert O.tour_length(P, t) == 4.0
+    t, _, _ = O.two_opt_best(P, np.arange(5))
+    assert t.tolist() == [0, 1, 2, 3, 4]
+
+
+def test_two_opt_tiny_n():
+    for n in (1, 2, 3):  # n=3: empty loop; n<3 underflows in the reference (documented no-op here)
+        P = O.Problem(np.arange(n, dtype=np.float32), np.zeros(n, dtype=np.float32))
+        t, st, _ = O.two_opt_ref(P, np.arange(n))
+        assert t.tolist() == list(range(n)) and st.moves == 0
+        t, st, _ = O.two_opt_best(P, np.arange(n))
+        assert t.tolist() == list(range(n)) and st.moves == 0
+
+
+def test_packed_triangle_vectors():  # distance_matrix.rs:326-349, 371-389
+    m = O.matrix_packed_f32([0.0, 0.0, 2.0], [0.0, 1.0, 0.0])
+    assert m[0] == 1.0 and m[1] == 2.0 and abs(m[2] - 2.236068) < 1e-6
+    m = O.matrix_packed_f32([0.0, 0.0, 2.0, 4.0], [0.0, 1.0, 0.0, 0.0])
+    assert len(m) == 6
+    P = O.Problem(tri=m, n=4)
+    assert O.distance(P, 1, 0) == 1.0 and O.distance(P, 2, 0) == 2.0
+    assert O.distance(P, 3, 0) == 4.0 and O.distance(P, 3, 2) == 2.0
+    assert abs(O.distance(P, 3, 1) - 4.1231055) < 1e-6
+    assert O.distance(P, 1, 3) == O.distance(P, 3, 1) and O.distance(P, 2, 2) == 0.0
+
+
+def test_tour_length_tsp5_and_short():  # distance_matrix.rs:221-245
+    P = O.Problem(*TSP5)
+    assert O.tour_length(P, [0, 1, 2, 3, 4]) == 4.0
+    assert O.tour_length(P, [3]) == 0.0 and O.tour_length(P, []) == 0.0
+    assert O.tour_length(P, [0, 2]) == 2.0  # closing edge + the one window
+
+
+def test_apply_relocation_vectors():  # or_opt.rs:202-240
+    assert O.or_opt_apply([0, 1, 2, 3, 4], 1, 1, 3, False).tolist() == [0, 2, 3, 1, 4]
+    assert O.or_opt_apply([0, 1, 2, 3, 4], 3, 1, 0, False).tolist() == [0, 3, 1, 2, 4]
+    assert O.or_opt_apply([0, 1, 2, 3, 4], 1, 2, 3, False).tolist() == [0, 3, 1, 2, 4]
+    assert O.or_opt_apply([0, 1, 2, 3, 4], 1, 2, 3, True).tolist() == [0, 3, 2, 1, 4]
+    assert O.or_opt_apply([0, 1, 2, 3, 4, 5], 1, 3, 4, False).tolist() == [0, 4, 1, 2, 3, 5]
+
+
+def test_or_opt_find_best_move_vectors():  # or_opt.rs:246-272
+    P = O.Problem([0.0, 1.0, 5.0, 2.0, 3.0], [0.0, 0.0, 5.0, 0.0, 0.0])
+    mv = O.or_opt_find_best(P, np.arange(5))
+    assert mv is not None and mv[0] < 0.0
+    Psq = O.Problem([0.0, 1.0, 1.0, 0.0], [0.0, 0.0, 1.0, 1.0])
+    assert O.or_opt_find_best(Psq, [0, 1, 2, 3]) is None
+
+
+def test_or_opt_solve_vectors():  # or_opt.rs:278-335
+    P = O.Problem([0.0, 1.0, 5.0, 2.0, 3.0], [0.0, 0.0, 5.0, 0.0, 0.0])
+    t, _, _ = O.or_opt(P, np.arange(5))
+    assert O.tour_length(P, t) < O.tour_length(P, np.arange(5))
+    Psq = O.Problem([0.0, 1.0, 1.0, 0.0], [0.0, 0.0, 1.0, 1.0])
+    t, _, _ = O.or_opt(Psq, [0, 1, 2, 3])
+    assert abs(O.tour_length(Psq, t) - 4.0) < 1e-2
+    P3 = O.Problem([0.0, 1.0, 1.0], [0.0, 0.0, 1.0])
+    t, st, _ = O.or_opt(P3, [2, 0, 1])
+    assert st.moves == 0  # n < 4 guard (the caller returns identity order, or_opt.rs:31-34)
+    P6 = O.Problem([0.0, 1.0, 5.0, 2.0, 3.0, 4.0], [0.0, 0.0, 5.0, 0.0, 0.0, 1.0])
+    t, _, _ = O.or_opt(P6, np.arange(6))
+    assert sorted(t.tolist()) == list(range(6))
+
+
+def test_knn_ordered_oracle_vector():  # tests/test_kdtree_and_distance_matrix.rs:199-243
+    P = O.Problem([0.0, 1.0, 2.0, 3.0, 10.0, 0.0], [0.0, 0.0, 0.0, 0.0, 0.0, 5.0])
+    want = [1, 2, 3, 5, 4]
+    for k in range(1, 6):
+        assert O.knn(P, k)[0].tolist() == want[:k]
+    assert O.knn(P, 7)[0].tolist() == want + [-1, -1]  # k > n-1: padded
+
+
+def test_knn_tie_rule_lower_position_first():  # mod.rs:1839-1858: insert after equal keys, gate d < kth
+    P = O.Problem([0.0, 1.0, -1.0, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0, -1.0])
+    assert O.knn(P, 2)[0].tolist() == [1, 2]
+    assert O.knn(P, 4)[0].tolist() == [1, 2, 3, 4]
+
+
+CITIES_10 = [(150, 20), (270, 70), (260, 180), (180, 280), (120, 290), (35, 220), (25, 80),
+             (80, 25), (155, 155), (90, 140)]  # teeline-web/src/explainers/explainer-cities.ts:15-26
+
+
+def test_mode_b_cyclic_two_optimal_scenario():  # teeline-web/src/explainers/two-opt.test.ts:76-83
+    x = [c[0] for c in CITIES_10]
+    y = [c[1] for c in CITIES_10]
+    P = O.Problem(x, y)
+    assert O.two_opt_best_scan(P, [0, 7, 6, 5, 4, 3, 2, 1, 8, 9], cyclic=True) is None
+
+
+def test_mode_b_threads_agree():
+    x, y = O.gen_uniform(400, 7)
+    P = O.Problem(x, y)
+    t = O.shuffle_tour(400, 3)
+    for cyc in (False, True):
+        a = O.two_opt_best_scan(P, t, cyclic=cyc, nthreads=1)
+        b = O.two_opt_best_scan(P, t, cyclic=cyc, nthreads=5)
+        assert a == b and a is not None
+
+
+def test_nint_metric_known_answer(berlin52, golden_dir):
+    """TSPLIB nint metric: berlin52's optimal tour is 7542 (tests/solvers_integration.rs:8)."""
+    ids, x, y = berlin52
+    opt = O.read_opt_tour(os.path.join(golden_dir, "berlin52.opt.tour"))
+    pos = {int(c): k for k, c in enumerate(ids)}
+    Pi = O.Problem(tri=O.matrix_packed_nint(x, y), n=52)
+    assert O.tour_length(Pi, [pos[int(c)] for c in opt]) == 7542.0
+    assert O.dist_nint(0, 0, 3, 4) == 5 and O.dist_nint(0, 0, 1, 1) == 1 and O.dist_nint(0, 0, 1, 2) == 2
+
+
+def test_generators_are_deterministic():
+    x, y = O.gen_uniform(8, 1000)
+    x2, y2 = O.gen_uniform(8, 1000)
+    assert (x == x2).all() and (y == y2).all() and x.min() >= 0 and x.max() < 1000
+    gx, gy = O.gen_grid(8, 1000)
+    assert (gx == np.floor(gx)).all() and gx.max() < 1e6
+    t = O.shuffle_tour(100, 5)
+    assert sorted(t.tolist()) == list(range(100)) and (t != np.arange(100)).any()
