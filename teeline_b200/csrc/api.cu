@@ -1,0 +1,359 @@
+// api.cu -- C ABI: context, problem, distance matrix, tour lengths, diagnostics.
+// See include/teeline_cuda.h for the reference interface each entry point replaces.
+#include "host.hpp"
+
+#include <cmath>
+#include <string>
+
+namespace tl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+bool tour_is_permutation(const uint32_t *tour, uint32_t n)
+{
+    std::vector<uint8_t> seen(n, 0);
+    for (uint32_t k = 0; k < n; ++k) {
+        if (tour[k] >= n || seen[tour[k]]) return false;
+        seen[tour[k]] = 1;
+    }
+    return true;
+}
+
+// sqrt_rn_fast is valid iff every dx*dx+dy*dy is 0 or >= 2^-101 and finite.  A
+// sufficient condition on the coordinates: all finite, |c| < 2^62 (no overflow), and
+// every non-zero |c| >= 2^-27 (so a non-zero difference is >= 2^-50 and its square
+// >= 2^-100).  Every TSPLIB-like instance satisfies it; anything else takes the
+// IEEE-safe kernels, with identical results.
+static bool coords_allow_fast_sqrt(const float *x, const float *y, uint32_t n)
+{
+    const float big = std::ldexp(1.0f, 62), tiny = std::ldexp(1.0f, -27);
+    for (uint32_t i = 0; i < n; ++i) {
+        for (float c : {x[i], y[i]}) {
+            if (!std::isfinite(c)) return false;
+            const float a = std::fabs(c);
+            if (a >= big || (a != 0.0f && a < tiny)) return false;
+        }
+    }
+    return true;
+}
+
+} // namespace tl
+
+using namespace tl;
+
+extern "C" {
+
+const char *tl_last_error(void) { return g_err; }
+const char *tl_version(void) { return "teeline_b200 0.1.0 (sm_100a)"; }
+
+static tl_status ctx_create_impl(int32_t device, void *stream, bool own, tl_ctx **out)
+{
+    if (!out) { set_error("tl_ctx_create: out is null"); return TL_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); libteeline_cuda has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return TL_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        set_error("tl_ctx_create: device %d out of range [0,%d)", device, count);
+        return TL_ERR_INVALID;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) { set_error("cudaSetDevice(%d) failed", device); return TL_ERR_CUDA; }
+    cudaDeviceProp prop;
+    TL_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                  prop.minor);
+        return TL_ERR_CUDA;
+    }
+    tl_ctx *c = new tl_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->total_mem = prop.totalGlobalMem;
+    if (own) {
+        cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) {
+            delete c;
+            set_error("cudaStreamCreate failed: %s", cudaGetErrorString(se));
+            return TL_ERR_CUDA;
+        }
+        c->own_stream = true;
+    } else {
+        c->stream = reinterpret_cast<cudaStream_t>(stream);
+    }
+    cudaError_t ce = configure_all_kernels();
+    if (ce != cudaSuccess) {
+        set_error("kernel attribute setup failed: %s", cudaGetErrorString(ce));
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return TL_ERR_CUDA;
+    }
+    *out = c;
+    return TL_OK;
+}
+
+tl_status tl_ctx_create(int32_t device, tl_ctx **out) { return ctx_create_impl(device, nullptr, true, out); }
+
+tl_status tl_ctx_create_on_stream(int32_t device, void *cuda_stream, tl_ctx **out)
+{
+    return ctx_create_impl(device, cuda_stream, false, out);
+}
+
+void tl_ctx_destroy(tl_ctx *ctx)
+{
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    if (ctx->nccl_comm) nccl_comm_destroy(ctx->nccl_comm);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+tl_status tl_ctx_sync(tl_ctx *ctx)
+{
+    if (!ctx) { set_error("tl_ctx_sync: null ctx"); return TL_ERR_INVALID; }
+    DeviceGuard g(ctx->device);
+    TL_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return TL_OK;
+}
+
+uint64_t tl_ctx_launch_count(const tl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+tl_status tl_nccl_unique_id(uint8_t id_out[TL_NCCL_ID_BYTES])
+{
+    if (!id_out) { set_error("tl_nccl_unique_id: null"); return TL_ERR_INVALID; }
+    return nccl_get_unique_id(id_out);
+}
+
+tl_status tl_ctx_attach_nccl(tl_ctx *ctx, const uint8_t id[TL_NCCL_ID_BYTES], int32_t rank, int32_t world)
+{
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) {
+        set_error("tl_ctx_attach_nccl: bad arguments");
+        return TL_ERR_INVALID;
+    }
+    DeviceGuard g(ctx->device);
+    if (ctx->nccl_comm) { nccl_comm_destroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    tl_status s = nccl_comm_init(&ctx->nccl_comm, id, rank, world);
+    if (s != TL_OK) return s;
+    ctx->rank = rank;
+    ctx->world = world;
+    return TL_OK;
+}
+
+// ---- problem ---------------------------------------------------------------------
+
+tl_status tl_problem_create_euc2d(tl_ctx *ctx, uint32_t n, const float *x, const float *y,
+                                  int32_t dist_kind, tl_problem **out)
+{
+    if (!ctx || !x || !y || !out) { set_error("tl_problem_create_euc2d: null argument"); return TL_ERR_INVALID; }
+    *out = nullptr;
+    if (n < 2) {
+        // DistanceMatrix::build: "distance matrix requires at least 2 points" (distance_matrix.rs:124-126)
+        set_error("distance matrix requires at least 2 points");
+        return TL_ERR_INVALID;
+    }
+    if (dist_kind != TL_DIST_F32_EXACT && dist_kind != TL_DIST_NINT_I32) {
+        set_error("unknown dist_kind %d", dist_kind);
+        return TL_ERR_INVALID;
+    }
+    DeviceGuard g(ctx->device);
+    tl_problem *p = new tl_problem();
+    p->ctx = ctx;
+    p->n = n;
+    p->kind = dist_kind == TL_DIST_NINT_I32 ? PK_EUC_NINT : PK_EUC_F32;
+    p->fast_sqrt = coords_allow_fast_sqrt(x, y, n);
+    std::vector<float2> h(n);
+    for (uint32_t i = 0; i < n; ++i) h[i] = make_float2(x[i], y[i]);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_xy), sizeof(float2) * n);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(p->d_xy, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("tl_problem_create_euc2d: %s", cudaGetErrorString(e));
+        if (p->d_xy) cudaFree(p->d_xy);
+        delete p;
+        return TL_ERR_CUDA;
+    }
+    *out = p;
+    return TL_OK;
+}
+
+tl_status tl_problem_create_explicit(tl_ctx *ctx, uint32_t n, const float *packed_tri, tl_problem **out)
+{
+    if (!ctx || !packed_tri || !out) { set_error("tl_problem_create_explicit: null argument"); return TL_ERR_INVALID; }
+    *out = nullptr;
+    if (n < 2) { set_error("distance matrix requires at least 2 points"); return TL_ERR_INVALID; }
+    DeviceGuard g(ctx->device);
+    const size_t cnt = (size_t)n * (n - 1) / 2;
+    tl_problem *p = new tl_problem();
+    p->ctx = ctx;
+    p->n = n;
+    p->kind = PK_EXPLICIT;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_tri), sizeof(float) * cnt);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(p->d_tri, packed_tri, sizeof(float) * cnt, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("tl_problem_create_explicit: %s", cudaGetErrorString(e));
+        if (p->d_tri) cudaFree(p->d_tri);
+        delete p;
+        return e == cudaErrorMemoryAllocation ? TL_ERR_NOMEM : TL_ERR_CUDA;
+    }
+    *out = p;
+    return TL_OK;
+}
+
+void tl_problem_destroy(tl_problem *p)
+{
+    if (!p) return;
+    DeviceGuard g(p->ctx->device);
+    if (p->d_xy) cudaFree(p->d_xy);
+    if (p->d_tri) cudaFree(p->d_tri);
+    delete p;
+}
+
+static tl_status matrix_packed_impl(tl_problem *p, void *out, bool want_int)
+{
+    if (!p || !out) { set_error("tl_dist_matrix_packed: null argument"); return TL_ERR_INVALID; }
+    tl_ctx *c = p->ctx;
+    DeviceGuard g(c->device);
+    const size_t cnt = (size_t)p->n * (p->n - 1) / 2;
+    if (p->kind == PK_EXPLICIT) {
+        if (want_int) { set_error("EXPLICIT problems hold f32 distances"); return TL_ERR_UNSUPPORTED; }
+        TL_CUDA_TRY(cudaMemcpyAsync(out, p->d_tri, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return TL_OK;
+    }
+    if (want_int != (p->kind == PK_EUC_NINT)) {
+        set_error("distance kind mismatch: problem is %s", p->kind == PK_EUC_NINT ? "NINT_I32" : "F32_EXACT");
+        return TL_ERR_UNSUPPORTED;
+    }
+    DevBuf<uint32_t> d;
+    if (d.alloc(cnt) != cudaSuccess) { set_error("packed matrix of %zu entries does not fit", cnt); return TL_ERR_NOMEM; }
+    launch_k1_packed(p->d_xy, p->n, p->fast_sqrt, want_int, d.p, c->sm_count, c->stream);
+    c->launches++;
+    TL_CUDA_TRY(cudaGetLastError());
+    TL_CUDA_TRY(cudaMemcpyAsync(out, d.p, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TL_OK;
+}
+
+tl_status tl_dist_matrix_packed(tl_problem *p, float *out) { return matrix_packed_impl(p, out, false); }
+tl_status tl_dist_matrix_packed_i32(tl_problem *p, int32_t *out) { return matrix_packed_impl(p, out, true); }
+
+// ---- tour lengths --------------------------------------------------------------------
+
+tl_status tl_tour_lengths(tl_problem *p, const uint32_t *tours, size_t batch, int32_t mode, float *out_f32)
+{
+    if (!p || (!tours && batch) || (!out_f32 && batch)) { set_error("tl_tour_lengths: null argument"); return TL_ERR_INVALID; }
+    if (mode != TL_LEN_EXACT && mode != TL_LEN_FAST) { set_error("tl_tour_lengths: unknown mode %d", mode); return TL_ERR_INVALID; }
+    if (p->kind == PK_EUC_NINT) { set_error("NINT_I32 problem: use tl_tour_lengths_i64"); return TL_ERR_UNSUPPORTED; }
+    if (batch == 0) return TL_OK;
+    tl_ctx *c = p->ctx;
+    DeviceGuard g(c->device);
+    DevBuf<uint32_t> d_t;
+    DevBuf<float> d_o;
+    if (d_t.alloc(batch * p->n) != cudaSuccess || d_o.alloc(batch) != cudaSuccess) {
+        set_error("tl_tour_lengths: device allocation failed");
+        return TL_ERR_NOMEM;
+    }
+    TL_CUDA_TRY(cudaMemcpyAsync(d_t.p, tours, batch * p->n * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_tour_lengths_f32(p->d_xy, p->d_tri, p->n, d_t.p, batch, p->fast_sqrt, mode == TL_LEN_FAST, d_o.p,
+                            c->sm_count, c->stream);
+    c->launches++;
+    TL_CUDA_TRY(cudaGetLastError());
+    TL_CUDA_TRY(cudaMemcpyAsync(out_f32, d_o.p, batch * 4, cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TL_OK;
+}
+
+tl_status tl_tour_lengths_i64(tl_problem *p, const uint32_t *tours, size_t batch, int64_t *out)
+{
+    if (!p || (!tours && batch) || (!out && batch)) { set_error("tl_tour_lengths_i64: null argument"); return TL_ERR_INVALID; }
+    if (p->kind != PK_EUC_NINT) { set_error("tl_tour_lengths_i64 needs a NINT_I32 problem"); return TL_ERR_UNSUPPORTED; }
+    if (batch == 0) return TL_OK;
+    tl_ctx *c = p->ctx;
+    DeviceGuard g(c->device);
+    DevBuf<uint32_t> d_t;
+    DevBuf<long long> d_o;
+    if (d_t.alloc(batch * p->n) != cudaSuccess || d_o.alloc(batch) != cudaSuccess) {
+        set_error("tl_tour_lengths_i64: device allocation failed");
+        return TL_ERR_NOMEM;
+    }
+    TL_CUDA_TRY(cudaMemcpyAsync(d_t.p, tours, batch * p->n * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_tour_lengths_nint(p->d_xy, p->n, d_t.p, batch, d_o.p, c->sm_count, c->stream);
+    c->launches++;
+    TL_CUDA_TRY(cudaGetLastError());
+    TL_CUDA_TRY(cudaMemcpyAsync(out, d_o.p, batch * 8, cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TL_OK;
+}
+
+// ---- diagnostics -----------------------------------------------------------------------
+
+tl_status tl_selftest_sqrt(tl_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches)
+{
+    if (!ctx || !mismatches || hi_bits < lo_bits) { set_error("tl_selftest_sqrt: bad arguments"); return TL_ERR_INVALID; }
+    DeviceGuard g(ctx->device);
+    DevBuf<unsigned long long> d;
+    TL_CUDA_TRY(d.alloc(1));
+    TL_CUDA_TRY(cudaMemsetAsync(d.p, 0, 8, ctx->stream));
+    launch_selftest_sqrt(lo_bits, hi_bits, d.p, ctx->sm_count, ctx->stream);
+    ctx->launches++;
+    TL_CUDA_TRY(cudaGetLastError());
+    unsigned long long h = 0;
+    TL_CUDA_TRY(cudaMemcpyAsync(&h, d.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TL_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *mismatches = h;
+    return TL_OK;
+}
+
+tl_status tl_microbench_fp32(tl_ctx *ctx, double *ffma_per_s, double *mufu_per_s)
+{
+    if (!ctx || !ffma_per_s || !mufu_per_s) { set_error("tl_microbench_fp32: null argument"); return TL_ERR_INVALID; }
+    DeviceGuard g(ctx->device);
+    DevBuf<float> sink;
+    TL_CUDA_TRY(sink.alloc(1));
+    cudaEvent_t e0, e1;
+    TL_CUDA_TRY(cudaEventCreate(&e0));
+    TL_CUDA_TRY(cudaEventCreate(&e1));
+    const int grid = ctx->sm_count * 8, iters = 4096;
+    double best_f = 0, best_m = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms = 0;
+        cudaEventRecord(e0, ctx->stream);
+        launch_microbench_ffma(sink.p, iters, grid, ctx->stream);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double f = (double)grid * 256 * iters * 16 * 8 / (ms * 1e-3);
+        if (rep && f > best_f) best_f = f;
+        cudaEventRecord(e0, ctx->stream);
+        launch_microbench_mufu(sink.p, iters / 4, grid, ctx->stream);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double m = (double)grid * 256 * (iters / 4) * 16 * 4 / (ms * 1e-3);
+        if (rep && m > best_m) best_m = m;
+        ctx->launches += 2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    TL_CUDA_TRY(cudaGetLastError());
+    *ffma_per_s = best_f;
+    *mufu_per_s = best_m;
+    return TL_OK;
+}
+
+} // extern "C"

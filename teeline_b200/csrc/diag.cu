@@ -1,0 +1,78 @@
+// diag.cu -- self-tests and microbenchmarks that back the numerics and roofline claims.
+#include "kernels.cuh"
+
+namespace tl {
+
+namespace {
+
+// sqrt_rn_fast == sqrt_rn_safe for every bit pattern in [lo, hi]
+__global__ void __launch_bounds__(256)
+    selftest_sqrt_kernel(uint32_t lo, uint32_t hi, unsigned long long *mismatch)
+{
+    const uint64_t span = (uint64_t)hi - lo + 1;
+    unsigned long long bad = 0;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < span;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float(lo + (uint32_t)t);
+        const float a = sqrt_rn_fast(x), b = sqrt_rn_safe(x);
+        bad += (__float_as_uint(a) != __float_as_uint(b));
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
+// dependent-free FFMA streams: 8 independent accumulators per thread
+__global__ void __launch_bounds__(256) microbench_ffma_kernel(float *sink, int iters)
+{
+    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+          a7 = a0 + 7;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = __fmaf_rn(a0, m, c);
+            a1 = __fmaf_rn(a1, m, c);
+            a2 = __fmaf_rn(a2, m, c);
+            a3 = __fmaf_rn(a3, m, c);
+            a4 = __fmaf_rn(a4, m, c);
+            a5 = __fmaf_rn(a5, m, c);
+            a6 = __fmaf_rn(a6, m, c);
+            a7 = __fmaf_rn(a7, m, c);
+        }
+    }
+    const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456f) sink[0] = s;
+}
+
+__global__ void __launch_bounds__(256) microbench_mufu_kernel(float *sink, int iters)
+{
+    float a0 = threadIdx.x + 1.0f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a0));
+            asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a1));
+            asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a2));
+            asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a3));
+        }
+    }
+    const float s = a0 + a1 + a2 + a3;
+    if (s == 123.456f) sink[0] = s;
+}
+
+} // namespace
+
+void launch_selftest_sqrt(uint32_t lo, uint32_t hi, unsigned long long *mismatch, int sm_count,
+                          cudaStream_t st)
+{
+    selftest_sqrt_kernel<<<sm_count * 16, 256, 0, st>>>(lo, hi, mismatch);
+}
+void launch_microbench_ffma(float *sink, int iters, int grid, cudaStream_t st)
+{
+    microbench_ffma_kernel<<<grid, 256, 0, st>>>(sink, iters);
+}
+void launch_microbench_mufu(float *sink, int iters, int grid, cudaStream_t st)
+{
+    microbench_mufu_kernel<<<grid, 256, 0, st>>>(sink, iters);
+}
+
+} // namespace tl

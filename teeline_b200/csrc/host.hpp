@@ -1,0 +1,85 @@
+// host.hpp -- host-side objects behind the opaque C handles (internal).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+struct tl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t total_mem = 0;
+    uint64_t launches = 0;
+    // NCCL (resolved at run time with dlopen, see nccl_shim.cu)
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+enum ProblemKind { PK_EUC_F32 = 0, PK_EUC_NINT = 1, PK_EXPLICIT = 2 };
+
+struct tl_problem {
+    tl_ctx *ctx = nullptr;
+    uint32_t n = 0;
+    ProblemKind kind = PK_EUC_F32;
+    bool fast_sqrt = false; // coordinates guarantee dx^2+dy^2 in {0} U [2^-101, FLT_MAX]
+    float2 *d_xy = nullptr; // city-ordered coordinates (coordinate problems)
+    float *d_tri = nullptr; // packed triangle (EXPLICIT problems)
+};
+
+namespace tl {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t count = 0;
+    cudaError_t alloc(size_t c)
+    {
+        release();
+        count = c;
+        if (c == 0) return cudaSuccess;
+        return cudaMalloc(reinterpret_cast<void **>(&p), c * sizeof(T));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        count = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+bool tour_is_permutation(const uint32_t *tour, uint32_t n);
+
+// NCCL shim (nccl_shim.cu)
+tl_status nccl_get_unique_id(uint8_t *id128);
+tl_status nccl_comm_init(void **comm, const uint8_t *id128, int rank, int world);
+tl_status nccl_all_gather_bytes(void *comm, const void *send, void *recv, size_t bytes_per_rank,
+                                cudaStream_t st);
+void nccl_comm_destroy(void *comm);
+
+} // namespace tl

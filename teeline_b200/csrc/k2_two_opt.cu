@@ -1,0 +1,333 @@
+// k2_two_opt.cu -- K2: best-improvement 2-opt scan ("Mode B"), coordinate-recompute path.
+//
+// What it computes ("2-opt B"; neighbourhood of
+// src/tsp/two_opt.rs:17,29,34): over all pairs 0 <= i, i+2 <= j <= jmax
+//     delta(i,j) = (d(p_i,p_j) + d(p_i+1,p_j+1)) - (d(p_i,p_i+1) + d(p_j,p_j+1))
+// each operation rounded to f32, and returns argmin with strict '<' from 0 in
+// (i,j) lexicographic order (lowest (i,j) wins ties).
+//
+// How: the triangle is walked along DIAGONALS k = j - i.  Moving down a diagonal,
+// d(p_i+1,p_j+1) of pair (i,j) is d(p_i',p_j') of pair (i+1,j+1), so every move
+// costs ONE new distance (5 FP32 ops + one IEEE sqrt) plus 3 adds and a min.
+// Lane l of a warp owns R consecutive diagonals K0 + l*R + r; the R+1 tour-ordered
+// points it needs form a sliding window held in registers (rotated by unrolling R
+// steps), so per row a lane issues two 128-bit LDS: the warp-broadcast row point
+// and one new window point.  Tour-ordered points (x, y, city, entering-edge length)
+// are staged per warp tile with TMA 1-D bulk copies (cp.async.bulk + mbarrier).
+// The running minimum is tracked with FMNMX3 trees and a rarely taken slow path
+// (improving moves are rare near a local optimum), so the hot loop carries no
+// index arithmetic.
+//
+// Roofline: FP32 issue (no tensor cores: K=2 is not a contraction).  Algorithmic
+// work 15 flop/move, ~0 bytes/move.
+#include "kernels.cuh"
+
+#include <math_constants.h>
+
+namespace tl {
+
+namespace {
+
+constexpr int R = kScanR;
+constexpr int BW = kScanBW;
+constexpr int TI = kScanTI;
+constexpr int WARPS = kScanWarps;
+constexpr int ROWS_CAP = TI + 1;       // positions i0 .. i0+cnt
+constexpr int COLS_CAP = TI + BW + 1;  // positions i0+K0 .. i0+K0+cnt+BW
+constexpr int WARP_PTS = ROWS_CAP + COLS_CAP;
+
+__device__ __forceinline__ int find_band(const int32_t *__restrict__ band_first, int nbands, int item)
+{
+    int lo = 0, hi = nbands - 1; // largest b with band_first[b] <= item
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&band_first[mid]) <= item)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+    two_opt_scan_recompute_kernel(const Pt *__restrict__ pts, const ScanGeom g,
+                                  const int32_t *__restrict__ band_first, BestF *__restrict__ blockbest,
+                                  const DevState *__restrict__ state)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (state->done) return;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Pt *srow = reinterpret_cast<Pt *>(smem_raw) + warp * WARP_PTS;
+    Pt *scol = srow + ROWS_CAP;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * WARP_PTS * sizeof(Pt));
+    uint64_t *bar = bars + warp;
+    BestF *red = reinterpret_cast<BestF *>(bars + WARPS);
+
+    if (lane == 0) mbar_init(bar, 1);
+    mbar_fence_init();
+    __syncthreads();
+
+    uint32_t phase = 0;
+    float best = 0.0f;
+    uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
+
+    const int total_warps = gridDim.x * WARPS;
+    for (int item = g.item_begin + blockIdx.x * WARPS + warp; item < g.item_end; item += total_warps) {
+        const int b = find_band(band_first, g.nbands, item);
+        const int K0 = 2 + b * BW;
+        const int H = g.jmax - K0 + 1; // rows 0 .. H-1 exist on the band's first diagonal
+        const int r_begin = (item - __ldg(&band_first[b])) * g.chunk;
+        const int r_end = min(r_begin + g.chunk, H);
+        const int lane_k0 = K0 + lane * R; // first diagonal of this lane
+
+        for (int i0 = r_begin; i0 < r_end; i0 += TI) {
+            const int cnt = min(TI, r_end - i0);
+            __syncwarp(); // everyone is done with the previous tile's smem
+            if (lane == 0) {
+                const uint32_t rb = (uint32_t)(cnt + 1) * sizeof(Pt);
+                const uint32_t cb = (uint32_t)(cnt + BW + 1) * sizeof(Pt);
+                mbar_expect_tx(bar, rb + cb);
+                tma_load_1d(srow, pts + i0, rb, bar);
+                tma_load_1d(scol, pts + i0 + K0, cb, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+
+            // carried distances E[r] = d(p_i, p_j) for j = i + lane_k0 + r, and the window of
+            // points at positions j+1
+            float E[R], wx[R], wy[R], ws[R];
+            {
+                const Pt rp0 = srow[0];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const Pt c = scol[lane * R + r];
+                    E[r] = dist_f32<FAST>(rp0.x, rp0.y, c.x, c.y);
+                    const Pt w = scol[lane * R + r + 1];
+                    wx[r] = w.x;
+                    wy[r] = w.y;
+                    ws[r] = w.sp;
+                }
+            }
+
+#pragma unroll 1
+            for (int t = 0; t < cnt; t += R) {
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    if (t + u < cnt) { // warp-uniform
+                        const int tau = t + u;
+                        const Pt rp = srow[tau + 1];                 // (x,y) of i+1 and s_i, broadcast
+                        const Pt nx = scol[tau + lane * R + R + 1];  // next window point
+                        float dl[R];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int ph = (r + u) % R;
+                            const float en = dist_f32<FAST>(rp.x, rp.y, wx[ph], wy[ph]);
+                            const float cur = __fadd_rn(rp.sp, ws[ph]);
+                            const float nw = __fadd_rn(E[r], en);
+                            dl[r] = __fsub_rn(nw, cur);
+                            E[r] = en;
+                        }
+                        float m = dl[0];
+#pragma unroll
+                        for (int r = 1; r < R; ++r) m = fminf(m, dl[r]);
+                        if (m < best) { // rare: an improving move better than this thread's best
+                            const uint32_t i = (uint32_t)(i0 + tau);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                const uint32_t j = i + (uint32_t)(lane_k0 + r);
+                                // the cyclic neighbourhood excludes (0, n-1): both edges share p_0
+                                const bool excluded = g.cyclic && i == 0 && j == (uint32_t)(g.n - 1);
+                                if (dl[r] < best && !excluded) {
+                                    best = dl[r];
+                                    bi = i;
+                                    bj = j;
+                                }
+                            }
+                        }
+                        wx[u] = nx.x;
+                        wy[u] = nx.y;
+                        ws[u] = nx.sp;
+                    }
+                }
+            }
+        }
+    }
+
+    // deterministic argmin: (delta, i, j) lexicographic across lanes, warps, blocks
+    warp_argmin_2opt(best, bi, bj);
+    if (lane == 0) red[warp] = BestF{best, bi, bj, 0u};
+    __syncthreads();
+    if (warp == 0) {
+        BestF v = (lane < WARPS) ? red[lane] : BestF{0.0f, 0xffffffffu, 0xffffffffu, 0u};
+        warp_argmin_2opt(v.delta, v.i, v.j);
+        if (lane == 0) blockbest[blockIdx.x] = v;
+    }
+}
+
+// tour-ordered point records from city coordinates and a tour
+template <bool FAST>
+__global__ void __launch_bounds__(256)
+    build_pts_kernel(const float2 *__restrict__ xy, const uint32_t *__restrict__ tour, uint32_t n,
+                     uint32_t npad, int cyclic, Pt *__restrict__ pts)
+{
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < npad; q += gridDim.x * blockDim.x) {
+        Pt p;
+        if (q < n || (q == n && cyclic)) {
+            const uint32_t c = tour[q == n ? 0 : q];
+            const uint32_t cp = tour[q == 0 ? n - 1 : q - 1];
+            const float2 a = xy[c], bprev = xy[cp];
+            p.x = a.x;
+            p.y = a.y;
+            p.city = (int32_t)c;
+            p.sp = (q == 0 && !cyclic) ? 0.0f : dist_f32<FAST>(bprev.x, bprev.y, a.x, a.y);
+        } else {
+            p.x = 0.0f;
+            p.y = 0.0f;
+            p.city = -1;
+            p.sp = -CUDART_INF_F; // delta = new - (s_i + -inf) = +inf: never selected
+        }
+        pts[q] = p;
+    }
+}
+
+// Reduce the candidate records (all blocks do it redundantly: <= a few hundred
+// records), then write dst = src with path[i+1..=j] reversed (swap_2opt,
+// src/tsp/two_opt.rs:69-79).  Entering-edge lengths inside the segment are the
+// old ones mirrored; the two new edges are recomputed.  The last block to finish
+// updates the loop state.
+template <bool FAST>
+__global__ void __launch_bounds__(256)
+    apply_two_opt_recompute_kernel(const Pt *__restrict__ src, Pt *__restrict__ dst, uint32_t n,
+                                   uint32_t npad, int cyclic, int dst_index, const BestF *__restrict__ cand,
+                                   int ncand, DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
+                                   uint64_t log_cap)
+{
+    if (state->done) return;
+    __shared__ BestF sred[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    BestF v{0.0f, 0xffffffffu, 0xffffffffu, 0u};
+    for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+        const BestF o = cand[c];
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    warp_argmin_2opt(v.delta, v.i, v.j);
+    if (lane == 0) sred[warp] = v;
+    __syncthreads();
+    v = sred[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+        const BestF o = sred[w];
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    const bool found = v.i != 0xffffffffu;
+    const uint32_t mi = v.i, mj = v.j;
+
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < npad; q += gridDim.x * blockDim.x) {
+        Pt p;
+        if (found && q > mi && q <= mj) {
+            p = src[mi + 1 + mj - q];
+            if (q == mi + 1) {
+                const Pt a = src[mi], b = src[mj];
+                p.sp = dist_f32<FAST>(a.x, a.y, b.x, b.y);
+            } else {
+                p.sp = src[mi + mj + 2 - q].sp;
+            }
+        } else {
+            p = src[q];
+            if (found && q == mj + 1) {
+                const Pt a = src[mi + 1];
+                p.sp = dist_f32<FAST>(a.x, a.y, p.x, p.y);
+            }
+        }
+        dst[q] = p;
+    }
+
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tk = atomicAdd(ticket, 1u);
+        if (tk == gridDim.x - 1) { // last block: everyone has read `state` by now
+            *ticket = 0u;
+            state->scans += 1;
+            state->cur_buf = dst_index;
+            if (found) {
+                const unsigned long long m = state->moves;
+                if (log && m < log_cap) log[m] = tl_move{v.delta, mi, mj, 0, 0, 0};
+                state->moves = m + 1;
+                if (state->max_moves >= 0 && (long long)(m + 1) >= state->max_moves) state->done = 1;
+            } else {
+                state->done = 1;
+                state->converged = 1;
+            }
+            __threadfence();
+        }
+    }
+    (void)n;
+    (void)cyclic;
+}
+
+__global__ void extract_tour_kernel(const Pt *__restrict__ pts, uint32_t n, uint32_t *__restrict__ tour)
+{
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+        tour[q] = (uint32_t)pts[q].city;
+}
+
+} // namespace
+
+size_t scan_recompute_smem_bytes()
+{
+    return (size_t)WARPS * WARP_PTS * sizeof(Pt) + WARPS * sizeof(uint64_t) + WARPS * sizeof(BestF);
+}
+
+cudaError_t scan_recompute_configure()
+{
+    cudaError_t e = cudaFuncSetAttribute(two_opt_scan_recompute_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)scan_recompute_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(two_opt_scan_recompute_kernel<false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)scan_recompute_smem_bytes());
+}
+
+void launch_scan_recompute(const Pt *pts, const ScanGeom &g, const int32_t *band_first, BestF *blockbest,
+                           const DevState *state, int grid, bool fast, cudaStream_t st)
+{
+    const size_t smem = scan_recompute_smem_bytes();
+    if (fast)
+        two_opt_scan_recompute_kernel<true><<<grid, WARPS * 32, smem, st>>>(pts, g, band_first, blockbest, state);
+    else
+        two_opt_scan_recompute_kernel<false><<<grid, WARPS * 32, smem, st>>>(pts, g, band_first, blockbest, state);
+}
+
+void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic,
+                      bool fast, Pt *pts, cudaStream_t st)
+{
+    const int grid = (int)((npad + 255) / 256);
+    if (fast)
+        build_pts_kernel<true><<<grid, 256, 0, st>>>(xy, tour, n, npad, cyclic, pts);
+    else
+        build_pts_kernel<false><<<grid, 256, 0, st>>>(xy, tour, n, npad, cyclic, pts);
+}
+
+void launch_apply_two_opt_recompute(const Pt *src, Pt *dst, uint32_t n, uint32_t npad, int cyclic,
+                                    int dst_index, bool fast, const BestF *cand, int ncand, DevState *state,
+                                    unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid,
+                                    cudaStream_t st)
+{
+    if (fast)
+        apply_two_opt_recompute_kernel<true><<<grid, 256, 0, st>>>(src, dst, n, npad, cyclic, dst_index, cand,
+                                                                  ncand, state, ticket, log, log_cap);
+    else
+        apply_two_opt_recompute_kernel<false><<<grid, 256, 0, st>>>(src, dst, n, npad, cyclic, dst_index, cand,
+                                                                   ncand, state, ticket, log, log_cap);
+}
+
+void launch_extract_tour(const Pt *pts, uint32_t n, uint32_t *tour, cudaStream_t st)
+{
+    extract_tour_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, tour);
+}
+
+} // namespace tl

@@ -1,0 +1,220 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+reference's published goldens.  Bit-exact for everything: distances, move sequences, tours."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import teeline_b200 as T
+    return T
+
+
+@pytest.fixture(scope="module")
+def ctx(T):
+    c = T.Context(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def f5(v):
+    return "%.5f" % v
+
+
+# ---- numerics foundation ---------------------------------------------------------------
+
+def test_fast_sqrt_is_ieee_over_its_whole_domain(ctx):
+    """sqrt_rn_fast == sqrt.rn for EVERY f32 in [2^-101, FLT_MAX] and for +0 (exhaustive)."""
+    assert ctx.selftest_sqrt(0x0D000000, 0x7F7FFFFF) == 0
+    assert ctx.selftest_sqrt(0, 0) == 0
+
+
+# ---- K1 -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["berlin52.tsp", "a280.tsp", "att532.tsp"])
+def test_k1_packed_matches_oracle_fixtures(T, ctx, golden_dir, name):
+    _, x, y = O.read_tsplib_coords(os.path.join(golden_dir, name))
+    p = T.Problem.euc2d(ctx, x, y)
+    assert (bits(p.matrix_packed()) == bits(O.matrix_packed_f32(x, y))).all()
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 1000, 3001])
+def test_k1_packed_matches_oracle_synthetic(T, ctx, n):
+    x, y = O.gen_uniform(n, n)
+    p = T.Problem.euc2d(ctx, x, y)
+    assert (bits(p.matrix_packed()) == bits(O.matrix_packed_f32(x, y))).all()
+
+
+def test_k1_reference_unit_vectors(T, ctx):  # distance_matrix.rs:326-349
+    p = T.Problem.euc2d(ctx, [0.0, 0.0], [0.0, 1.0])
+    assert p.matrix_packed().tolist() == [1.0]
+    m = T.Problem.euc2d(ctx, [0.0, 0.0, 2.0], [0.0, 1.0, 0.0]).matrix_packed()
+    assert m[0] == 1.0 and m[1] == 2.0 and abs(m[2] - 2.236068) < 1e-6
+    with pytest.raises(T.TeelineError):  # "distance matrix requires at least 2 points"
+        T.Problem.euc2d(ctx, [100.0], [100.0])
+
+
+def test_k1_nint_matches_oracle(T, ctx, berlin52):
+    _, x, y = berlin52
+    p = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32)
+    assert (p.matrix_packed() == O.matrix_packed_nint(x, y)).all()
+    gx, gy = O.gen_grid(1500, 1500)
+    p = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32)
+    assert (p.matrix_packed() == O.matrix_packed_nint(gx, gy)).all()
+
+
+def test_k1_safe_sqrt_path_for_wild_coordinates(T, ctx):
+    """Coordinates outside the fast-sqrt guarantee (tiny / huge) take the IEEE-safe kernels."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(300) * 1e-30).astype(np.float32)
+    y = (rng.standard_normal(300) * 1e-30).astype(np.float32)
+    x[:10] = 0.0
+    p = T.Problem.euc2d(ctx, x, y)
+    assert (bits(p.matrix_packed()) == bits(O.matrix_packed_f32(x, y))).all()
+
+
+# ---- K4 -------------------------------------------------------------------------------
+
+def test_k4_goldens(T, ctx, berlin52, golden_dir):
+    ids, x, y = berlin52
+    p = T.Problem.euc2d(ctx, x, y)
+    P = O.Problem(x, y)
+    nn = O.nn_tour(P, 3)
+    assert f5(p.tour_lengths(nn)[0]) == "8980.91797"  # G1
+    opt = O.read_opt_tour(os.path.join(golden_dir, "berlin52.opt.tour"))
+    pos = {int(c): k for k, c in enumerate(ids)}
+    assert f5(p.tour_lengths([pos[int(c)] for c in opt])[0]) == "7544.36572"  # G3
+
+
+def test_k4_batch_exact_matches_oracle(T, ctx):
+    n, B = 1000, 257
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    p = T.Problem.euc2d(ctx, x, y)
+    tours = np.stack([O.shuffle_tour(n, s) for s in range(1, B + 1)])
+    want = O.tour_lengths(P, tours).astype(np.float32)
+    got = p.tour_lengths(tours, T.LEN_EXACT)
+    assert (bits(got) == bits(want)).all()
+    fast = p.tour_lengths(tours, T.LEN_FAST)
+    assert np.allclose(fast, want, rtol=1e-5)  # f64 pairwise sum of the same f32 edges
+
+
+def test_k4_edge_cases(T, ctx):
+    x, y = O.gen_uniform(33, 3)
+    P = O.Problem(x, y)
+    p = T.Problem.euc2d(ctx, x, y)
+    t = O.shuffle_tour(33, 9)
+    assert bits(p.tour_lengths(t))[0] == bits(np.float32(O.tour_length(P, t)))[0]
+    bad = t.copy().astype(np.uint32)
+    bad[7] = 1000  # unknown position -> 0.0 (distance_matrix.rs:221-231)
+    assert p.tour_lengths(bad)[0] == 0.0
+    p2 = T.Problem.euc2d(ctx, [0.0, 3.0], [0.0, 4.0])
+    assert p2.tour_lengths([0, 1])[0] == 10.0  # closing edge + the one window
+
+
+def test_k4_explicit_and_nint(T, ctx, berlin52, golden_dir):
+    ids, x, y = berlin52
+    tri = O.matrix_packed_f32(x, y)
+    pe = T.Problem.explicit(ctx, tri, 52)
+    P = O.Problem(x, y)
+    nn = O.nn_tour(P, 3)
+    assert f5(pe.tour_lengths(nn)[0]) == "8980.91797"
+    pi = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32)
+    opt = O.read_opt_tour(os.path.join(golden_dir, "berlin52.opt.tour"))
+    pos = {int(c): k for k, c in enumerate(ids)}
+    assert pi.tour_lengths([pos[int(c)] for c in opt])[0] == 7542
+
+
+# ---- K2 Mode B, recompute path ------------------------------------------------------------
+
+def check_mode_b(T, ctx, x, y, start, cyclic=False, max_moves=-1):
+    P = O.Problem(x, y)
+    want_t, want_st, want_mv = O.two_opt_best(P, start, cyclic=cyclic, max_moves=max_moves, nthreads=4,
+                                              log_cap=1 << 16)
+    p = T.Problem.euc2d(ctx, x, y)
+    algo = T.ALGO_TWO_OPT_BEST_CYCLIC if cyclic else T.ALGO_TWO_OPT_BEST
+    got_t, st, mv = p.local_search(algo, start, path=T.PATH_RECOMPUTE, max_moves=max_moves, log_cap=1 << 16)
+    assert [(m[1], m[2]) for m in mv] == [(m[1], m[2]) for m in want_mv]
+    assert [np.float32(m[0]) for m in mv] == [np.float32(m[0]) for m in want_mv]
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals)
+    assert bool(st.converged) == (max_moves < 0 or want_st.moves < max_moves)
+    return got_t, st
+
+
+def test_k2_best_berlin52(T, ctx, berlin52):
+    _, x, y = berlin52
+    check_mode_b(T, ctx, x, y, O.nn_tour(O.Problem(x, y), 3))
+    check_mode_b(T, ctx, x, y, np.arange(52))
+    check_mode_b(T, ctx, x, y, np.arange(52), cyclic=True)
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 13, 290, 291, 292, 600])
+def test_k2_best_small_and_band_edges(T, ctx, n):
+    x, y = O.gen_uniform(n, 100 + n)
+    for cyclic in (False, True):
+        check_mode_b(T, ctx, x, y, O.shuffle_tour(n, n), cyclic=cyclic)
+
+
+def test_k2_best_tiny_n_is_noop(T, ctx):
+    for n in (2, 3):
+        x, y = O.gen_uniform(n, n)
+        p = T.Problem.euc2d(ctx, x, y)
+        t, st, mv = p.local_search(T.ALGO_TWO_OPT_BEST, np.arange(n)[::-1].copy())
+        assert t.tolist() == list(range(n))[::-1] and int(st.moves) == 0 and st.converged == 1
+
+
+def test_k2_best_1k_nn_start_matches_survey_probe(T, ctx):
+    x, y = O.gen_uniform(1000, 1000)
+    P = O.Problem(x, y)
+    t, st = check_mode_b(T, ctx, x, y, O.nn_tour(P, 3))
+    assert f5(O.tour_length(P, t)) == "25282.04297" and int(st.moves) == 170
+
+
+def test_k2_best_1k_random_start_bounded(T, ctx):
+    x, y = O.gen_uniform(1000, 1000)
+    check_mode_b(T, ctx, x, y, O.shuffle_tour(1000, 11), max_moves=60)
+
+
+def test_k2_best_ties_resolve_to_lowest_ij(T, ctx):
+    """Integer lattice => many exactly equal deltas; the lowest (i,j) must win every time."""
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 12, 400).astype(np.float32)
+    y = rng.integers(0, 12, 400).astype(np.float32)
+    check_mode_b(T, ctx, x, y, O.shuffle_tour(400, 2), max_moves=80)
+    check_mode_b(T, ctx, x, y, O.shuffle_tour(400, 2), cyclic=True, max_moves=80)
+
+
+def test_k2_scan_only_10k(T, ctx):
+    """One full-size scan (P(10k) = 49 975 003 pairs) against the threaded oracle scan."""
+    n = 10000
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    p = T.Problem.euc2d(ctx, x, y)
+    for seed in (1, 2):
+        t = O.shuffle_tour(n, seed)
+        s = p.session(T.ALGO_TWO_OPT_BEST, t, T.PATH_RECOMPUTE)
+        got = s.scan()
+        want = O.two_opt_best_scan(P, t, nthreads=8)
+        assert got is not None and (got[1], got[2]) == (want[1], want[2])
+        assert np.float32(got[0]) == np.float32(want[0])
+        s.close()
+
+
+def test_k2_rejects_bad_tours(T, ctx):
+    x, y = O.gen_uniform(10, 1)
+    p = T.Problem.euc2d(ctx, x, y)
+    with pytest.raises(T.TeelineError):
+        p.local_search(T.ALGO_TWO_OPT_BEST, [0, 1, 2, 3, 4, 5, 6, 7, 8, 8])
+    with pytest.raises(T.TeelineError):
+        p.local_search(T.ALGO_TWO_OPT_BEST, [0, 1, 2, 3, 4, 5, 6, 7, 8, 10])
