@@ -21,6 +21,7 @@
 // Roofline: FP32 issue (no tensor cores: K=2 is not a contraction).  Algorithmic
 // work 15 flop/move, ~0 bytes/move.
 #include "kernels.cuh"
+#include "two_opt_apply.cuh"
 
 #include <math_constants.h>
 
@@ -192,16 +193,17 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Reduce the candidate records (all blocks do it redundantly: <= a few hundred
-// records), then write dst = src with path[i+1..=j] reversed (swap_2opt,
-// src/tsp/two_opt.rs:69-79).  Entering-edge lengths inside the segment are the
-// old ones mirrored; the two new edges are recomputed.  The last block to finish
-// updates the loop state.
+// Reduce the candidate records (every block does it redundantly: at most a few hundred
+// records), then reverse path[i+1..=j] IN PLACE (swap_2opt, src/tsp/two_opt.rs:69-79).
+// Thread t swaps the (x, y, city) fields of positions (i+1+t, j-t) and the entering-edge
+// lengths of positions (i+2+t, j-t): inside the segment the old edge lengths are simply
+// mirrored (the metric is bitwise symmetric); the two new edges are recomputed by thread 0.
+// Every field of every record is read and written by exactly one thread, so the in-place
+// update is race free.  The last block to finish updates the loop state.
 template <bool FAST>
 __global__ void __launch_bounds__(256)
-    apply_two_opt_recompute_kernel(const Pt *__restrict__ src, Pt *__restrict__ dst, uint32_t n,
-                                   uint32_t npad, int cyclic, int dst_index, const BestF *__restrict__ cand,
-                                   int ncand, DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
+    apply_two_opt_recompute_kernel(Pt *__restrict__ pts, const BestF *__restrict__ cand, int ncand,
+                                   DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
                                    uint64_t log_cap)
 {
     if (state->done) return;
@@ -224,25 +226,7 @@ __global__ void __launch_bounds__(256)
     const bool found = v.i != 0xffffffffu;
     const uint32_t mi = v.i, mj = v.j;
 
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < npad; q += gridDim.x * blockDim.x) {
-        Pt p;
-        if (found && q > mi && q <= mj) {
-            p = src[mi + 1 + mj - q];
-            if (q == mi + 1) {
-                const Pt a = src[mi], b = src[mj];
-                p.sp = dist_f32<FAST>(a.x, a.y, b.x, b.y);
-            } else {
-                p.sp = src[mi + mj + 2 - q].sp;
-            }
-        } else {
-            p = src[q];
-            if (found && q == mj + 1) {
-                const Pt a = src[mi + 1];
-                p.sp = dist_f32<FAST>(a.x, a.y, p.x, p.y);
-            }
-        }
-        dst[q] = p;
-    }
+    if (found) reverse_segment_inplace<FAST>(pts, mi, mj, nullptr);
 
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -251,7 +235,6 @@ __global__ void __launch_bounds__(256)
         if (tk == gridDim.x - 1) { // last block: everyone has read `state` by now
             *ticket = 0u;
             state->scans += 1;
-            state->cur_buf = dst_index;
             if (found) {
                 const unsigned long long m = state->moves;
                 if (log && m < log_cap) log[m] = tl_move{v.delta, mi, mj, 0, 0, 0};
@@ -264,8 +247,6 @@ __global__ void __launch_bounds__(256)
             __threadfence();
         }
     }
-    (void)n;
-    (void)cyclic;
 }
 
 __global__ void extract_tour_kernel(const Pt *__restrict__ pts, uint32_t n, uint32_t *__restrict__ tour)
@@ -312,17 +293,14 @@ void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32
         build_pts_kernel<false><<<grid, 256, 0, st>>>(xy, tour, n, npad, cyclic, pts);
 }
 
-void launch_apply_two_opt_recompute(const Pt *src, Pt *dst, uint32_t n, uint32_t npad, int cyclic,
-                                    int dst_index, bool fast, const BestF *cand, int ncand, DevState *state,
+void launch_apply_two_opt_recompute(Pt *pts, bool fast, const BestF *cand, int ncand, DevState *state,
                                     unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid,
                                     cudaStream_t st)
 {
     if (fast)
-        apply_two_opt_recompute_kernel<true><<<grid, 256, 0, st>>>(src, dst, n, npad, cyclic, dst_index, cand,
-                                                                  ncand, state, ticket, log, log_cap);
+        apply_two_opt_recompute_kernel<true><<<grid, 256, 0, st>>>(pts, cand, ncand, state, ticket, log, log_cap);
     else
-        apply_two_opt_recompute_kernel<false><<<grid, 256, 0, st>>>(src, dst, n, npad, cyclic, dst_index, cand,
-                                                                   ncand, state, ticket, log, log_cap);
+        apply_two_opt_recompute_kernel<false><<<grid, 256, 0, st>>>(pts, cand, ncand, state, ticket, log, log_cap);
 }
 
 void launch_extract_tour(const Pt *pts, uint32_t n, uint32_t *tour, cudaStream_t st)

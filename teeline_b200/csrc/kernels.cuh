@@ -33,13 +33,14 @@ struct DevState {
     long long max_moves; // < 0: unlimited
     int32_t done;        // 1: converged or max_moves reached -> later launches are no-ops
     int32_t converged;
-    int32_t cur_buf;     // which ping-pong buffer holds the current tour
-    int32_t pad0;
     // Mode R cursor
     int32_t cur_i, cur_j;
     int32_t improved_in_pass;
     int32_t window_rows;
     unsigned long long passes;
+    unsigned long long found_key; // Mode R: (i << 32 | j) of the first improving pair, ~0 if none
+    float last_delta;
+    int32_t pad1;
 };
 
 struct BestF {
@@ -75,11 +76,16 @@ void launch_scan_recompute(const Pt *pts, const ScanGeom &g, const int32_t *band
                            const DevState *state, int grid, bool fast, cudaStream_t st);
 void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic,
                       bool fast, Pt *pts, cudaStream_t st);
-void launch_apply_two_opt_recompute(const Pt *src, Pt *dst, uint32_t n, uint32_t npad, int cyclic,
-                                    int dst_index, bool fast, const BestF *cand, int ncand, DevState *state,
+void launch_apply_two_opt_recompute(Pt *pts, bool fast, const BestF *cand, int ncand, DevState *state,
                                     unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid,
                                     cudaStream_t st);
 void launch_extract_tour(const Pt *pts, uint32_t n, uint32_t *tour, cudaStream_t st);
+
+// K2 Mode R (reference-exact first improvement)
+constexpr int kRefWindow0 = 8; // rows scanned per launch right after a hit
+void launch_find_first(const Pt *pts, uint32_t n, DevState *state, int grid, bool fast, cudaStream_t st);
+void launch_apply_first(Pt *pts, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
+                        uint64_t log_cap, int grid, bool fast, cudaStream_t st);
 
 // K4
 void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, const uint32_t *tours,

@@ -1,7 +1,7 @@
 // session.cu -- device-resident local-search sessions and the one-call wrappers.
 //
-// A session keeps the tour on the device in tour order (two ping-pong buffers of
-// 16-byte point records) and runs  scan -> [all-gather] -> apply  iterations without
+// A session keeps the tour on the device in tour order (16-byte point records,
+// reversed in place by the apply kernel) and runs  scan -> [all-gather] -> apply  iterations without
 // host round trips: the apply kernel decides convergence on the device and later
 // launches become no-ops, so the host only synchronises once per batch of steps.
 #include "host.hpp"
@@ -27,8 +27,7 @@ struct tl_session {
 
     // recompute-path state
     uint32_t npad = 0;
-    DevBuf<Pt> pts[2];
-    int src = 0; // buffer the next scan reads
+    DevBuf<Pt> pts; // tour-ordered point records, updated in place by the apply kernel
 
     ScanGeom geom{};
     DevBuf<int32_t> band_first;
@@ -113,14 +112,13 @@ tl_status pull_state(tl_session *s)
 {
     TL_CUDA_TRY(cudaMemcpyAsync(&s->h, s->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, s->c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(s->c->stream));
-    s->src = s->h.cur_buf;
     return TL_OK;
 }
 
 tl_status launch_scan(tl_session *s)
 {
     BestF *mine = s->cand.p + (size_t)s->shard_index * s->grid;
-    launch_scan_recompute(s->pts[s->src].p, s->geom, s->band_first.p, mine, s->state.p, s->grid,
+    launch_scan_recompute(s->pts.p, s->geom, s->band_first.p, mine, s->state.p, s->grid,
                           s->p->fast_sqrt, s->c->stream);
     s->c->launches++;
     if (s->shard_count > 1) {
@@ -140,16 +138,26 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
         TL_CUDA_TRY(cudaEventRecord(s->ev0, s->c->stream));
         s->timing_open = true;
     }
-    const int apply_grid = (int)std::min<uint32_t>((s->npad + 255) / 256, (uint32_t)s->c->sm_count * 4);
+    // one thread per swapped pair, at most n/2 pairs
+    const int apply_grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((s->n / 2 + 255) / 256, (uint32_t)s->c->sm_count));
+    if (s->algo == TL_ALGO_TWO_OPT_REF) {
+        const int find_grid = s->c->sm_count * 2;
+        for (uint32_t k = 0; k < steps; ++k) {
+            launch_find_first(s->pts.p, s->n, s->state.p, find_grid, s->p->fast_sqrt, s->c->stream);
+            launch_apply_first(s->pts.p, s->n, s->state.p, s->ticket.p, s->log.p, s->log_cap, apply_grid,
+                               s->p->fast_sqrt, s->c->stream);
+            s->c->launches += 2;
+        }
+        TL_CUDA_TRY(cudaGetLastError());
+        return TL_OK;
+    }
     for (uint32_t k = 0; k < steps; ++k) {
         tl_status st = launch_scan(s);
         if (st != TL_OK) return st;
-        const int dst = s->src ^ 1;
-        launch_apply_two_opt_recompute(s->pts[s->src].p, s->pts[dst].p, s->n, s->npad, s->cyclic, dst,
-                                       s->p->fast_sqrt, s->cand.p, s->grid * s->shard_count, s->state.p,
-                                       s->ticket.p, s->log.p, s->log_cap, apply_grid, s->c->stream);
+        launch_apply_two_opt_recompute(s->pts.p, s->p->fast_sqrt, s->cand.p, s->grid * s->shard_count,
+                                       s->state.p, s->ticket.p, s->log.p, s->log_cap, apply_grid,
+                                       s->c->stream);
         s->c->launches++;
-        s->src = dst;
     }
     TL_CUDA_TRY(cudaGetLastError());
     return TL_OK;
@@ -175,7 +183,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
 {
     if (!p || !tour || !out) { set_error("tl_session_create: null argument"); return TL_ERR_INVALID; }
     *out = nullptr;
-    if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC) {
+    if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC && algo != TL_ALGO_TWO_OPT_REF) {
         set_error("tl_session_create: algo %d not available in this build", algo);
         return TL_ERR_UNSUPPORTED;
     }
@@ -208,8 +216,8 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         return st;
     };
     DevBuf<uint32_t> d_tour;
-    if (d_tour.alloc(p->n) != cudaSuccess || s->pts[0].alloc(s->npad) != cudaSuccess ||
-        s->pts[1].alloc(s->npad) != cudaSuccess || s->state.alloc(1) != cudaSuccess ||
+    if (d_tour.alloc(p->n) != cudaSuccess || s->pts.alloc(s->npad) != cudaSuccess ||
+        s->state.alloc(1) != cudaSuccess ||
         s->ticket.alloc(1) != cudaSuccess || s->log.alloc(s->log_cap) != cudaSuccess ||
         cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         set_error("tl_session_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -218,17 +226,25 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     cudaError_t e = cudaMemcpyAsync(d_tour.p, tour, (size_t)p->n * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->ticket.p, 0, 4, c->stream);
     if (e != cudaSuccess) { set_error("tl_session_create: %s", cudaGetErrorString(e)); return fail(TL_ERR_CUDA); }
-    launch_build_pts(p->d_xy, d_tour.p, p->n, s->npad, s->cyclic, p->fast_sqrt, s->pts[0].p, c->stream);
+    launch_build_pts(p->d_xy, d_tour.p, p->n, s->npad, s->cyclic, p->fast_sqrt, s->pts.p, c->stream);
     c->launches++;
-    // both buffers start identical, so a no-op step leaves either one valid
-    e = cudaMemcpyAsync(s->pts[1].p, s->pts[0].p, (size_t)s->npad * sizeof(Pt), cudaMemcpyDeviceToDevice, c->stream);
-    if (e != cudaSuccess) { set_error("tl_session_create: %s", cudaGetErrorString(e)); return fail(TL_ERR_CUDA); }
     memset(&s->h, 0, sizeof s->h);
     s->h.max_moves = -1;
-    if (s->trivial) { s->h.done = 1; s->h.converged = 1; s->h.scans = 1; }
+    s->h.cur_i = 0;
+    s->h.cur_j = 2;
+    s->h.window_rows = kRefWindow0;
+    s->h.found_key = ~0ull;
+    if (s->trivial) {
+        // oracle/reference behaviour for n < 4: Mode B scans once and finds nothing; the reference
+        // loop runs one empty pass for n == 3 and is skipped for n < 3 (two_opt.rs:17,29 underflow)
+        s->h.done = 1;
+        s->h.converged = 1;
+        s->h.scans = 1;
+        s->h.passes = (p->n == 3) ? 1 : 0;
+    }
     tl_status st = push_state(s); // also waits for d_tour's consumers
     if (st != TL_OK) return fail(st);
-    if (!s->trivial) {
+    if (!s->trivial && algo != TL_ALGO_TWO_OPT_REF) {
         st = upload_geometry(s);
         if (st != TL_OK) return fail(st);
     }
@@ -249,6 +265,10 @@ void tl_session_destroy(tl_session *s)
 tl_status tl_session_set_shard(tl_session *s, int32_t index, int32_t count)
 {
     if (!s || count < 1 || index < 0 || index >= count) { set_error("tl_session_set_shard: bad arguments"); return TL_ERR_INVALID; }
+    if (s->algo == TL_ALGO_TWO_OPT_REF) {
+        if (count > 1) { set_error("Mode R does not shard (replicas only)"); return TL_ERR_UNSUPPORTED; }
+        return TL_OK;
+    }
     DeviceGuard g(s->c->device);
     s->shard_index = index;
     s->shard_count = count;
@@ -260,6 +280,7 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
 {
     if (!s || !found) { set_error("tl_session_scan: null argument"); return TL_ERR_INVALID; }
     *found = 0;
+    if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_scan: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
     if (s->trivial) return TL_OK;
     DeviceGuard g(s->c->device);
     // a scan of a finished session is still a scan: lift the no-op flag for this launch
@@ -301,8 +322,8 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
     st = push_state(s);
     if (st != TL_OK) return st;
     while (!s->h.done) {
-        uint32_t batch = 16;
-        if (max_moves >= 0) batch = (uint32_t)std::min<int64_t>(batch, std::max<int64_t>(1, max_moves - (int64_t)s->h.moves));
+        uint32_t batch = s->algo == TL_ALGO_TWO_OPT_REF ? 64 : 16;
+        if (max_moves >= 0 && s->algo != TL_ALGO_TWO_OPT_REF) batch = (uint32_t)std::min<int64_t>(batch, std::max<int64_t>(1, max_moves - (int64_t)s->h.moves));
         st = enqueue_steps(s, batch);
         if (st != TL_OK) return st;
         st = pull_state(s);
@@ -319,7 +340,7 @@ tl_status tl_session_tour(tl_session *s, uint32_t *tour_out)
     if (st != TL_OK) return st;
     DevBuf<uint32_t> d;
     TL_CUDA_TRY(d.alloc(s->n));
-    launch_extract_tour(s->pts[s->h.cur_buf].p, s->n, d.p, s->c->stream);
+    launch_extract_tour(s->pts.p, s->n, d.p, s->c->stream);
     s->c->launches++;
     TL_CUDA_TRY(cudaGetLastError());
     TL_CUDA_TRY(cudaMemcpyAsync(tour_out, d.p, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->c->stream));
@@ -336,9 +357,9 @@ tl_status tl_session_stats(tl_session *s, tl_stats *stats)
     st = close_timing(s);
     if (st != TL_OK) return st;
     memset(stats, 0, sizeof *stats);
-    stats->passes = s->h.scans;
+    stats->passes = s->algo == TL_ALGO_TWO_OPT_REF ? s->h.passes : s->h.scans;
     stats->moves = s->h.moves;
-    stats->evals = s->h.scans * s->pairs_per_scan;
+    stats->evals = stats->passes * s->pairs_per_scan;
     stats->launches = s->c->launches - s->launches0;
     stats->device_ms = s->device_ms;
     stats->converged = s->h.converged;

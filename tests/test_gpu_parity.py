@@ -218,3 +218,56 @@ def test_k2_rejects_bad_tours(T, ctx):
         p.local_search(T.ALGO_TWO_OPT_BEST, [0, 1, 2, 3, 4, 5, 6, 7, 8, 8])
     with pytest.raises(T.TeelineError):
         p.local_search(T.ALGO_TWO_OPT_BEST, [0, 1, 2, 3, 4, 5, 6, 7, 8, 10])
+
+
+# ---- K2 Mode R (reference-exact first improvement) -------------------------------------------
+
+def check_mode_r(T, ctx, x, y, start, max_moves=-1):
+    P = O.Problem(x, y)
+    want_t, want_st, want_mv = O.two_opt_ref(P, start, log_cap=1 << 16)
+    p = T.Problem.euc2d(ctx, x, y)
+    got_t, st, mv = p.local_search(T.ALGO_TWO_OPT_REF, start, log_cap=1 << 16)
+    assert [(m[1], m[2]) for m in mv] == [(m[1], m[2]) for m in want_mv]
+    assert [np.float32(m[0]) for m in mv] == [np.float32(m[0]) for m in want_mv]
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals)
+    assert st.converged == 1
+    return got_t, st
+
+
+def test_mode_r_goldens_G4_G5(T, ctx, berlin52):
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    p = T.Problem.euc2d(ctx, x, y)
+    t, st = check_mode_r(T, ctx, x, y, np.arange(52))
+    assert f5(p.tour_lengths(t)[0]) == "9368.31836"  # G4, docs/benchmarks.md:28
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (87, 5, 6125)
+    t, st = check_mode_r(T, ctx, x, y, O.nn_tour(P, 3))
+    assert f5(p.tour_lengths(t)[0]) == "8384.18848"  # G5, README.md:385
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (8, 3, 3675)
+
+
+def test_mode_r_tsp5_reference_unit_test(T, ctx):  # two_opt.rs:100-131
+    x, y = [0.0, 0.0, 0.0, 1.0, 1.0], [0.0, 0.5, 1.0, 1.0, 0.0]
+    p = T.Problem.euc2d(ctx, x, y)
+    t, st, _ = p.local_search(T.ALGO_TWO_OPT_REF, np.arange(5))
+    assert t.tolist() == [0, 1, 2, 3, 4] and p.tour_lengths(t)[0] == 4.0
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 9, 40, 300])
+def test_mode_r_small(T, ctx, n):
+    x, y = O.gen_uniform(n, 200 + n)
+    check_mode_r(T, ctx, x, y, O.shuffle_tour(n, n + 1))
+
+
+def test_mode_r_1k_matches_survey_probe(T, ctx):
+    x, y = O.gen_uniform(1000, 1000)
+    P = O.Problem(x, y)
+    t, st = check_mode_r(T, ctx, x, y, O.nn_tour(P, 3))
+    assert f5(O.tour_length(P, t)) == "25436.69336"
+    assert (int(st.passes), int(st.moves), int(st.evals)) == (6, 331, 2985018)
+
+
+def test_mode_r_1k_random_start(T, ctx):
+    x, y = O.gen_uniform(1000, 1000)
+    check_mode_r(T, ctx, x, y, O.shuffle_tour(1000, 5))
