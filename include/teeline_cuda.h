@@ -175,6 +175,9 @@ void tl_session_destroy(tl_session *s);
 tl_status tl_session_set_shard(tl_session *s, int32_t index, int32_t count);
 /* One full scan without applying: the best move (found=0 when none improves). */
 tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found);
+/* Launch the scan kernel `reps` times back to back (no apply) between two CUDA events on
+ * the context's stream and return the average launch duration: the roofline numerator. */
+tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms);
 /* Enqueue `steps` scan+apply iterations; does not synchronise. */
 tl_status tl_session_enqueue(tl_session *s, uint32_t steps);
 /* Run until the local optimum or max_moves, then synchronise. */

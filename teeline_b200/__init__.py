@@ -192,6 +192,12 @@ class Session:
         capi.check(self._lib.tl_session_scan(self.h, C.byref(mv), C.byref(found)))
         return mv.astuple() if found.value else None
 
+    def time_scans(self, reps: int) -> float:
+        """Average scan-kernel launch duration in ms (CUDA events on the context's stream)."""
+        out = C.c_double()
+        capi.check(self._lib.tl_session_time_scans(self.h, reps, C.byref(out)))
+        return out.value
+
     def enqueue(self, steps: int):
         capi.check(self._lib.tl_session_enqueue(self.h, steps))
 

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libteeline_cuda.so")
+LIB_PATH = os.environ.get("TL_LIB") or os.path.join(_HERE, "libteeline_cuda.so")  # TL_LIB: tuning builds only
 
 # enums (teeline_cuda.h)
 TL_OK = 0
@@ -29,7 +29,8 @@ EXPORTS = [
     "tl_problem_create_euc2d", "tl_problem_create_explicit", "tl_problem_destroy",
     "tl_dist_matrix_packed", "tl_dist_matrix_packed_i32", "tl_knn", "tl_nn_tour", "tl_tour_lengths",
     "tl_tour_lengths_i64", "tl_local_search", "tl_two_opt_batch", "tl_session_create",
-    "tl_session_destroy", "tl_session_set_shard", "tl_session_scan", "tl_session_enqueue",
+    "tl_session_destroy", "tl_session_set_shard", "tl_session_scan", "tl_session_time_scans",
+    "tl_session_enqueue",
     "tl_session_run", "tl_session_tour", "tl_session_stats", "tl_session_log", "tl_selftest_sqrt",
     "tl_microbench_fp32",
 ]
@@ -102,6 +103,7 @@ def load():
     L.tl_session_set_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     L.tl_session_scan.argtypes = [C.c_void_p, C.POINTER(Move), C.POINTER(C.c_int32)]
     L.tl_session_enqueue.argtypes = [C.c_void_p, C.c_uint32]
+    L.tl_session_time_scans.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_double)]
     L.tl_session_run.argtypes = [C.c_void_p, C.c_int64]
     L.tl_session_tour.argtypes = [C.c_void_p, C.c_void_p]
     L.tl_session_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]

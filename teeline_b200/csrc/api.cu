@@ -2,6 +2,7 @@
 // See include/teeline_cuda.h for the reference interface each entry point replaces.
 #include "host.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <string>
 
@@ -251,6 +252,51 @@ static tl_status matrix_packed_impl(tl_problem *p, void *out, bool want_int)
 
 tl_status tl_dist_matrix_packed(tl_problem *p, float *out) { return matrix_packed_impl(p, out, false); }
 tl_status tl_dist_matrix_packed_i32(tl_problem *p, int32_t *out) { return matrix_packed_impl(p, out, true); }
+
+// ---- k-NN and the nearest-neighbour constructor ----------------------------------------
+
+static int metric_id(const tl_problem *p) { return p->kind == PK_EUC_NINT ? 2 : (p->fast_sqrt ? 0 : 1); }
+
+tl_status tl_knn(tl_problem *p, uint32_t k, uint32_t *out)
+{
+    if (!p || !out) { set_error("tl_knn: null argument"); return TL_ERR_INVALID; }
+    if (k == 0) return TL_OK;
+    if (k > 32) { set_error("tl_knn: k = %u > 32 is not supported", k); return TL_ERR_UNSUPPORTED; }
+    tl_ctx *c = p->ctx;
+    DeviceGuard g(c->device);
+    DevBuf<uint32_t> d;
+    if (d.alloc((size_t)p->n * k) != cudaSuccess) { set_error("tl_knn: device allocation failed"); return TL_ERR_NOMEM; }
+    launch_knn(p->d_xy, p->d_tri, p->n, k, metric_id(p), d.p, c->stream);
+    c->launches++;
+    TL_CUDA_TRY(cudaGetLastError());
+    TL_CUDA_TRY(cudaMemcpyAsync(out, d.p, (size_t)p->n * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TL_OK;
+}
+
+tl_status tl_nn_tour(tl_problem *p, uint32_t k, uint32_t *tour_out)
+{
+    // k only changes which candidates the reference looks at first; with its buffer rule the
+    // chosen city is the nearest unvisited one (ties to the lower position) for every k.
+    (void)k;
+    if (!p || !tour_out) { set_error("tl_nn_tour: null argument"); return TL_ERR_INVALID; }
+    tl_ctx *c = p->ctx;
+    DeviceGuard g(c->device);
+    if (nn_tour_smem_bytes(p->n) > 200 * 1024) { set_error("tl_nn_tour: n = %u too large for the visited bitmap", p->n); return TL_ERR_UNSUPPORTED; }
+    const uint32_t kk = std::min<uint32_t>(32, p->n - 1);
+    DevBuf<uint32_t> d_knn, d_tour;
+    if (d_knn.alloc((size_t)p->n * kk) != cudaSuccess || d_tour.alloc(p->n) != cudaSuccess) {
+        set_error("tl_nn_tour: device allocation failed");
+        return TL_ERR_NOMEM;
+    }
+    launch_knn(p->d_xy, p->d_tri, p->n, kk, metric_id(p), d_knn.p, c->stream);
+    launch_nn_tour(p->d_xy, p->d_tri, p->n, d_knn.p, kk, metric_id(p), d_tour.p, c->stream);
+    c->launches += 2;
+    TL_CUDA_TRY(cudaGetLastError());
+    TL_CUDA_TRY(cudaMemcpyAsync(tour_out, d_tour.p, (size_t)p->n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TL_OK;
+}
 
 // ---- tour lengths --------------------------------------------------------------------
 

@@ -25,6 +25,8 @@
 
 #include <math_constants.h>
 
+#include <type_traits>
+
 namespace tl {
 
 namespace {
@@ -36,6 +38,15 @@ constexpr int WARPS = kScanWarps;
 constexpr int ROWS_CAP = TI + 1;       // positions i0 .. i0+cnt
 constexpr int COLS_CAP = TI + BW + 1;  // positions i0+K0 .. i0+K0+cnt+BW
 constexpr int WARP_PTS = ROWS_CAP + COLS_CAP;
+
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (N > 0) {
+        static_for<N - 1>(f);
+        f(std::integral_constant<int, N - 1>{});
+    }
+}
 
 __device__ __forceinline__ int find_band(const int32_t *__restrict__ band_first, int nbands, int item)
 {
@@ -51,10 +62,11 @@ __device__ __forceinline__ int find_band(const int32_t *__restrict__ band_first,
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(WARPS * 32, 2)
-    two_opt_scan_recompute_kernel(const Pt *__restrict__ pts, const ScanGeom g,
+__global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
+    two_opt_scan_recompute_kernel(Pt *__restrict__ pts, const ScanGeom g,
                                   const int32_t *__restrict__ band_first, BestF *__restrict__ blockbest,
-                                  const DevState *__restrict__ state)
+                                  DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
+                                  uint64_t log_cap, int fuse_apply)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (state->done) return;
@@ -83,8 +95,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         const int r_end = min(r_begin + g.chunk, H);
         const int lane_k0 = K0 + lane * R; // first diagonal of this lane
 
-        for (int i0 = r_begin; i0 < r_end; i0 += TI) {
-            const int cnt = min(TI, r_end - i0);
+        // even tiles of at most TI rows
+        const int ntiles = (r_end - r_begin + TI - 1) / TI;
+        const int tile_rows = ntiles > 0 ? (r_end - r_begin + ntiles - 1) / ntiles : 0;
+        for (int i0 = r_begin; i0 < r_end; i0 += tile_rows) {
+            const int cnt = min(tile_rows, r_end - i0);
             __syncwarp(); // everyone is done with the previous tile's smem
             if (lane == 0) {
                 const uint32_t rb = (uint32_t)(cnt + 1) * sizeof(Pt);
@@ -112,47 +127,55 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
                 }
             }
 
-#pragma unroll 1
-            for (int t = 0; t < cnt; t += R) {
+            // One row step for compile-time window phase U (the register window is rotated by
+            // unrolling R steps, so no data ever moves between registers).
+            auto step = [&](auto Uc, int tau) {
+                constexpr int U = decltype(Uc)::value;
+                const Pt rp = srow[tau + 1];                // (x,y) of i+1 and s_i, warp broadcast
+                const Pt nx = scol[tau + lane * R + R + 1]; // next window point
+                float dl[R];
 #pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    if (t + u < cnt) { // warp-uniform
-                        const int tau = t + u;
-                        const Pt rp = srow[tau + 1];                 // (x,y) of i+1 and s_i, broadcast
-                        const Pt nx = scol[tau + lane * R + R + 1];  // next window point
-                        float dl[R];
+                for (int r = 0; r < R; ++r) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int ph = (r + U) % R;
+                    const float en = dist_f32<FAST>(rp.x, rp.y, wx[ph], wy[ph]);
+                    const float cur = __fadd_rn(rp.sp, ws[ph]);
+                    const float nw = __fadd_rn(E[r], en);
+                    dl[r] = __fsub_rn(nw, cur);
+                    E[r] = en;
+                }
+                float m = dl[0];
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const int ph = (r + u) % R;
-                            const float en = dist_f32<FAST>(rp.x, rp.y, wx[ph], wy[ph]);
-                            const float cur = __fadd_rn(rp.sp, ws[ph]);
-                            const float nw = __fadd_rn(E[r], en);
-                            dl[r] = __fsub_rn(nw, cur);
-                            E[r] = en;
+                for (int r = 1; r < R; ++r) m = fminf(m, dl[r]);
+                if (m < best) { // rare: an improving move better than this thread's best
+                    const uint32_t i = (uint32_t)(i0 + tau);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t j = i + (uint32_t)(lane_k0 + r);
+                        // the cyclic neighbourhood excludes (0, n-1): both edges share p_0
+                        const bool excluded = g.cyclic && i == 0 && j == (uint32_t)(g.n - 1);
+                        if (dl[r] < best && !excluded) {
+                            best = dl[r];
+                            bi = i;
+                            bj = j;
                         }
-                        float m = dl[0];
-#pragma unroll
-                        for (int r = 1; r < R; ++r) m = fminf(m, dl[r]);
-                        if (m < best) { // rare: an improving move better than this thread's best
-                            const uint32_t i = (uint32_t)(i0 + tau);
-#pragma unroll
-                            for (int r = 0; r < R; ++r) {
-                                const uint32_t j = i + (uint32_t)(lane_k0 + r);
-                                // the cyclic neighbourhood excludes (0, n-1): both edges share p_0
-                                const bool excluded = g.cyclic && i == 0 && j == (uint32_t)(g.n - 1);
-                                if (dl[r] < best && !excluded) {
-                                    best = dl[r];
-                                    bi = i;
-                                    bj = j;
-                                }
-                            }
-                        }
-                        wx[u] = nx.x;
-                        wy[u] = nx.y;
-                        ws[u] = nx.sp;
                     }
                 }
+                wx[U] = nx.x;
+                wy[U] = nx.y;
+                ws[U] = nx.sp;
+            };
+
+            int t = 0;
+#pragma unroll 1
+            for (; t + R <= cnt; t += R) { // full groups: straight-line code, no per-step predicate
+                static_for<R>([&](auto Uc) { step(Uc, t + decltype(Uc)::value); });
             }
+            // tail: fewer than R rows left; the window phase restarts at 0 after a full group
+            static_for<R>([&](auto Uc) {
+                if (t + decltype(Uc)::value < cnt) step(Uc, t + decltype(Uc)::value);
+            });
         }
     }
 
@@ -164,6 +187,42 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         BestF v = (lane < WARPS) ? red[lane] : BestF{0.0f, 0xffffffffu, 0xffffffffu, 0u};
         warp_argmin_2opt(v.delta, v.i, v.j);
         if (lane == 0) blockbest[blockIdx.x] = v;
+    }
+    if (!fuse_apply) return;
+
+    // Fused step tail (single-GPU sessions): the last CTA to finish reduces the per-CTA records,
+    // reverses the segment in place and updates the loop state, saving a kernel launch per step.
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    BestF v{0.0f, 0xffffffffu, 0xffffffffu, 0u};
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+        // L2 read: the records were written by other CTAs of this launch
+        const float4 raw = __ldcg(reinterpret_cast<const float4 *>(blockbest) + c);
+        const BestF o{raw.x, __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    warp_argmin_2opt(v.delta, v.i, v.j);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    v = red[0];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) {
+        const BestF o = red[w];
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    const bool found = v.i != 0xffffffffu;
+    if (found) reverse_segment_inplace<FAST>(pts, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        finish_best_step(state, found, v.delta, v.i, v.j, log, log_cap);
     }
 }
 
@@ -226,7 +285,9 @@ __global__ void __launch_bounds__(256)
     const bool found = v.i != 0xffffffffu;
     const uint32_t mi = v.i, mj = v.j;
 
-    if (found) reverse_segment_inplace<FAST>(pts, mi, mj, nullptr);
+    if (found)
+        reverse_segment_inplace<FAST>(pts, mi, mj, nullptr, blockIdx.x * blockDim.x + threadIdx.x,
+                                      gridDim.x * blockDim.x);
 
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -234,16 +295,7 @@ __global__ void __launch_bounds__(256)
         const unsigned int tk = atomicAdd(ticket, 1u);
         if (tk == gridDim.x - 1) { // last block: everyone has read `state` by now
             *ticket = 0u;
-            state->scans += 1;
-            if (found) {
-                const unsigned long long m = state->moves;
-                if (log && m < log_cap) log[m] = tl_move{v.delta, mi, mj, 0, 0, 0};
-                state->moves = m + 1;
-                if (state->max_moves >= 0 && (long long)(m + 1) >= state->max_moves) state->done = 1;
-            } else {
-                state->done = 1;
-                state->converged = 1;
-            }
+            finish_best_step(state, found, v.delta, mi, mj, log, log_cap);
             __threadfence();
         }
     }
@@ -273,14 +325,17 @@ cudaError_t scan_recompute_configure()
                                 (int)scan_recompute_smem_bytes());
 }
 
-void launch_scan_recompute(const Pt *pts, const ScanGeom &g, const int32_t *band_first, BestF *blockbest,
-                           const DevState *state, int grid, bool fast, cudaStream_t st)
+void launch_scan_recompute(Pt *pts, const ScanGeom &g, const int32_t *band_first, BestF *blockbest,
+                           DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap,
+                           bool fuse_apply, int grid, bool fast, cudaStream_t st)
 {
     const size_t smem = scan_recompute_smem_bytes();
     if (fast)
-        two_opt_scan_recompute_kernel<true><<<grid, WARPS * 32, smem, st>>>(pts, g, band_first, blockbest, state);
+        two_opt_scan_recompute_kernel<true><<<grid, WARPS * 32, smem, st>>>(pts, g, band_first, blockbest, state,
+                                                                          ticket, log, log_cap, fuse_apply);
     else
-        two_opt_scan_recompute_kernel<false><<<grid, WARPS * 32, smem, st>>>(pts, g, band_first, blockbest, state);
+        two_opt_scan_recompute_kernel<false><<<grid, WARPS * 32, smem, st>>>(pts, g, band_first, blockbest, state,
+                                                                           ticket, log, log_cap, fuse_apply);
 }
 
 void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic,

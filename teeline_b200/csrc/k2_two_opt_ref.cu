@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(256)
     const bool found = key != kNoKey;
     const uint32_t mi = (uint32_t)(key >> 32), mj = (uint32_t)key;
     const int32_t ci = state->cur_i, W = state->window_rows;
-    if (found) reverse_segment_inplace<FAST>(pts, mi, mj, &state->last_delta);
+    if (found)
+        reverse_segment_inplace<FAST>(pts, mi, mj, &state->last_delta, blockIdx.x * blockDim.x + threadIdx.x,
+                                      gridDim.x * blockDim.x);
 
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -66,14 +66,25 @@ void launch_k1_square_from_packed(const uint32_t *tri, const int32_t *slot_city,
 cudaError_t configure_all_kernels();
 
 // K2 recompute path
-constexpr int kScanR = 9;              // diagonals per lane (odd => conflict-free 128-bit LDS)
-constexpr int kScanBW = 32 * kScanR;   // diagonals per band
-constexpr int kScanTI = 64;            // rows per staged tile
-constexpr int kScanWarps = 8;          // warps per CTA
+#ifndef TL_SCAN_R
+#define TL_SCAN_R 7
+#endif
+#ifndef TL_SCAN_TI
+#define TL_SCAN_TI 128
+#endif
+#ifndef TL_SCAN_MINB
+#define TL_SCAN_MINB 3
+#endif
+constexpr int kScanR = TL_SCAN_R;       // diagonals per lane (odd => conflict-free 128-bit LDS)
+constexpr int kScanBW = 32 * kScanR;    // diagonals per band
+constexpr int kScanTI = TL_SCAN_TI;     // max rows per staged tile
+constexpr int kScanWarps = 8;           // warps per CTA
+constexpr int kScanMinBlocks = TL_SCAN_MINB; // resident CTAs per SM the kernel is compiled for
 size_t scan_recompute_smem_bytes();
 cudaError_t scan_recompute_configure();
-void launch_scan_recompute(const Pt *pts, const ScanGeom &g, const int32_t *band_first, BestF *blockbest,
-                           const DevState *state, int grid, bool fast, cudaStream_t st);
+void launch_scan_recompute(Pt *pts, const ScanGeom &g, const int32_t *band_first, BestF *blockbest,
+                           DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap,
+                           bool fuse_apply, int grid, bool fast, cudaStream_t st);
 void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic,
                       bool fast, Pt *pts, cudaStream_t st);
 void launch_apply_two_opt_recompute(Pt *pts, bool fast, const BestF *cand, int ncand, DevState *state,
@@ -86,6 +97,14 @@ constexpr int kRefWindow0 = 8; // rows scanned per launch right after a hit
 void launch_find_first(const Pt *pts, uint32_t n, DevState *state, int grid, bool fast, cudaStream_t st);
 void launch_apply_first(Pt *pts, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
                         uint64_t log_cap, int grid, bool fast, cudaStream_t st);
+
+// K5 / N1
+void launch_knn(const float2 *xy, const float *tri, uint32_t n, uint32_t k, int metric_id, uint32_t *out,
+                cudaStream_t st);
+size_t nn_tour_smem_bytes(uint32_t n);
+cudaError_t nn_tour_configure();
+void launch_nn_tour(const float2 *xy, const float *tri, uint32_t n, const uint32_t *knn, uint32_t kk,
+                    int metric_id, uint32_t *tour, cudaStream_t st);
 
 // K4
 void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, const uint32_t *tours,

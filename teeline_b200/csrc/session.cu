@@ -12,7 +12,12 @@ using namespace tl;
 
 namespace tl {
 
-cudaError_t configure_all_kernels() { return scan_recompute_configure(); }
+cudaError_t configure_all_kernels()
+{
+    cudaError_t e = scan_recompute_configure();
+    if (e == cudaSuccess) e = nn_tour_configure();
+    return e;
+}
 
 } // namespace tl
 
@@ -62,9 +67,9 @@ void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
     g.kmax = n - 2;
     g.nbands = (g.kmax - 2) / kScanBW + 1;
     auto H = [&](int b) { return g.jmax - (2 + b * kScanBW) + 1; };
-    // one work item per resident warp (2 CTAs/SM x 8 warps), times the shard count so that
+    // one work item per resident warp (kScanMinBlocks CTAs/SM x 8 warps), times the shard count so that
     // every rank of a sharded scan still fills its GPU
-    const int64_t target = (int64_t)s->c->sm_count * 2 * kScanWarps * s->shard_count;
+    const int64_t target = (int64_t)s->c->sm_count * kScanMinBlocks * kScanWarps * s->shard_count;
     auto items_for = [&](int chunk) {
         int64_t t = 0;
         for (int b = 0; b < g.nbands; ++b) t += (H(b) + chunk - 1) / chunk;
@@ -87,7 +92,7 @@ void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
     g.item_end = (int32_t)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
     // same grid on every rank so the all-gather is symmetric
     const int64_t blocks = (per + kScanWarps - 1) / kScanWarps;
-    s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * 2));
+    s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * kScanMinBlocks));
 }
 
 tl_status upload_geometry(tl_session *s)
@@ -115,11 +120,12 @@ tl_status pull_state(tl_session *s)
     return TL_OK;
 }
 
-tl_status launch_scan(tl_session *s)
+// fuse: let the scan kernel's last CTA apply the move (single-GPU stepping only)
+tl_status launch_scan(tl_session *s, bool fuse)
 {
     BestF *mine = s->cand.p + (size_t)s->shard_index * s->grid;
-    launch_scan_recompute(s->pts.p, s->geom, s->band_first.p, mine, s->state.p, s->grid,
-                          s->p->fast_sqrt, s->c->stream);
+    launch_scan_recompute(s->pts.p, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p,
+                          s->log_cap, fuse && s->shard_count == 1, s->grid, s->p->fast_sqrt, s->c->stream);
     s->c->launches++;
     if (s->shard_count > 1) {
         if (!s->c->nccl_comm) { set_error("sharded session needs tl_ctx_attach_nccl first"); return TL_ERR_NCCL; }
@@ -152,8 +158,9 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
         return TL_OK;
     }
     for (uint32_t k = 0; k < steps; ++k) {
-        tl_status st = launch_scan(s);
+        tl_status st = launch_scan(s, true);
         if (st != TL_OK) return st;
+        if (s->shard_count == 1) continue; // the scan kernel's last CTA applied the move
         launch_apply_two_opt_recompute(s->pts.p, s->p->fast_sqrt, s->cand.p, s->grid * s->shard_count,
                                        s->state.p, s->ticket.p, s->log.p, s->log_cap, apply_grid,
                                        s->c->stream);
@@ -286,7 +293,7 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
     // a scan of a finished session is still a scan: lift the no-op flag for this launch
     const int was_done = s->h.done;
     if (was_done) { s->h.done = 0; tl_status st = push_state(s); if (st != TL_OK) return st; }
-    tl_status st = launch_scan(s);
+    tl_status st = launch_scan(s, false);
     if (st != TL_OK) return st;
     TL_CUDA_TRY(cudaGetLastError());
     std::vector<BestF> hc((size_t)s->grid * s->shard_count);
@@ -301,6 +308,38 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
         if (best) *best = tl_move{v.delta, v.i, v.j, 0, 0, 0};
     }
     return TL_OK;
+}
+
+tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
+{
+    if (!s || !avg_ms || reps == 0) { set_error("tl_session_time_scans: bad arguments"); return TL_ERR_INVALID; }
+    if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_time_scans: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
+    *avg_ms = 0.0;
+    if (s->trivial) return TL_OK;
+    DeviceGuard g(s->c->device);
+    tl_status st = pull_state(s);
+    if (st != TL_OK) return st;
+    const int was_done = s->h.done;
+    if (was_done) { s->h.done = 0; st = push_state(s); if (st != TL_OK) return st; }
+    cudaEvent_t a, b;
+    TL_CUDA_TRY(cudaEventCreate(&a));
+    TL_CUDA_TRY(cudaEventCreate(&b));
+    st = launch_scan(s, false); // warm
+    if (st == TL_OK) {
+        cudaEventRecord(a, s->c->stream);
+        for (uint32_t r = 0; r < reps && st == TL_OK; ++r) st = launch_scan(s, false);
+        cudaEventRecord(b, s->c->stream);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        *avg_ms = (double)ms / reps;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (st != TL_OK) return st;
+    TL_CUDA_TRY(cudaGetLastError());
+    if (was_done) { s->h.done = was_done; st = push_state(s); }
+    return st;
 }
 
 tl_status tl_session_enqueue(tl_session *s, uint32_t steps)
@@ -412,8 +451,6 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
 
 // ---- not built yet -----------------------------------------------------------------
 
-tl_status tl_knn(tl_problem *, uint32_t, uint32_t *) { set_error("tl_knn: not built yet"); return TL_ERR_UNSUPPORTED; }
-tl_status tl_nn_tour(tl_problem *, uint32_t, uint32_t *) { set_error("tl_nn_tour: not built yet"); return TL_ERR_UNSUPPORTED; }
 tl_status tl_two_opt_batch(tl_problem *, int32_t, uint32_t *, size_t, int64_t, tl_stats *, float *)
 {
     set_error("tl_two_opt_batch: not built yet");

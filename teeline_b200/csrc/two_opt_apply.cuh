@@ -14,11 +14,11 @@ namespace tl {
 // (d(p_i,p_j) + d(p_i+1,p_j+1)) - (d(p_i,p_i+1) + d(p_j,p_j+1)) there.
 template <bool FAST>
 __device__ __forceinline__ void reverse_segment_inplace(Pt *__restrict__ pts, uint32_t mi, uint32_t mj,
-                                                        float *delta_out)
+                                                        float *delta_out, uint32_t tid, uint32_t nthreads)
 {
     const uint32_t L = mj - mi; // segment mi+1 .. mj, L >= 2
     const uint32_t nxy = L / 2, nsp = (L - 1) / 2;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nxy; t += gridDim.x * blockDim.x) {
+    for (uint32_t t = tid; t < nxy; t += nthreads) {
         const uint32_t a = mi + 1 + t, b = mj - t;
         const Pt A = pts[a], B = pts[b];
         if (t == 0) {
@@ -41,6 +41,22 @@ __device__ __forceinline__ void reverse_segment_inplace(Pt *__restrict__ pts, ui
             pts[a2].sp = B.sp;
             pts[b].sp = sa;
         }
+    }
+}
+
+// Loop-state update after a Mode B step (one thread).
+__device__ __forceinline__ void finish_best_step(DevState *state, bool found, float delta, uint32_t mi,
+                                                 uint32_t mj, tl_move *__restrict__ log, uint64_t log_cap)
+{
+    state->scans += 1;
+    if (found) {
+        const unsigned long long m = state->moves;
+        if (log && m < log_cap) log[m] = tl_move{delta, mi, mj, 0, 0, 0};
+        state->moves = m + 1;
+        if (state->max_moves >= 0 && (long long)(m + 1) >= state->max_moves) state->done = 1;
+    } else {
+        state->done = 1;
+        state->converged = 1;
     }
 }
 

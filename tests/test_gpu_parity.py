@@ -271,3 +271,63 @@ def test_mode_r_1k_matches_survey_probe(T, ctx):
 def test_mode_r_1k_random_start(T, ctx):
     x, y = O.gen_uniform(1000, 1000)
     check_mode_r(T, ctx, x, y, O.shuffle_tour(1000, 5))
+
+
+# ---- K5 k-NN and the nearest-neighbour constructor ---------------------------------------------
+
+def test_knn_reference_ordered_vector(T, ctx):  # tests/test_kdtree_and_distance_matrix.rs:199-243
+    p = T.Problem.euc2d(ctx, [0.0, 1.0, 2.0, 3.0, 10.0, 0.0], [0.0, 0.0, 0.0, 0.0, 0.0, 5.0])
+    want = [1, 2, 3, 5, 4]
+    for k in range(1, 6):
+        assert p.knn(k)[0].tolist() == want[:k]
+    assert p.knn(7)[0].tolist() == want + [0xFFFFFFFF] * 2
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 8, 12, 32])
+def test_knn_matches_oracle(T, ctx, att532, k):
+    _, x, y = att532
+    got = T.Problem.euc2d(ctx, x, y).knn(k).astype(np.int64)
+    assert (got == O.knn(O.Problem(x, y), k)).all()
+
+
+def test_knn_ties_lower_position_first(T, ctx):
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 9, 700).astype(np.float32)
+    y = rng.integers(0, 9, 700).astype(np.float32)  # heavy ties and duplicates
+    got = T.Problem.euc2d(ctx, x, y).knn(5).astype(np.int64)
+    assert (got == O.knn(O.Problem(x, y), 5)).all()
+
+
+def test_knn_explicit_and_nint(T, ctx, berlin52):
+    _, x, y = berlin52
+    tri = O.matrix_packed_f32(x, y)
+    got = T.Problem.explicit(ctx, tri, 52).knn(5).astype(np.int64)
+    assert (got == O.knn(O.Problem(tri=tri, n=52), 5)).all()
+    gx, gy = O.gen_grid(800, 800)
+    got = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32).knn(5).astype(np.int64)
+    assert (got == O.knn(O.Problem(tri=O.matrix_packed_nint(gx, gy), n=800), 5)).all()
+
+
+def test_nn_tour_goldens_G1_G2(T, ctx, berlin52, att532):
+    for (_, x, y), want in ((berlin52, "8980.91797"), (att532, "112099.42188")):
+        p = T.Problem.euc2d(ctx, x, y)
+        t = p.nn_tour(3)
+        assert (t.astype(np.int64) == O.nn_tour(O.Problem(x, y), 3)).all()
+        assert f5(p.tour_lengths(t)[0]) == want
+
+
+@pytest.mark.parametrize("n", [2, 3, 33, 1000, 10000])
+def test_nn_tour_matches_oracle(T, ctx, n):
+    x, y = O.gen_uniform(n, n)
+    t = T.Problem.euc2d(ctx, x, y).nn_tour(3)
+    assert (t.astype(np.int64) == O.nn_tour(O.Problem(x, y), 3)).all()
+
+
+def test_nn_tour_explicit_and_nint(T, ctx, berlin52):
+    _, x, y = berlin52
+    tri = O.matrix_packed_f32(x, y)
+    t = T.Problem.explicit(ctx, tri, 52).nn_tour(3)
+    assert (t.astype(np.int64) == O.nn_tour(O.Problem(tri=tri, n=52), 3)).all()
+    gx, gy = O.gen_grid(700, 7)
+    t = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32).nn_tour(3)
+    assert (t.astype(np.int64) == O.nn_tour(O.Problem(tri=O.matrix_packed_nint(gx, gy), n=700), 3)).all()
