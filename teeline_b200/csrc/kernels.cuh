@@ -98,6 +98,20 @@ void launch_find_first(const Pt *pts, uint32_t n, DevState *state, int grid, boo
 void launch_apply_first(Pt *pts, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
                         uint64_t log_cap, int grid, bool fast, cudaStream_t st);
 
+// K3 Or-opt (recompute path)
+constexpr int kOrR = 8;          // columns per lane
+constexpr int kOrTI = 96;        // max rows per staged tile
+constexpr int kOrWarps = 8;
+constexpr int kOrMinBlocks = 2;
+size_t or_scan_smem_bytes();
+cudaError_t or_scan_configure();
+void launch_or_rowinfo(const Pt *pts, uint32_t n, uint32_t npad, float4 *info, const DevState *state, bool fast,
+                       cudaStream_t st);
+void launch_or_scan(const Pt *pts, const float4 *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
+                    int item_end, BestF *blockbest, const DevState *state, int grid, bool fast, cudaStream_t st);
+void launch_or_apply(Pt *pts, Pt *tmp, uint32_t n, const BestF *cand, int ncand, DevState *state,
+                     unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid, bool fast, cudaStream_t st);
+
 // K5 / N1
 void launch_knn(const float2 *xy, const float *tri, uint32_t n, uint32_t k, int metric_id, uint32_t *out,
                 cudaStream_t st);

@@ -16,6 +16,7 @@ cudaError_t configure_all_kernels()
 {
     cudaError_t e = scan_recompute_configure();
     if (e == cudaSuccess) e = nn_tour_configure();
+    if (e == cudaSuccess) e = or_scan_configure();
     return e;
 }
 
@@ -33,6 +34,9 @@ struct tl_session {
     // recompute-path state
     uint32_t npad = 0;
     DevBuf<Pt> pts; // tour-ordered point records, updated in place by the apply kernel
+    DevBuf<Pt> tmp;          // Or-opt: relocated range staging
+    DevBuf<float4> rowinfo;  // Or-opt: per-row removal gains
+    int or_chunk = 0, or_items_per_cb = 0, or_item_begin = 0, or_item_end = 0;
 
     ScanGeom geom{};
     DevBuf<int32_t> band_first;
@@ -95,8 +99,31 @@ void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
     s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * kScanMinBlocks));
 }
 
+// Or-opt work decomposition: column blocks of 32*kOrR insertion edges x row chunks.
+void build_or_geometry(tl_session *s)
+{
+    const int n = (int)s->n;
+    const int cw = 32 * kOrR;
+    const int ncb = (n + cw - 1) / cw;
+    const int64_t target = (int64_t)s->c->sm_count * kOrMinBlocks * kOrWarps * s->shard_count;
+    const int per_cb = (int)std::max<int64_t>(1, target / ncb);
+    s->or_chunk = std::max(8, (n + per_cb - 1) / per_cb);
+    s->or_items_per_cb = (n + s->or_chunk - 1) / s->or_chunk;
+    s->nitems = ncb * s->or_items_per_cb;
+    const int64_t per = ((int64_t)s->nitems + s->shard_count - 1) / s->shard_count;
+    s->or_item_begin = (int)std::min<int64_t>(s->nitems, per * s->shard_index);
+    s->or_item_end = (int)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
+    const int64_t blocks = (per + kOrWarps - 1) / kOrWarps;
+    s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * kOrMinBlocks));
+}
+
 tl_status upload_geometry(tl_session *s)
 {
+    if (s->algo == TL_ALGO_OR_OPT) {
+        build_or_geometry(s);
+        TL_CUDA_TRY(s->cand.alloc((size_t)s->grid * s->shard_count));
+        return TL_OK;
+    }
     std::vector<int32_t> bf;
     build_geometry(s, bf);
     TL_CUDA_TRY(s->band_first.alloc(bf.size()));
@@ -124,9 +151,15 @@ tl_status pull_state(tl_session *s)
 tl_status launch_scan(tl_session *s, bool fuse)
 {
     BestF *mine = s->cand.p + (size_t)s->shard_index * s->grid;
+    if (s->algo == TL_ALGO_OR_OPT) {
+        launch_or_rowinfo(s->pts.p, s->n, s->npad, s->rowinfo.p, s->state.p, s->p->fast_sqrt, s->c->stream);
+        launch_or_scan(s->pts.p, s->rowinfo.p, s->n, s->or_chunk, s->or_items_per_cb, s->or_item_begin,
+                       s->or_item_end, mine, s->state.p, s->grid, s->p->fast_sqrt, s->c->stream);
+        s->c->launches += 2;
+    } else
     launch_scan_recompute(s->pts.p, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p,
                           s->log_cap, fuse && s->shard_count == 1, s->grid, s->p->fast_sqrt, s->c->stream);
-    s->c->launches++;
+    if (s->algo != TL_ALGO_OR_OPT) s->c->launches++;
     if (s->shard_count > 1) {
         if (!s->c->nccl_comm) { set_error("sharded session needs tl_ctx_attach_nccl first"); return TL_ERR_NCCL; }
         // in-place all-gather: every rank contributes its `grid` block records
@@ -160,6 +193,12 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
     for (uint32_t k = 0; k < steps; ++k) {
         tl_status st = launch_scan(s, true);
         if (st != TL_OK) return st;
+        if (s->algo == TL_ALGO_OR_OPT) {
+            launch_or_apply(s->pts.p, s->tmp.p, s->n, s->cand.p, s->grid * s->shard_count, s->state.p,
+                            s->ticket.p, s->log.p, s->log_cap, apply_grid, s->p->fast_sqrt, s->c->stream);
+            s->c->launches += 2;
+            continue;
+        }
         if (s->shard_count == 1) continue; // the scan kernel's last CTA applied the move
         launch_apply_two_opt_recompute(s->pts.p, s->p->fast_sqrt, s->cand.p, s->grid * s->shard_count,
                                        s->state.p, s->ticket.p, s->log.p, s->log_cap, apply_grid,
@@ -190,7 +229,8 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
 {
     if (!p || !tour || !out) { set_error("tl_session_create: null argument"); return TL_ERR_INVALID; }
     *out = nullptr;
-    if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC && algo != TL_ALGO_TWO_OPT_REF) {
+    if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC && algo != TL_ALGO_TWO_OPT_REF &&
+        algo != TL_ALGO_OR_OPT) {
         set_error("tl_session_create: algo %d not available in this build", algo);
         return TL_ERR_UNSUPPORTED;
     }
@@ -209,14 +249,20 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     s->c = c;
     s->algo = algo;
     s->n = p->n;
-    s->cyclic = algo == TL_ALGO_TWO_OPT_BEST_CYCLIC;
+    s->cyclic = algo == TL_ALGO_TWO_OPT_BEST_CYCLIC || algo == TL_ALGO_OR_OPT;
     s->trivial = p->n < 4;
     s->launches0 = c->launches;
     s->log_cap = 1u << 16;
     const uint64_t n = p->n;
     s->pairs_per_scan = s->trivial ? 0 : (s->cyclic ? n * (n - 3) / 2 : (n - 3) * (n - 2) / 2);
+    if (algo == TL_ALGO_OR_OPT && !s->trivial) {
+        // candidates per find_best_move: sum over s of (n-s+1)(n-s-1), doubled for s > 1 (fwd + rev)
+        s->pairs_per_scan = 0;
+        for (uint64_t sg = 1; sg <= 3; ++sg)
+            if (n > sg + 1) s->pairs_per_scan += (n - sg + 1) * (n - sg - 1) * (sg > 1 ? 2 : 1);
+    }
     // pad so that every staged window [i0+K0, i0+K0+TI+BW] of a valid row stays in bounds
-    s->npad = p->n + kScanBW + kScanTI + 64;
+    s->npad = p->n + std::max(kScanBW + kScanTI, 32 * kOrR + kOrR) + 64;
 
     auto fail = [&](tl_status st) {
         tl_session_destroy(s);
@@ -229,6 +275,17 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         set_error("tl_session_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(TL_ERR_NOMEM);
+    }
+    if (algo == TL_ALGO_OR_OPT && (s->tmp.alloc(s->npad) != cudaSuccess || s->rowinfo.alloc(s->npad) != cudaSuccess)) {
+        set_error("tl_session_create: device allocation failed");
+        return fail(TL_ERR_NOMEM);
+    }
+    // or_opt::solve ignores the seed and returns identity order when n < 4 (or_opt.rs:31-34)
+    std::vector<uint32_t> ident;
+    if (algo == TL_ALGO_OR_OPT && s->trivial) {
+        ident.resize(p->n);
+        for (uint32_t k = 0; k < p->n; ++k) ident[k] = k;
+        tour = ident.data();
     }
     cudaError_t e = cudaMemcpyAsync(d_tour.p, tour, (size_t)p->n * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->ticket.p, 0, 4, c->stream);
@@ -246,7 +303,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         // loop runs one empty pass for n == 3 and is skipped for n < 3 (two_opt.rs:17,29 underflow)
         s->h.done = 1;
         s->h.converged = 1;
-        s->h.scans = 1;
+        s->h.scans = algo == TL_ALGO_OR_OPT ? 0 : 1;
         s->h.passes = (p->n == 3) ? 1 : 0;
     }
     tl_status st = push_state(s); // also waits for d_tour's consumers
@@ -301,6 +358,23 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
     TL_CUDA_TRY(cudaStreamSynchronize(s->c->stream));
     if (was_done) { s->h.done = was_done; st = push_state(s); if (st != TL_OK) return st; }
     BestF v{0.0f, 0xffffffffu, 0xffffffffu, 0u};
+    if (s->algo == TL_ALGO_OR_OPT) {
+        auto rank_less = [](const BestF &a, const BestF &b) {
+            if ((a.aux >> 1) != (b.aux >> 1)) return (a.aux >> 1) < (b.aux >> 1);
+            if (a.i != b.i) return a.i < b.i;
+            if (a.j != b.j) return a.j < b.j;
+            return (a.aux & 1u) < (b.aux & 1u);
+        };
+        for (const BestF &o : hc) {
+            if (o.i == 0xffffffffu) continue;
+            if (v.i == 0xffffffffu || o.delta < v.delta || (o.delta == v.delta && rank_less(o, v))) v = o;
+        }
+        if (v.i != 0xffffffffu) {
+            *found = 1;
+            if (best) *best = tl_move{v.delta, v.i, v.j, (uint8_t)((v.aux >> 1) + 1), (uint8_t)(v.aux & 1u), 0};
+        }
+        return TL_OK;
+    }
     for (const BestF &o : hc)
         if (o.delta < v.delta || (o.delta == v.delta && (o.i < v.i || (o.i == v.i && o.j < v.j)))) v = o;
     if (v.i != 0xffffffffu) {

@@ -331,3 +331,73 @@ def test_nn_tour_explicit_and_nint(T, ctx, berlin52):
     gx, gy = O.gen_grid(700, 7)
     t = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32).nn_tour(3)
     assert (t.astype(np.int64) == O.nn_tour(O.Problem(tri=O.matrix_packed_nint(gx, gy), n=700), 3)).all()
+
+
+# ---- K3 Or-opt -------------------------------------------------------------------------------------
+
+def check_or_opt(T, ctx, x, y, start, max_moves=-1):
+    P = O.Problem(x, y)
+    want_t, want_st, want_mv = O.or_opt(P, start, max_moves=max_moves, log_cap=1 << 16)
+    p = T.Problem.euc2d(ctx, x, y)
+    got_t, st, mv = p.local_search(T.ALGO_OR_OPT, start, max_moves=max_moves, log_cap=1 << 16)
+    assert [m[1:] for m in mv] == [m[1:] for m in want_mv]
+    assert [np.float32(m[0]) for m in mv] == [np.float32(m[0]) for m in want_mv]
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals)
+    return got_t, st
+
+
+def test_or_opt_golden_G6(T, ctx, berlin52):  # docs/benchmarks.md:48
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    t, st = check_or_opt(T, ctx, x, y, O.nn_tour(P, 3))
+    assert f5(T.Problem.euc2d(ctx, x, y).tour_lengths(t)[0]) == "8097.47607"
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (10, 11, 136378)
+
+
+def test_or_opt_reference_unit_vectors(T, ctx):  # or_opt.rs:246-335
+    x, y = [0.0, 1.0, 5.0, 2.0, 3.0], [0.0, 0.0, 5.0, 0.0, 0.0]
+    p = T.Problem.euc2d(ctx, x, y)
+    s = p.session(T.ALGO_OR_OPT, np.arange(5))
+    mv = s.scan()
+    assert mv is not None and mv[0] < 0.0 and mv == tuple(
+        [np.float32(O.or_opt_find_best(O.Problem(x, y), np.arange(5))[0])] + list(O.or_opt_find_best(O.Problem(x, y), np.arange(5))[1:]))
+    s.close()
+    psq = T.Problem.euc2d(ctx, [0.0, 1.0, 1.0, 0.0], [0.0, 0.0, 1.0, 1.0])
+    s = psq.session(T.ALGO_OR_OPT, [0, 1, 2, 3])
+    assert s.scan() is None  # find_best_move returns None on the optimal square
+    s.close()
+    t, st, _ = psq.local_search(T.ALGO_OR_OPT, [0, 1, 2, 3])
+    assert abs(psq.tour_lengths(t)[0] - 4.0) < 1e-2
+    p3 = T.Problem.euc2d(ctx, [0.0, 1.0, 1.0], [0.0, 0.0, 1.0])
+    t, st, _ = p3.local_search(T.ALGO_OR_OPT, [2, 0, 1])
+    assert t.tolist() == [0, 1, 2]  # n < 4: identity order, seed ignored (or_opt.rs:31-34)
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 8, 31, 255, 256, 257, 258, 259, 600])
+def test_or_opt_small_and_block_edges(T, ctx, n):
+    x, y = O.gen_uniform(n, 300 + n)
+    check_or_opt(T, ctx, x, y, O.shuffle_tour(n, n + 2), max_moves=120)
+
+
+def test_or_opt_1k_nn_start(T, ctx):
+    x, y = O.gen_uniform(1000, 1000)
+    check_or_opt(T, ctx, x, y, O.nn_tour(O.Problem(x, y), 3))
+
+
+def test_or_opt_ties_on_lattice(T, ctx):
+    rng = np.random.default_rng(8)
+    x = rng.integers(0, 10, 300).astype(np.float32)
+    y = rng.integers(0, 10, 300).astype(np.float32)
+    check_or_opt(T, ctx, x, y, O.shuffle_tour(300, 4), max_moves=100)
+
+
+def test_or_opt_scan_only_10k(T, ctx):
+    n = 10000
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    t = O.shuffle_tour(n, 3)
+    s = T.Problem.euc2d(ctx, x, y).session(T.ALGO_OR_OPT, t)
+    got, want = s.scan(), O.or_opt_find_best(P, t)
+    assert got is not None and got[1:] == want[1:] and np.float32(got[0]) == np.float32(want[0])
+    s.close()
