@@ -21,6 +21,7 @@
 // Roofline: FP32 issue (no tensor cores: K=2 is not a contraction).  Algorithmic
 // work 15 flop/move, ~0 bytes/move.
 #include "kernels.cuh"
+#include "policy.cuh"
 #include "two_opt_apply.cuh"
 
 #include <math_constants.h>
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
         if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
     }
     const bool found = v.i != 0xffffffffu;
-    if (found) reverse_segment_inplace<FAST>(pts, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
+    if (found) reverse_segment_inplace(EucPol<FAST>{pts}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0) {
         *ticket = 0u;
         finish_best_step(state, found, v.delta, v.i, v.j, log, log_cap);
@@ -250,61 +251,6 @@ __global__ void __launch_bounds__(256)
         }
         pts[q] = p;
     }
-}
-
-// Reduce the candidate records (every block does it redundantly: at most a few hundred
-// records), then reverse path[i+1..=j] IN PLACE (swap_2opt, src/tsp/two_opt.rs:69-79).
-// Thread t swaps the (x, y, city) fields of positions (i+1+t, j-t) and the entering-edge
-// lengths of positions (i+2+t, j-t): inside the segment the old edge lengths are simply
-// mirrored (the metric is bitwise symmetric); the two new edges are recomputed by thread 0.
-// Every field of every record is read and written by exactly one thread, so the in-place
-// update is race free.  The last block to finish updates the loop state.
-template <bool FAST>
-__global__ void __launch_bounds__(256)
-    apply_two_opt_recompute_kernel(Pt *__restrict__ pts, const BestF *__restrict__ cand, int ncand,
-                                   DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
-                                   uint64_t log_cap)
-{
-    if (state->done) return;
-    __shared__ BestF sred[8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    BestF v{0.0f, 0xffffffffu, 0xffffffffu, 0u};
-    for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
-        const BestF o = cand[c];
-        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
-    }
-    warp_argmin_2opt(v.delta, v.i, v.j);
-    if (lane == 0) sred[warp] = v;
-    __syncthreads();
-    v = sred[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) {
-        const BestF o = sred[w];
-        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
-    }
-    const bool found = v.i != 0xffffffffu;
-    const uint32_t mi = v.i, mj = v.j;
-
-    if (found)
-        reverse_segment_inplace<FAST>(pts, mi, mj, nullptr, blockIdx.x * blockDim.x + threadIdx.x,
-                                      gridDim.x * blockDim.x);
-
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int tk = atomicAdd(ticket, 1u);
-        if (tk == gridDim.x - 1) { // last block: everyone has read `state` by now
-            *ticket = 0u;
-            finish_best_step(state, found, v.delta, mi, mj, log, log_cap);
-            __threadfence();
-        }
-    }
-}
-
-__global__ void extract_tour_kernel(const Pt *__restrict__ pts, uint32_t n, uint32_t *__restrict__ tour)
-{
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
-        tour[q] = (uint32_t)pts[q].city;
 }
 
 } // namespace
@@ -346,21 +292,6 @@ void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32
         build_pts_kernel<true><<<grid, 256, 0, st>>>(xy, tour, n, npad, cyclic, pts);
     else
         build_pts_kernel<false><<<grid, 256, 0, st>>>(xy, tour, n, npad, cyclic, pts);
-}
-
-void launch_apply_two_opt_recompute(Pt *pts, bool fast, const BestF *cand, int ncand, DevState *state,
-                                    unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid,
-                                    cudaStream_t st)
-{
-    if (fast)
-        apply_two_opt_recompute_kernel<true><<<grid, 256, 0, st>>>(pts, cand, ncand, state, ticket, log, log_cap);
-    else
-        apply_two_opt_recompute_kernel<false><<<grid, 256, 0, st>>>(pts, cand, ncand, state, ticket, log, log_cap);
-}
-
-void launch_extract_tour(const Pt *pts, uint32_t n, uint32_t *tour, cudaStream_t st)
-{
-    extract_tour_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, tour);
 }
 
 } // namespace tl

@@ -1,0 +1,307 @@
+// k2_two_opt_matrix.cu -- K2 "Mode B" scan, matrix-backed path (f32 or int32 distances in HBM).
+//
+// Same move space and argmin rule as k2_two_opt.cu.  Distances come from the n x ld matrix M,
+// stored in SLOT order; the tour-ordered records cs[q] = (slot, entering-edge length, city) map
+// tour positions to matrix slots.  The session lays M out in tour order (slot == position) when
+// it starts and re-lays it whenever the tour has fragmented, so that walking a row of the
+// (i,j) triangle reads a (nearly) contiguous run of a matrix row.
+//
+// Walk: diagonals k = j - i again, so d(p_i+1,p_j+1) of pair (i,j) is reused as d(p_i',p_j') of
+// pair (i+1,j+1): ONE matrix element is loaded per move -- each element M[a][b] of the upper
+// triangle is read exactly once per scan (4 algorithmic bytes per move).  Lane l owns the
+// diagonals K0 + l + 32 r, r < R, so for fixed r the 32 lanes of a warp read 32 consecutive
+// columns of one matrix row: a single 128-byte request when slot == position.  The (slot, s_j)
+// pairs of the columns are staged per warp in shared memory (compacted to 8 bytes) and read with
+// conflict-free 64-bit LDS; the loads of the next row are issued before the current row is
+// consumed (register double buffer) to keep enough bytes in flight for HBM.
+//
+// Roofline: HBM bandwidth, 4 B per move.
+#include "kernels.cuh"
+#include "policy.cuh"
+#include "two_opt_apply.cuh"
+
+#include <type_traits>
+
+namespace tl {
+
+namespace {
+
+constexpr int R = kMatR;
+constexpr int BW = kMatBW;
+constexpr int TI = kMatTI;
+constexpr int WARPS = kMatWarps;
+constexpr int ROWS_CAP = TI + 1;      // positions i0 .. i0+cnt
+constexpr int COLS_CAP = TI + BW + 1; // positions i0+K0 .. i0+K0+cnt+BW
+constexpr int WARP_RECS = ROWS_CAP + COLS_CAP;
+
+__device__ __forceinline__ int find_band_m(const int32_t *__restrict__ band_first, int nbands, int item)
+{
+    int lo = 0, hi = nbands - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&band_first[mid]) <= item)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+// streaming load: every matrix element is used once per scan, keep it out of L1
+template <typename V>
+__device__ __forceinline__ V ld_stream(const V *p)
+{
+    int32_t v;
+    asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return Val<V>::from_bits(v);
+}
+
+template <typename V>
+__global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
+    two_opt_scan_matrix_kernel(const V *__restrict__ M, uint32_t ld, Cs *__restrict__ cs, const ScanGeom g,
+                               const int32_t *__restrict__ band_first, Best<V> *__restrict__ blockbest,
+                               DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
+                               uint64_t log_cap, int fuse_apply)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (state->done) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-warp staging of (slot, entering-edge bits) pairs, 8 bytes each => conflict-free LDS.64
+    int2 *srow = reinterpret_cast<int2 *>(smem_raw) + warp * WARP_RECS;
+    int2 *scol = srow + ROWS_CAP;
+    Best<V> *red = reinterpret_cast<Best<V> *>(smem_raw + (size_t)WARPS * WARP_RECS * sizeof(int2));
+
+    V best = (V)0;
+    uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
+    const int total_warps = gridDim.x * WARPS;
+
+    for (int item = g.item_begin + blockIdx.x * WARPS + warp; item < g.item_end; item += total_warps) {
+        const int b = find_band_m(band_first, g.nbands, item);
+        const int K0 = 2 + b * BW;
+        const int H = g.jmax - K0 + 1;
+        const int r_begin = (item - __ldg(&band_first[b])) * g.chunk;
+        const int r_end = min(r_begin + g.chunk, H);
+        const int ntiles = (r_end - r_begin + TI - 1) / TI;
+        const int tile_rows = ntiles > 0 ? (r_end - r_begin + ntiles - 1) / ntiles : 0;
+
+        for (int i0 = r_begin; i0 < r_end; i0 += tile_rows) {
+            const int cnt = min(tile_rows, r_end - i0);
+            __syncwarp();
+            for (int t = lane; t < cnt + 1; t += 32) {
+                const Cs c = cs[i0 + t];
+                srow[t] = make_int2(c.slot, c.sp_bits);
+            }
+            for (int t = lane; t < cnt + BW + 1; t += 32) {
+                const Cs c = cs[i0 + K0 + t];
+                scol[t] = make_int2(c.slot, c.sp_bits);
+            }
+            __syncwarp();
+
+            // E[r] = d(p_i, p_j) carried down diagonal k_r = K0 + lane + 32 r; the record of
+            // position j+1 at row i0+tau sits at scol[tau + 1 + lane + 32 r].
+            V E[R], nxt[R];
+            int32_t spc[R];
+            {
+                const V *row0 = M + (size_t)srow[0].x * ld;
+                const V *row1 = M + (size_t)srow[1].x * ld;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    E[r] = ld_stream(row0 + scol[lane + 32 * r].x);
+                    const int2 c1 = scol[1 + lane + 32 * r];
+                    nxt[r] = ld_stream(row1 + c1.x);
+                    spc[r] = c1.y;
+                }
+            }
+#pragma unroll 1
+            for (int tau = 0; tau < cnt; ++tau) {
+                const int2 rp = srow[tau + 1]; // slot of p_i+1 and s_i
+                V en[R];
+                int32_t spn[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    en[r] = nxt[r];
+                    spn[r] = spc[r];
+                }
+                if (tau + 1 < cnt) { // issue the next row's loads before consuming this one
+                    const V *rown = M + (size_t)srow[tau + 2].x * ld;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int2 c2 = scol[tau + 2 + lane + 32 * r];
+                        nxt[r] = ld_stream(rown + c2.x);
+                        spc[r] = c2.y;
+                    }
+                }
+                const V si = Val<V>::from_bits(rp.y);
+                V dl[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const V cur = Val<V>::add(si, Val<V>::from_bits(spn[r]));
+                    const V nw = Val<V>::add(E[r], en[r]);
+                    dl[r] = Val<V>::sub(nw, cur);
+                    E[r] = en[r];
+                }
+                V m = dl[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) m = Val<V>::vmin(m, dl[r]);
+                if (m < best) { // rare; within a thread the scan order is (i, j) ascending
+                    const uint32_t i = (uint32_t)(i0 + tau);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t j = i + (uint32_t)(K0 + lane + 32 * r);
+                        const bool excluded = g.cyclic && i == 0 && j == (uint32_t)(g.n - 1);
+                        if (!excluded && dl[r] < best) {
+                            best = dl[r];
+                            bi = i;
+                            bj = j;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    warp_argmin_2opt(best, bi, bj);
+    if (lane == 0) red[warp] = Best<V>{best, bi, bj, 0u};
+    __syncthreads();
+    if (warp == 0) {
+        Best<V> v = (lane < WARPS) ? red[lane] : Best<V>{(V)0, 0xffffffffu, 0xffffffffu, 0u};
+        warp_argmin_2opt(v.delta, v.i, v.j);
+        if (lane == 0) blockbest[blockIdx.x] = v;
+    }
+    if (!fuse_apply) return;
+
+    // fused step tail: the last CTA reduces the per-CTA records and applies the move in place
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    Best<V> v{(V)0, 0xffffffffu, 0xffffffffu, 0u};
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+        const int4 raw = __ldcg(reinterpret_cast<const int4 *>(blockbest) + c);
+        const Best<V> o{Val<V>::from_bits(raw.x), (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    warp_argmin_2opt(v.delta, v.i, v.j);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    v = red[0];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) {
+        const Best<V> o = red[w];
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    const bool found = v.i != 0xffffffffu;
+    if (found) reverse_segment_inplace(MatPol<V>{cs, M, ld}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        finish_best_step(state, found, (float)v.delta, v.i, v.j, log, log_cap);
+    }
+}
+
+// cs[q] = {slot q, entering edge M[slot q-1][slot q], city}; wrap copy at n when cyclic; -inf padding
+template <typename V>
+__global__ void __launch_bounds__(256)
+    build_cs_kernel(const V *__restrict__ M, uint32_t ld, const uint32_t *__restrict__ tour, uint32_t n,
+                    uint32_t npad, int cyclic, Cs *__restrict__ cs)
+{
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < npad; q += gridDim.x * blockDim.x) {
+        Cs c;
+        c.pad = 0;
+        if (q < n || (q == n && cyclic)) {
+            const uint32_t slot = q == n ? 0 : q;
+            const uint32_t pslot = slot == 0 ? n - 1 : slot - 1;
+            c.slot = (int32_t)slot;
+            c.city = (int32_t)tour[slot];
+            const V e = (q == 0 && !cyclic) ? (V)0 : M[(size_t)pslot * ld + slot];
+            c.sp_bits = Val<V>::bits(e);
+        } else {
+            c.slot = 0;
+            c.city = -1;
+            c.sp_bits = Val<V>::bits(Val<V>::neg_inf());
+        }
+        cs[q] = c;
+    }
+}
+
+// slot-ordered scratch for building M in tour order
+__global__ void __launch_bounds__(256)
+    gather_slots_kernel(const float2 *__restrict__ xy, const uint32_t *__restrict__ tour, const Cs *__restrict__ cs,
+                        uint32_t n, float2 *__restrict__ sxy, int32_t *__restrict__ slot_city)
+{
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t city = tour ? tour[q] : (uint32_t)cs[q].city;
+        if (sxy && xy) sxy[q] = xy[city];
+        if (slot_city) slot_city[q] = (int32_t)city;
+    }
+}
+
+// after M has been re-laid in the current tour order: slot == position again
+__global__ void __launch_bounds__(256) reset_slots_kernel(Cs *__restrict__ cs, uint32_t n, int cyclic)
+{
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q <= n; q += gridDim.x * blockDim.x) {
+        if (q < n)
+            cs[q].slot = (int32_t)q;
+        else if (cyclic)
+            cs[q].slot = 0;
+    }
+}
+
+} // namespace
+
+size_t scan_matrix_smem_bytes()
+{
+    return (size_t)WARPS * WARP_RECS * sizeof(int2) + WARPS * sizeof(BestF);
+}
+
+cudaError_t scan_matrix_configure()
+{
+    cudaError_t e = cudaFuncSetAttribute(two_opt_scan_matrix_kernel<float>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_matrix_smem_bytes());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(two_opt_scan_matrix_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)scan_matrix_smem_bytes());
+}
+
+void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_first, void *blockbest,
+                        DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap, bool fuse_apply,
+                        int grid, cudaStream_t st)
+{
+    const size_t smem = scan_matrix_smem_bytes();
+    if (src.is_int())
+        two_opt_scan_matrix_kernel<int32_t><<<grid, WARPS * 32, smem, st>>>(
+            (const int32_t *)src.M, src.ld, src.cs, g, band_first, (BestI *)blockbest, state, ticket, log, log_cap,
+            fuse_apply);
+    else
+        two_opt_scan_matrix_kernel<float><<<grid, WARPS * 32, smem, st>>>(
+            (const float *)src.M, src.ld, src.cs, g, band_first, (BestF *)blockbest, state, ticket, log, log_cap,
+            fuse_apply);
+}
+
+void launch_build_cs(const Src &src, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st)
+{
+    const int grid = (int)((npad + 255) / 256);
+    if (src.is_int())
+        build_cs_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t *)src.M, src.ld, tour, n, npad, cyclic, src.cs);
+    else
+        build_cs_kernel<float><<<grid, 256, 0, st>>>((const float *)src.M, src.ld, tour, n, npad, cyclic, src.cs);
+}
+
+void launch_gather_slots(const float2 *xy, const uint32_t *tour, const Cs *cs, uint32_t n, float2 *sxy,
+                         int32_t *slot_city, cudaStream_t st)
+{
+    gather_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(xy, tour, cs, n, sxy, slot_city);
+}
+
+void launch_reset_slots(const Src &src, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st)
+{
+    (void)npad;
+    reset_slots_kernel<<<(n + 256) / 256, 256, 0, st>>>(src.cs, n, cyclic);
+}
+
+} // namespace tl

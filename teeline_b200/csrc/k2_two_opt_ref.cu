@@ -18,6 +18,7 @@
 // changes the path the next comparison sees), so this path is latency- not throughput-bound;
 // it exists for exact parity with the reference, not for the Tmove/s metric.
 #include "kernels.cuh"
+#include "policy.cuh"
 #include "two_opt_apply.cuh"
 
 namespace tl {
@@ -26,9 +27,11 @@ namespace {
 
 constexpr unsigned long long kNoKey = ~0ull;
 
-template <bool FAST>
-__global__ void __launch_bounds__(256) find_first_kernel(const Pt *__restrict__ pts, uint32_t n, DevState *state)
+template <class Pol>
+__global__ void __launch_bounds__(256) find_first_kernel(Pol P, uint32_t n, DevState *state)
 {
+    using V = typename Pol::V;
+    using Rec = typename Pol::Rec;
     if (state->done) return;
     const uint32_t ci = (uint32_t)state->cur_i, cj = (uint32_t)state->cur_j;
     const uint32_t W = (uint32_t)state->window_rows;
@@ -47,14 +50,14 @@ __global__ void __launch_bounds__(256) find_first_kernel(const Pt *__restrict__ 
         }
         __syncthreads();
         if (s_skip) break; // block-uniform
-        const Pt pi = pts[i], pi1 = pts[i + 1];
+        const Rec pi = P.load(i), pi1 = P.load(i + 1);
         const uint32_t j0 = (w == 0) ? cj : i + 2;
         for (uint32_t j = j0 + threadIdx.x; j <= last_col; j += blockDim.x) {
             if (j >= *(volatile unsigned int *)&s_j) break;
-            const Pt pj = pts[j], pj1 = pts[j + 1];
-            const float cur = __fadd_rn(pi1.sp, pj1.sp);
-            const float nw = __fadd_rn(dist_f32<FAST>(pi.x, pi.y, pj.x, pj.y),
-                                       dist_f32<FAST>(pi1.x, pi1.y, pj1.x, pj1.y));
+            const Rec pj = P.load(j), pj1 = P.load(j + 1);
+            // two separately rounded sums, compared directly (two_opt.rs:35-49)
+            const V cur = Val<V>::add(Pol::sp(pi1), Pol::sp(pj1));
+            const V nw = Val<V>::add(P.dist(pi, pj), P.dist(pi1, pj1));
             if (nw < cur) {
                 atomicMin(&s_j, j);
                 break;
@@ -66,10 +69,10 @@ __global__ void __launch_bounds__(256) find_first_kernel(const Pt *__restrict__ 
     }
 }
 
-template <bool FAST>
+template <class Pol>
 __global__ void __launch_bounds__(256)
-    apply_first_kernel(Pt *__restrict__ pts, uint32_t n, DevState *state, unsigned int *ticket,
-                       tl_move *__restrict__ log, uint64_t log_cap)
+    apply_first_kernel(Pol P, uint32_t n, DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
+                       uint64_t log_cap)
 {
     if (state->done) return;
     const unsigned long long key = state->found_key; // only the last block rewrites it, at the very end
@@ -77,8 +80,8 @@ __global__ void __launch_bounds__(256)
     const uint32_t mi = (uint32_t)(key >> 32), mj = (uint32_t)key;
     const int32_t ci = state->cur_i, W = state->window_rows;
     if (found)
-        reverse_segment_inplace<FAST>(pts, mi, mj, &state->last_delta, blockIdx.x * blockDim.x + threadIdx.x,
-                                      gridDim.x * blockDim.x);
+        reverse_segment_inplace(P, mi, mj, &state->last_delta, blockIdx.x * blockDim.x + threadIdx.x,
+                                gridDim.x * blockDim.x);
 
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -124,23 +127,37 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-} // namespace
-
-void launch_find_first(const Pt *pts, uint32_t n, DevState *state, int grid, bool fast, cudaStream_t st)
+template <class Pol>
+__global__ void extract_tour_kernel(Pol P, uint32_t n, uint32_t *__restrict__ tour)
 {
-    if (fast)
-        find_first_kernel<true><<<grid, 256, 0, st>>>(pts, n, state);
-    else
-        find_first_kernel<false><<<grid, 256, 0, st>>>(pts, n, state);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+        tour[q] = (uint32_t)Pol::city(P.load(q));
 }
 
-void launch_apply_first(Pt *pts, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
-                        uint64_t log_cap, int grid, bool fast, cudaStream_t st)
+} // namespace
+
+void launch_find_first(const Src &src, uint32_t n, DevState *state, int grid, cudaStream_t st)
 {
-    if (fast)
-        apply_first_kernel<true><<<grid, 256, 0, st>>>(pts, n, state, ticket, log, log_cap);
-    else
-        apply_first_kernel<false><<<grid, 256, 0, st>>>(pts, n, state, ticket, log, log_cap);
+    TL_DISPATCH_POL(src, (find_first_kernel<<<grid, 256, 0, st>>>(P, n, state)));
+}
+
+void launch_apply_first(const Src &src, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
+                        uint64_t log_cap, int grid, cudaStream_t st)
+{
+    TL_DISPATCH_POL(src, (apply_first_kernel<<<grid, 256, 0, st>>>(P, n, state, ticket, log, log_cap)));
+}
+
+void launch_apply_two_opt(const Src &src, const void *cand, int ncand, DevState *state, unsigned int *ticket,
+                          tl_move *log, uint64_t log_cap, int grid, cudaStream_t st)
+{
+    TL_DISPATCH_POL(src, (apply_two_opt_kernel<<<grid, 256, 0, st>>>(
+                             P, reinterpret_cast<const Best<typename decltype(P)::V> *>(cand), ncand, state,
+                             ticket, log, log_cap)));
+}
+
+void launch_extract_tour(const Src &src, uint32_t n, uint32_t *tour, cudaStream_t st)
+{
+    TL_DISPATCH_POL(src, (extract_tour_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, n, tour)));
 }
 
 } // namespace tl

@@ -22,6 +22,7 @@
 //
 // Roofline: FP32 issue; ~6.5 issued instructions per candidate.
 #include "kernels.cuh"
+#include "policy.cuh"
 
 #include <math_constants.h>
 
@@ -37,6 +38,11 @@ constexpr int TI = kOrTI;           // max rows per staged tile
 constexpr int WARPS = kOrWarps;
 constexpr int ROWPTS = TI + 3;      // positions i0 .. i0+cnt+1 (+1 slack)
 constexpr uint32_t kNone = 0xffffffffu;
+
+template <typename V>
+struct __align__(16) Quad {
+    V x, y, z, w;
+};
 
 template <int N, typename F>
 __device__ __forceinline__ void static_for(F &&f)
@@ -59,18 +65,20 @@ __device__ __forceinline__ bool rank_less(uint32_t i1, uint32_t j1, uint32_t a1,
 }
 
 // (delta, rank) lexicographic; a record with i == kNone is "no candidate yet" and only loses
-__device__ __forceinline__ bool better_or(const BestF &a, const BestF &b)
+template <typename V>
+__device__ __forceinline__ bool better_or(const Best<V> &a, const Best<V> &b)
 {
     if (a.i == kNone) return false;
     if (b.i == kNone) return true;
     return a.delta < b.delta || (a.delta == b.delta && rank_less(a.i, a.j, a.aux, b.i, b.j, b.aux));
 }
 
-__device__ __forceinline__ void warp_argmin_or(BestF &v)
+template <typename V>
+__device__ __forceinline__ void warp_argmin_or(Best<V> &v)
 {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        BestF o;
+        Best<V> o;
         o.delta = __shfl_xor_sync(0xffffffffu, v.delta, off);
         o.i = __shfl_xor_sync(0xffffffffu, v.i, off);
         o.j = __shfl_xor_sync(0xffffffffu, v.j, off);
@@ -80,53 +88,59 @@ __device__ __forceinline__ void warp_argmin_or(BestF &v)
 }
 
 // Per-row removal gains: info[i] = (-rg_1, -rg_2, -rg_3, 0); +inf disables a segment length.
-template <bool FAST>
+template <class Pol>
 __global__ void __launch_bounds__(256)
-    or_rowinfo_kernel(const Pt *__restrict__ pts, uint32_t n, uint32_t npad, float4 *__restrict__ info,
+    or_rowinfo_kernel(Pol P, uint32_t n, uint32_t npad, Quad<typename Pol::V> *__restrict__ info,
                       const DevState *__restrict__ state)
 {
+    using V = typename Pol::V;
+    using Rec = typename Pol::Rec;
     if (state->done) return;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += gridDim.x * blockDim.x) {
-        float v[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
+        V v[3] = {Val<V>::pos_inf(), Val<V>::pos_inf(), Val<V>::pos_inf()};
         if (i < n) {
             const uint32_t prev = i == 0 ? n - 1 : i - 1;
-            const Pt a = pts[prev];
-            const float daf = pts[i].sp; // d(p_prev, p_i); pts[0].sp is the closing edge
+            const Rec a = P.load(prev);
+            const V daf = Pol::sp(P.load(i)); // d(p_prev, p_i); position 0 carries the closing edge
 #pragma unroll
             for (uint32_t s = 1; s <= 3; ++s) {
                 if (n > s + 1 && i + s <= n) {
-                    const Pt dd = pts[i + s]; // position n is the wrap copy of position 0
-                    const float dldd = dd.sp;  // d(p_i+s-1, p_after)
-                    const float dadd = dist_f32<FAST>(a.x, a.y, dd.x, dd.y);
-                    const float rg = __fsub_rn(__fadd_rn(daf, dldd), dadd);
+                    const Rec dd = P.load(i + s); // position n is the wrap copy of position 0
+                    const V dldd = Pol::sp(dd);    // d(p_i+s-1, p_after)
+                    const V dadd = P.dist(a, dd);
+                    const V rg = Val<V>::sub(Val<V>::add(daf, dldd), dadd);
                     v[s - 1] = -rg;
                 }
             }
         }
-        info[i] = make_float4(v[0], v[1], v[2], 0.0f);
+        info[i] = Quad<V>{v[0], v[1], v[2], (V)0};
     }
 }
 
-template <bool FAST>
+template <class Pol>
 __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
-    or_opt_scan_kernel(const Pt *__restrict__ pts, const float4 *__restrict__ info, uint32_t n, int chunk,
-                       int items_per_cb, int item_begin, int item_end, BestF *__restrict__ blockbest,
-                       const DevState *__restrict__ state)
+    or_opt_scan_kernel(Pol P, const Quad<typename Pol::V> *__restrict__ info, uint32_t n, int chunk,
+                       int items_per_cb, int item_begin, int item_end,
+                       Best<typename Pol::V> *__restrict__ blockbest, const DevState *__restrict__ state)
 {
+    using V = typename Pol::V;
+    using Rec = typename Pol::Rec;
+    using Col = typename Pol::Col;
+    using BestV = Best<V>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (state->done) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Pt *srow = reinterpret_cast<Pt *>(smem_raw) + warp * (ROWPTS + TI);
-    float4 *sinfo = reinterpret_cast<float4 *>(srow + ROWPTS);
+    Rec *srow = reinterpret_cast<Rec *>(smem_raw) + warp * (ROWPTS + TI);
+    Quad<V> *sinfo = reinterpret_cast<Quad<V> *>(srow + ROWPTS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * (ROWPTS + TI) * 16);
     uint64_t *bar = bars + warp;
-    BestF *red = reinterpret_cast<BestF *>(bars + WARPS);
+    BestV *red = reinterpret_cast<BestV *>(bars + WARPS);
     if (lane == 0) mbar_init(bar, 1);
     mbar_fence_init();
     __syncthreads();
     uint32_t phase = 0;
 
-    BestF best{-1e-3f, kNone, kNone, 0u}; // or_opt.rs:86: best_delta = -1e-3
+    BestV best{Val<V>::or_threshold(), kNone, kNone, 0u}; // or_opt.rs:86: best_delta = -1e-3
     const int total_warps = gridDim.x * WARPS;
 
     for (int item = item_begin + blockIdx.x * WARPS + warp; item < item_end; item += total_warps) {
@@ -137,14 +151,14 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
         const int j0 = J0 + lane * R;     // first column of this lane
 
         // column points p_j0 .. p_j0+R and the insertion-edge lengths d(p_j, p_j+1) = sp[j+1]
-        float cx[R + 1], cy[R + 1], exy[R];
+        Col cc[R + 1];
+        V exy[R];
 #pragma unroll
         for (int c = 0; c <= R; ++c) {
-            const Pt p = pts[j0 + c];
-            cx[c] = p.x;
-            cy[c] = p.y;
+            const Rec p = P.load(j0 + c);
+            cc[c] = Pol::col(p);
             // columns j >= n do not exist: exy = -inf makes every candidate there +inf
-            if (c > 0) exy[c - 1] = (j0 + c - 1 < (int)n) ? p.sp : -CUDART_INF_F;
+            if (c > 0) exy[c - 1] = (j0 + c - 1 < (int)n) ? Pol::sp(p) : Val<V>::neg_inf();
         }
 
         const int ntiles = (r_end - r_begin + TI - 1) / TI;
@@ -153,23 +167,23 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
             const int cnt = min(tile_rows, r_end - i0);
             __syncwarp();
             if (lane == 0) {
-                const uint32_t rb = (uint32_t)(cnt + 2) * sizeof(Pt);
-                const uint32_t ib = (uint32_t)cnt * sizeof(float4);
+                const uint32_t rb = (uint32_t)(cnt + 2) * sizeof(Rec);
+                const uint32_t ib = (uint32_t)cnt * sizeof(Quad<V>);
                 mbar_expect_tx(bar, rb + ib);
-                tma_load_1d(srow, pts + i0, rb, bar);
+                tma_load_1d(srow, P.base() + i0, rb, bar);
                 tma_load_1d(sinfo, info + i0, ib, bar);
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
 
             // A[c][.] = E(column, row i+c); three live columns rotate through A0/A1/A2
-            float A[3][R + 1];
+            V A[3][R + 1];
             {
-                const Pt r0 = srow[0], r1 = srow[1];
+                const Rec r0 = srow[0], r1 = srow[1];
 #pragma unroll
                 for (int c = 0; c <= R; ++c) {
-                    A[0][c] = dist_f32<FAST>(r0.x, r0.y, cx[c], cy[c]);
-                    A[1][c] = dist_f32<FAST>(r1.x, r1.y, cx[c], cy[c]);
+                    A[0][c] = P.dist_rc(r0, cc[c]);
+                    A[1][c] = P.dist_rc(r1, cc[c]);
                 }
             }
 
@@ -177,39 +191,39 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
                 constexpr int PH = decltype(PHc)::value;
                 constexpr bool MASKED = decltype(MASKc)::value;
                 constexpr int P0 = PH % 3, P1 = (PH + 1) % 3, P2 = (PH + 2) % 3;
-                const Pt rp = srow[tau + 2];
-                const float4 ri = sinfo[tau];
+                const Rec rp = srow[tau + 2];
+                const Quad<V> ri = sinfo[tau];
 #pragma unroll
-                for (int c = 0; c <= R; ++c) A[P2][c] = dist_f32<FAST>(rp.x, rp.y, cx[c], cy[c]);
+                for (int c = 0; c <= R; ++c) A[P2][c] = P.dist_rc(rp, cc[c]);
                 const int i = i0 + tau;
                 const int prev = i == 0 ? (int)n - 1 : i - 1;
                 // candidate (r, k): k = 0 fwd1, 1 fwd2, 2 rev2, 3 fwd3, 4 rev3
-                auto cand = [&](int r, int k) -> float {
-                    const float nrg = k == 0 ? ri.x : (k <= 2 ? ri.y : ri.z);
-                    const float first = (k == 2) ? A[P1][r] : (k == 4 ? A[P2][r] : A[P0][r]);
-                    const float second = (k == 1) ? A[P1][r + 1] : (k == 3 ? A[P2][r + 1] : A[P0][r + 1]);
-                    float d = __fsub_rn(__fadd_rn(__fadd_rn(nrg, first), second), exy[r]);
+                auto cand = [&](int r, int k) -> V {
+                    const V nrg = k == 0 ? ri.x : (k <= 2 ? ri.y : ri.z);
+                    const V first = (k == 2) ? A[P1][r] : (k == 4 ? A[P2][r] : A[P0][r]);
+                    const V second = (k == 1) ? A[P1][r + 1] : (k == 3 ? A[P2][r + 1] : A[P0][r + 1]);
+                    V d = Val<V>::sub(Val<V>::add(Val<V>::add(nrg, first), second), exy[r]);
                     if (MASKED) {
                         const int j = j0 + r;
                         const int s = k == 0 ? 1 : (k <= 2 ? 2 : 3);
-                        if (j == prev || (j >= i && j < i + s)) d = CUDART_INF_F;
+                        if (j == prev || (j >= i && j < i + s)) d = Val<V>::pos_inf();
                     }
                     return d;
                 };
-                float m = CUDART_INF_F;
+                V m = Val<V>::pos_inf();
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) m = fminf(m, cand(r, k));
+                    for (int k = 0; k < 5; ++k) m = Val<V>::vmin(m, cand(r, k));
                 }
                 if (m <= best.delta) { // rare
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
 #pragma unroll
                         for (int k = 0; k < 5; ++k) {
-                            const float d = cand(r, k);
+                            const V d = cand(r, k);
                             const uint32_t aux = k == 0 ? 0u : (uint32_t)(k + 1); // (s-1)*2 + rev
-                            const BestF o{d, (uint32_t)i, (uint32_t)(j0 + r), aux};
+                            const BestV o{d, (uint32_t)i, (uint32_t)(j0 + r), aux};
                             const bool take = best.i == kNone ? (d < best.delta) : better_or(o, best);
                             if (take) best = o;
                         }
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
     if (lane == 0) red[warp] = best;
     __syncthreads();
     if (warp == 0) {
-        BestF v = (lane < WARPS) ? red[lane] : BestF{0.0f, kNone, kNone, 0u};
+        BestV v = (lane < WARPS) ? red[lane] : BestV{(V)0, kNone, kNone, 0u};
         warp_argmin_or(v);
         if (lane == 0) blockbest[blockIdx.x] = v;
     }
@@ -254,12 +268,13 @@ struct OrMove {
     uint32_t i, j, s, rev, lo, hi;
 };
 
-__device__ __forceinline__ OrMove reduce_or_candidates(const BestF *__restrict__ cand, int ncand, BestF *sred)
+template <typename V>
+__device__ __forceinline__ OrMove reduce_or_candidates(const Best<V> *__restrict__ cand, int ncand, Best<V> *sred)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    BestF v{0.0f, kNone, kNone, 0u};
+    Best<V> v{(V)0, kNone, kNone, 0u};
     for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
-        const BestF o = cand[c];
+        const Best<V> o = cand[c];
         if (better_or(o, v)) v = o;
     }
     warp_argmin_or(v);
@@ -270,7 +285,7 @@ __device__ __forceinline__ OrMove reduce_or_candidates(const BestF *__restrict__
         if (better_or(sred[w], v)) v = sred[w];
     OrMove m;
     m.found = v.i != kNone;
-    m.delta = v.delta;
+    m.delta = (float)v.delta;
     m.i = v.i;
     m.j = v.j;
     m.s = (v.aux >> 1) + 1;
@@ -295,59 +310,60 @@ __device__ __forceinline__ uint32_t or_source(const OrMove &m, uint32_t q)
     return q - m.s;
 }
 
+template <class Pol>
 __global__ void __launch_bounds__(256)
-    or_apply_gather_kernel(const Pt *__restrict__ pts, Pt *__restrict__ tmp, const BestF *__restrict__ cand,
-                           int ncand, const DevState *__restrict__ state)
+    or_apply_gather_kernel(Pol P, typename Pol::Rec *__restrict__ tmp,
+                           const Best<typename Pol::V> *__restrict__ cand, int ncand,
+                           const DevState *__restrict__ state)
 {
     if (state->done) return;
-    __shared__ BestF sred[8];
+    __shared__ Best<typename Pol::V> sred[8];
     const OrMove m = reduce_or_candidates(cand, ncand, sred);
     if (!m.found) return;
     for (uint32_t q = m.lo + blockIdx.x * blockDim.x + threadIdx.x; q <= m.hi; q += gridDim.x * blockDim.x)
-        tmp[q - m.lo] = pts[or_source(m, q)];
+        tmp[q - m.lo] = P.load(or_source(m, q));
 }
 
-template <bool FAST>
+template <class Pol>
 __global__ void __launch_bounds__(256)
-    or_apply_scatter_kernel(Pt *__restrict__ pts, const Pt *__restrict__ tmp, uint32_t n,
-                            const BestF *__restrict__ cand, int ncand, DevState *state, unsigned int *ticket,
-                            tl_move *__restrict__ log, uint64_t log_cap)
+    or_apply_scatter_kernel(Pol P, const typename Pol::Rec *__restrict__ tmp, uint32_t n,
+                            const Best<typename Pol::V> *__restrict__ cand, int ncand, DevState *state,
+                            unsigned int *ticket, tl_move *__restrict__ log, uint64_t log_cap)
 {
+    using Rec = typename Pol::Rec;
     if (state->done) return;
-    __shared__ BestF sred[8];
+    __shared__ Best<typename Pol::V> sred[8];
     const OrMove m = reduce_or_candidates(cand, ncand, sred);
     if (m.found) {
         // record now at position q (q in 0..n): relocated range from tmp, everything else unchanged
-        auto newpt = [&](uint32_t q) -> Pt {
+        auto newpt = [&](uint32_t q) -> Rec {
             const uint32_t qq = q == n ? 0u : q;
-            return (qq >= m.lo && qq <= m.hi) ? tmp[qq - m.lo] : pts[qq];
+            return (qq >= m.lo && qq <= m.hi) ? tmp[qq - m.lo] : P.load(qq);
         };
         // positions lo .. hi+1 get a new record and/or a new entering edge; every read of a
         // relocated position goes to tmp, so the in-place writes below cannot race with them
         for (uint32_t q = m.lo + blockIdx.x * blockDim.x + threadIdx.x; q <= m.hi + 1; q += gridDim.x * blockDim.x) {
-            Pt p = newpt(q);
-            if (q >= 1) {
-                const Pt b = newpt(q - 1);
-                p.sp = dist_f32<FAST>(b.x, b.y, p.x, p.y);
-                if (q <= n) {
-                    if (q <= m.hi) {
-                        pts[q] = p;
-                    } else {
-                        pts[q].sp = p.sp; // hi+1: same city (or the wrap copy), new entering edge
-                    }
-                }
+            if (q < 1 || q > n) continue;
+            Rec p = newpt(q);
+            const Rec b = newpt(q - 1);
+            const typename Pol::V e = P.dist(b, p);
+            if (q <= m.hi) {
+                Pol::set_sp(p, e);
+                P.store(q, p);
+            } else {
+                P.store_sp(q, e); // hi+1: same city (or the wrap copy), new entering edge
             }
         }
         // closing edge and the wrap copy at position n
         if (blockIdx.x == 0 && threadIdx.x == 0 && (m.lo == 0 || m.hi >= n - 1)) {
-            Pt p0 = newpt(0);
-            const Pt last = newpt(n - 1);
-            p0.sp = dist_f32<FAST>(last.x, last.y, p0.x, p0.y);
-            pts[n] = p0;
+            Rec p0 = newpt(0);
+            const Rec last = newpt(n - 1);
+            Pol::set_sp(p0, P.dist(last, p0));
+            P.store(n, p0);
             if (m.lo == 0) {
-                pts[0] = p0;
+                P.store(0, p0);
             } else {
-                pts[0].sp = p0.sp;
+                P.store_sp(0, Pol::sp(p0));
             }
         }
     }
@@ -381,43 +397,42 @@ size_t or_scan_smem_bytes()
 
 cudaError_t or_scan_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(or_opt_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)or_scan_smem_bytes());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(or_opt_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)or_scan_smem_bytes());
+    const int bytes = (int)or_scan_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(or_opt_scan_kernel<EucPol<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(or_opt_scan_kernel<EucPol<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(or_opt_scan_kernel<MatPol<float>>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(or_opt_scan_kernel<MatPol<int32_t>>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
 }
 
-void launch_or_rowinfo(const Pt *pts, uint32_t n, uint32_t npad, float4 *info, const DevState *state, bool fast,
+void launch_or_rowinfo(const Src &src, uint32_t n, uint32_t npad, void *info, const DevState *state,
                        cudaStream_t st)
 {
     const int grid = (int)((npad + 255) / 256);
-    if (fast)
-        or_rowinfo_kernel<true><<<grid, 256, 0, st>>>(pts, n, npad, info, state);
-    else
-        or_rowinfo_kernel<false><<<grid, 256, 0, st>>>(pts, n, npad, info, state);
+    TL_DISPATCH_POL(src, (or_rowinfo_kernel<<<grid, 256, 0, st>>>(
+                             P, n, npad, reinterpret_cast<Quad<typename decltype(P)::V> *>(info), state)));
 }
 
-void launch_or_scan(const Pt *pts, const float4 *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
-                    int item_end, BestF *blockbest, const DevState *state, int grid, bool fast, cudaStream_t st)
+void launch_or_scan(const Src &src, const void *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
+                    int item_end, void *blockbest, const DevState *state, int grid, cudaStream_t st)
 {
     const size_t smem = or_scan_smem_bytes();
-    if (fast)
-        or_opt_scan_kernel<true><<<grid, WARPS * 32, smem, st>>>(pts, info, n, chunk, items_per_cb, item_begin,
-                                                                item_end, blockbest, state);
-    else
-        or_opt_scan_kernel<false><<<grid, WARPS * 32, smem, st>>>(pts, info, n, chunk, items_per_cb, item_begin,
-                                                                 item_end, blockbest, state);
+    TL_DISPATCH_POL(src, (or_opt_scan_kernel<<<grid, WARPS * 32, smem, st>>>(
+                             P, reinterpret_cast<const Quad<typename decltype(P)::V> *>(info), n, chunk,
+                             items_per_cb, item_begin, item_end,
+                             reinterpret_cast<Best<typename decltype(P)::V> *>(blockbest), state)));
 }
 
-void launch_or_apply(Pt *pts, Pt *tmp, uint32_t n, const BestF *cand, int ncand, DevState *state,
-                     unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid, bool fast, cudaStream_t st)
+void launch_or_apply(const Src &src, void *tmp, uint32_t n, const void *cand, int ncand, DevState *state,
+                     unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid, cudaStream_t st)
 {
-    or_apply_gather_kernel<<<grid, 256, 0, st>>>(pts, tmp, cand, ncand, state);
-    if (fast)
-        or_apply_scatter_kernel<true><<<grid, 256, 0, st>>>(pts, tmp, n, cand, ncand, state, ticket, log, log_cap);
-    else
-        or_apply_scatter_kernel<false><<<grid, 256, 0, st>>>(pts, tmp, n, cand, ncand, state, ticket, log, log_cap);
+    TL_DISPATCH_POL(src, {
+        using PolT = decltype(P);
+        auto *t = reinterpret_cast<typename PolT::Rec *>(tmp);
+        auto *c = reinterpret_cast<const Best<typename PolT::V> *>(cand);
+        or_apply_gather_kernel<<<grid, 256, 0, st>>>(P, t, c, ncand, state);
+        or_apply_scatter_kernel<<<grid, 256, 0, st>>>(P, t, n, c, ncand, state, ticket, log, log_cap);
+    });
 }
 
 } // namespace tl

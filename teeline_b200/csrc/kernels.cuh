@@ -43,14 +43,25 @@ struct DevState {
     int32_t pad1;
 };
 
-struct BestF {
-    float delta;
-    uint32_t i, j, aux;
+
+// Where a launch gets its distances from (selects the Policy instantiation, policy.cuh).
+enum SrcKind { SRC_EUC_FAST = 0, SRC_EUC_SAFE = 1, SRC_MAT_F32 = 2, SRC_MAT_I32 = 3 };
+struct Src {
+    int kind = SRC_EUC_FAST;
+    Pt *pts = nullptr;       // SRC_EUC_*
+    Cs *cs = nullptr;        // SRC_MAT_*
+    const void *M = nullptr; // slot-ordered n x ld matrix (f32 or i32)
+    uint32_t ld = 0;
+    bool is_int() const { return kind == SRC_MAT_I32; }
+    void *records() const { return kind <= SRC_EUC_SAFE ? (void *)pts : (void *)cs; }
 };
-struct BestI {
-    int32_t delta;
-    uint32_t i, j, aux;
-};
+#define TL_DISPATCH_POL(src, ...)                                                             \
+    switch ((src).kind) {                                                                     \
+    case SRC_EUC_FAST: { EucPol<true> P{(src).pts}; __VA_ARGS__; } break;                      \
+    case SRC_EUC_SAFE: { EucPol<false> P{(src).pts}; __VA_ARGS__; } break;                     \
+    case SRC_MAT_F32: { MatPol<float> P{(src).cs, (const float *)(src).M, (src).ld}; __VA_ARGS__; } break; \
+    default: { MatPol<int32_t> P{(src).cs, (const int32_t *)(src).M, (src).ld}; __VA_ARGS__; } break;      \
+    }
 
 // ---------------------------------------------------------------------------
 // launchers
@@ -87,16 +98,15 @@ void launch_scan_recompute(Pt *pts, const ScanGeom &g, const int32_t *band_first
                            bool fuse_apply, int grid, bool fast, cudaStream_t st);
 void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic,
                       bool fast, Pt *pts, cudaStream_t st);
-void launch_apply_two_opt_recompute(Pt *pts, bool fast, const BestF *cand, int ncand, DevState *state,
-                                    unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid,
-                                    cudaStream_t st);
-void launch_extract_tour(const Pt *pts, uint32_t n, uint32_t *tour, cudaStream_t st);
+void launch_apply_two_opt(const Src &src, const void *cand, int ncand, DevState *state, unsigned int *ticket,
+                          tl_move *log, uint64_t log_cap, int grid, cudaStream_t st);
+void launch_extract_tour(const Src &src, uint32_t n, uint32_t *tour, cudaStream_t st);
 
 // K2 Mode R (reference-exact first improvement)
 constexpr int kRefWindow0 = 8; // rows scanned per launch right after a hit
-void launch_find_first(const Pt *pts, uint32_t n, DevState *state, int grid, bool fast, cudaStream_t st);
-void launch_apply_first(Pt *pts, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
-                        uint64_t log_cap, int grid, bool fast, cudaStream_t st);
+void launch_find_first(const Src &src, uint32_t n, DevState *state, int grid, cudaStream_t st);
+void launch_apply_first(const Src &src, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
+                        uint64_t log_cap, int grid, cudaStream_t st);
 
 // K3 Or-opt (recompute path)
 constexpr int kOrR = 8;          // columns per lane
@@ -105,12 +115,12 @@ constexpr int kOrWarps = 8;
 constexpr int kOrMinBlocks = 2;
 size_t or_scan_smem_bytes();
 cudaError_t or_scan_configure();
-void launch_or_rowinfo(const Pt *pts, uint32_t n, uint32_t npad, float4 *info, const DevState *state, bool fast,
+void launch_or_rowinfo(const Src &src, uint32_t n, uint32_t npad, void *info, const DevState *state,
                        cudaStream_t st);
-void launch_or_scan(const Pt *pts, const float4 *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
-                    int item_end, BestF *blockbest, const DevState *state, int grid, bool fast, cudaStream_t st);
-void launch_or_apply(Pt *pts, Pt *tmp, uint32_t n, const BestF *cand, int ncand, DevState *state,
-                     unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid, bool fast, cudaStream_t st);
+void launch_or_scan(const Src &src, const void *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
+                    int item_end, void *blockbest, const DevState *state, int grid, cudaStream_t st);
+void launch_or_apply(const Src &src, void *tmp, uint32_t n, const void *cand, int ncand, DevState *state,
+                     unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid, cudaStream_t st);
 
 // K5 / N1
 void launch_knn(const float2 *xy, const float *tri, uint32_t n, uint32_t k, int metric_id, uint32_t *out,
@@ -119,6 +129,25 @@ size_t nn_tour_smem_bytes(uint32_t n);
 cudaError_t nn_tour_configure();
 void launch_nn_tour(const float2 *xy, const float *tri, uint32_t n, const uint32_t *knn, uint32_t kk,
                     int metric_id, uint32_t *tour, cudaStream_t st);
+
+// K2 matrix path
+constexpr int kMatR = 8;                 // diagonals per lane (strided by 32 => coalesced rows)
+constexpr int kMatBW = 32 * kMatR;
+constexpr int kMatTI = 64;
+constexpr int kMatWarps = 8;
+constexpr int kMatMinBlocks = 3;
+size_t scan_matrix_smem_bytes();
+cudaError_t scan_matrix_configure();
+void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_first, void *blockbest,
+                        DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap, bool fuse_apply,
+                        int grid, cudaStream_t st);
+// cs[q] = {slot = q, sp = M[q-1][q], city = tour[q]} (+ wrap copy at n when cyclic, -inf padding)
+void launch_build_cs(const Src &src, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st);
+// slot-ordered scratch for (re)building the matrix in tour order: from `tour` (session start)
+// or from the current records (re-permutation); also resets slot = position
+void launch_gather_slots(const float2 *xy, const uint32_t *tour, const Cs *cs, uint32_t n, float2 *sxy,
+                         int32_t *slot_city, cudaStream_t st);
+void launch_reset_slots(const Src &src, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st);
 
 // K4
 void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, const uint32_t *tours,

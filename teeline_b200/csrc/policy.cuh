@@ -1,0 +1,83 @@
+// policy.cuh -- where a kernel gets distances from.
+//
+// Every local-search kernel is written once against a Policy:
+//   EucPol<FAST> : distances recomputed from tour-ordered coordinates (16-byte Pt records)
+//   MatPol<V>    : distances read from the slot-ordered n x ld matrix in HBM through the
+//                  tour-ordered Cs records (slot, entering-edge length, city), V = float | int32
+// Both are bit-identical for EUC_2D f32 problems; MatPol also serves
+// EXPLICIT matrices and the TSPLIB nint metric.
+#pragma once
+
+#include "common.cuh"
+
+namespace tl {
+
+template <bool FAST>
+struct EucPol {
+    using V = float;
+    using Rec = Pt;
+    struct Col {
+        float x, y;
+    };
+    Pt *pts;
+
+    __device__ __forceinline__ Rec load(uint32_t q) const { return pts[q]; }
+    __device__ __forceinline__ const Rec *base() const { return pts; }
+    static __device__ __forceinline__ Col col(const Rec &r) { return Col{r.x, r.y}; }
+    static __device__ __forceinline__ V sp(const Rec &r) { return r.sp; }
+    static __device__ __forceinline__ void set_sp(Rec &r, V v) { r.sp = v; }
+    static __device__ __forceinline__ int32_t city(const Rec &r) { return r.city; }
+    __device__ __forceinline__ V dist(const Rec &a, const Rec &b) const
+    {
+        return dist_f32<FAST>(a.x, a.y, b.x, b.y);
+    }
+    __device__ __forceinline__ V dist_rc(const Rec &a, const Col &c) const
+    {
+        return dist_f32<FAST>(a.x, a.y, c.x, c.y);
+    }
+    // everything that identifies the city at q, but not its entering-edge length
+    __device__ __forceinline__ void store_id(uint32_t q, const Rec &from) const
+    {
+        pts[q].x = from.x;
+        pts[q].y = from.y;
+        pts[q].city = from.city;
+    }
+    __device__ __forceinline__ void store_sp(uint32_t q, V v) const { pts[q].sp = v; }
+    __device__ __forceinline__ void store(uint32_t q, const Rec &r) const { pts[q] = r; }
+};
+
+template <typename VT>
+struct MatPol {
+    using V = VT;
+    using Rec = Cs;
+    struct Col {
+        int32_t slot;
+    };
+    Cs *cs;
+    const VT *M;
+    uint32_t ld;
+
+    __device__ __forceinline__ Rec load(uint32_t q) const { return cs[q]; }
+    __device__ __forceinline__ const Rec *base() const { return cs; }
+    static __device__ __forceinline__ Col col(const Rec &r) { return Col{r.slot}; }
+    static __device__ __forceinline__ V sp(const Rec &r) { return Val<V>::from_bits(r.sp_bits); }
+    static __device__ __forceinline__ void set_sp(Rec &r, V v) { r.sp_bits = Val<V>::bits(v); }
+    static __device__ __forceinline__ int32_t city(const Rec &r) { return r.city; }
+    __device__ __forceinline__ V dist(const Rec &a, const Rec &b) const
+    {
+        return __ldg(&M[(size_t)a.slot * ld + b.slot]);
+    }
+    __device__ __forceinline__ V dist_rc(const Rec &a, const Col &c) const
+    {
+        return __ldg(&M[(size_t)a.slot * ld + c.slot]);
+    }
+    __device__ __forceinline__ void store_id(uint32_t q, const Rec &from) const
+    {
+        cs[q].slot = from.slot;
+        cs[q].city = from.city;
+    }
+    __device__ __forceinline__ void store_sp(uint32_t q, V v) const { cs[q].sp_bits = Val<V>::bits(v); }
+    __device__ __forceinline__ void store(uint32_t q, const Rec &r) const { cs[q] = r; }
+};
+
+} // namespace tl

@@ -1,12 +1,18 @@
 // session.cu -- device-resident local-search sessions and the one-call wrappers.
 //
-// A session keeps the tour on the device in tour order (16-byte point records,
-// reversed in place by the apply kernel) and runs  scan -> [all-gather] -> apply  iterations without
-// host round trips: the apply kernel decides convergence on the device and later
-// launches become no-ops, so the host only synchronises once per batch of steps.
+// A session keeps the tour on the device in tour order (16-byte records, updated in place
+// by the apply kernels) and runs  scan -> [all-gather] -> apply  iterations without host round
+// trips: the apply step decides convergence on the device and later launches become no-ops,
+// so the host only synchronises once per batch of steps.
+//
+// Two distance sources (policy.cuh): coordinate recompute (Pt records) and the slot-ordered
+// n x ld matrix in HBM (Cs records).  The matrix is laid out in tour order when the session
+// starts and re-laid every `repermute_every` steps, which keeps the 2-opt scan's row reads
+// contiguous as reversals fragment the tour.
 #include "host.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace tl;
 
@@ -17,6 +23,7 @@ cudaError_t configure_all_kernels()
     cudaError_t e = scan_recompute_configure();
     if (e == cudaSuccess) e = nn_tour_configure();
     if (e == cudaSuccess) e = or_scan_configure();
+    if (e == cudaSuccess) e = scan_matrix_configure();
     return e;
 }
 
@@ -31,11 +38,20 @@ struct tl_session {
     int cyclic = 0;
     bool trivial = false; // n < 4: nothing to scan
 
-    // recompute-path state
     uint32_t npad = 0;
-    DevBuf<Pt> pts; // tour-ordered point records, updated in place by the apply kernel
-    DevBuf<Pt> tmp;          // Or-opt: relocated range staging
-    DevBuf<float4> rowinfo;  // Or-opt: per-row removal gains
+    Src src;                 // which policy the kernels run with, and its device pointers
+    DevBuf<Pt> pts;          // recompute path: tour-ordered point records
+    DevBuf<Cs> cs;           // matrix path: tour-ordered (slot, edge, city) records
+    DevBuf<uint32_t> M;      // matrix path: n x ld distances (f32 bits or int32), slot order
+    uint32_t ld = 0;
+    DevBuf<float2> sxy;          // scratch: slot-ordered coordinates for (re)building M
+    DevBuf<int32_t> slot_city;   // scratch: slot -> city for EXPLICIT problems
+    int repermute_every = 0;     // matrix path: re-lay M in tour order every this many steps (0 = never)
+    uint32_t steps_since_permute = 0;
+    uint64_t repermutes = 0;
+
+    DevBuf<unsigned char> tmp;     // Or-opt: relocated range staging (npad records of 16 B)
+    DevBuf<unsigned char> rowinfo; // Or-opt: per-row removal gains (npad x 16 B)
     int or_chunk = 0, or_items_per_cb = 0, or_item_begin = 0, or_item_end = 0;
 
     ScanGeom geom{};
@@ -44,7 +60,7 @@ struct tl_session {
     int grid = 1;
     int shard_index = 0, shard_count = 1;
 
-    DevBuf<BestF> cand; // shard_count * grid records; this rank's at [shard_index*grid]
+    DevBuf<BestF> cand; // shard_count * grid records (BestF and BestI have the same layout)
     DevBuf<DevState> state;
     DevBuf<unsigned int> ticket;
     DevBuf<tl_move> log;
@@ -56,24 +72,29 @@ struct tl_session {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_open = false;
     double device_ms = 0.0;
+
+    bool matrix() const { return path_used == TL_PATH_MATRIX; }
 };
 
 namespace {
 
-// Work decomposition of the diagonal bands (see kernels.cuh: ScanGeom).
+// Work decomposition of the 2-opt diagonal bands (see kernels.cuh: ScanGeom).
 void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
 {
+    const int bw = s->matrix() ? kMatBW : kScanBW;
+    const int warps = s->matrix() ? kMatWarps : kScanWarps;
+    const int minb = s->matrix() ? kMatMinBlocks : kScanMinBlocks;
     const int n = (int)s->n;
     ScanGeom &g = s->geom;
     g.n = n;
     g.cyclic = s->cyclic;
     g.jmax = s->cyclic ? n - 1 : n - 2;
     g.kmax = n - 2;
-    g.nbands = (g.kmax - 2) / kScanBW + 1;
-    auto H = [&](int b) { return g.jmax - (2 + b * kScanBW) + 1; };
-    // one work item per resident warp (kScanMinBlocks CTAs/SM x 8 warps), times the shard count so that
-    // every rank of a sharded scan still fills its GPU
-    const int64_t target = (int64_t)s->c->sm_count * kScanMinBlocks * kScanWarps * s->shard_count;
+    g.nbands = (g.kmax - 2) / bw + 1;
+    auto H = [&](int b) { return g.jmax - (2 + b * bw) + 1; };
+    // one work item per resident warp, times the shard count so that every rank of a sharded
+    // scan still fills its GPU
+    const int64_t target = (int64_t)s->c->sm_count * minb * warps * s->shard_count;
     auto items_for = [&](int chunk) {
         int64_t t = 0;
         for (int b = 0; b < g.nbands; ++b) t += (H(b) + chunk - 1) / chunk;
@@ -95,8 +116,8 @@ void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
     g.item_begin = (int32_t)std::min<int64_t>(s->nitems, per * s->shard_index);
     g.item_end = (int32_t)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
     // same grid on every rank so the all-gather is symmetric
-    const int64_t blocks = (per + kScanWarps - 1) / kScanWarps;
-    s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * kScanMinBlocks));
+    const int64_t blocks = (per + warps - 1) / warps;
+    s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * minb));
 }
 
 // Or-opt work decomposition: column blocks of 32*kOrR insertion edges x row chunks.
@@ -147,25 +168,56 @@ tl_status pull_state(tl_session *s)
     return TL_OK;
 }
 
-// fuse: let the scan kernel's last CTA apply the move (single-GPU stepping only)
+// (Re)build the slot-ordered matrix: slot q holds the city at `tour[q]` (session start) or at
+// the current position q (re-permutation, tour == nullptr).
+void build_matrix(tl_session *s, const uint32_t *d_tour)
+{
+    tl_problem *p = s->p;
+    cudaStream_t st = s->c->stream;
+    if (p->kind == PK_EXPLICIT) {
+        launch_gather_slots(nullptr, d_tour, s->cs.p, s->n, nullptr, s->slot_city.p, st);
+        launch_k1_square_from_packed(reinterpret_cast<const uint32_t *>(p->d_tri), s->slot_city.p, s->n, s->ld,
+                                     s->M.p, st);
+    } else {
+        launch_gather_slots(p->d_xy, d_tour, s->cs.p, s->n, s->sxy.p, nullptr, st);
+        launch_k1_square(s->sxy.p, s->n, s->ld, p->fast_sqrt, p->kind == PK_EUC_NINT, s->M.p, st);
+    }
+    s->c->launches += 2;
+}
+
+void repermute(tl_session *s)
+{
+    build_matrix(s, nullptr);
+    launch_reset_slots(s->src, s->n, s->npad, s->cyclic, s->c->stream);
+    s->c->launches++;
+    s->repermutes++;
+    s->steps_since_permute = 0;
+}
+
+// fuse: let the 2-opt scan kernel's last CTA apply the move (single-GPU stepping only)
 tl_status launch_scan(tl_session *s, bool fuse)
 {
     BestF *mine = s->cand.p + (size_t)s->shard_index * s->grid;
+    cudaStream_t st = s->c->stream;
     if (s->algo == TL_ALGO_OR_OPT) {
-        launch_or_rowinfo(s->pts.p, s->n, s->npad, s->rowinfo.p, s->state.p, s->p->fast_sqrt, s->c->stream);
-        launch_or_scan(s->pts.p, s->rowinfo.p, s->n, s->or_chunk, s->or_items_per_cb, s->or_item_begin,
-                       s->or_item_end, mine, s->state.p, s->grid, s->p->fast_sqrt, s->c->stream);
+        launch_or_rowinfo(s->src, s->n, s->npad, s->rowinfo.p, s->state.p, st);
+        launch_or_scan(s->src, s->rowinfo.p, s->n, s->or_chunk, s->or_items_per_cb, s->or_item_begin,
+                       s->or_item_end, mine, s->state.p, s->grid, st);
         s->c->launches += 2;
-    } else
-    launch_scan_recompute(s->pts.p, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p,
-                          s->log_cap, fuse && s->shard_count == 1, s->grid, s->p->fast_sqrt, s->c->stream);
-    if (s->algo != TL_ALGO_OR_OPT) s->c->launches++;
+    } else if (s->matrix()) {
+        launch_scan_matrix(s->src, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p, s->log_cap,
+                           fuse && s->shard_count == 1, s->grid, st);
+        s->c->launches++;
+    } else {
+        launch_scan_recompute(s->pts.p, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p,
+                              s->log_cap, fuse && s->shard_count == 1, s->grid, s->src.kind == SRC_EUC_FAST, st);
+        s->c->launches++;
+    }
     if (s->shard_count > 1) {
         if (!s->c->nccl_comm) { set_error("sharded session needs tl_ctx_attach_nccl first"); return TL_ERR_NCCL; }
         // in-place all-gather: every rank contributes its `grid` block records
-        tl_status st = nccl_all_gather_bytes(s->c->nccl_comm, mine, s->cand.p, (size_t)s->grid * sizeof(BestF),
-                                             s->c->stream);
-        if (st != TL_OK) return st;
+        tl_status rc = nccl_all_gather_bytes(s->c->nccl_comm, mine, s->cand.p, (size_t)s->grid * sizeof(BestF), st);
+        if (rc != TL_OK) return rc;
     }
     return TL_OK;
 }
@@ -177,32 +229,36 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
         TL_CUDA_TRY(cudaEventRecord(s->ev0, s->c->stream));
         s->timing_open = true;
     }
+    cudaStream_t st = s->c->stream;
     // one thread per swapped pair, at most n/2 pairs
-    const int apply_grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((s->n / 2 + 255) / 256, (uint32_t)s->c->sm_count));
+    const int apply_grid =
+        (int)std::max<uint32_t>(1, std::min<uint32_t>((s->n / 2 + 255) / 256, (uint32_t)s->c->sm_count));
     if (s->algo == TL_ALGO_TWO_OPT_REF) {
         const int find_grid = s->c->sm_count * 2;
         for (uint32_t k = 0; k < steps; ++k) {
-            launch_find_first(s->pts.p, s->n, s->state.p, find_grid, s->p->fast_sqrt, s->c->stream);
-            launch_apply_first(s->pts.p, s->n, s->state.p, s->ticket.p, s->log.p, s->log_cap, apply_grid,
-                               s->p->fast_sqrt, s->c->stream);
+            launch_find_first(s->src, s->n, s->state.p, find_grid, st);
+            launch_apply_first(s->src, s->n, s->state.p, s->ticket.p, s->log.p, s->log_cap, apply_grid, st);
             s->c->launches += 2;
         }
         TL_CUDA_TRY(cudaGetLastError());
         return TL_OK;
     }
     for (uint32_t k = 0; k < steps; ++k) {
-        tl_status st = launch_scan(s, true);
-        if (st != TL_OK) return st;
+        if (s->matrix() && s->algo != TL_ALGO_OR_OPT && s->repermute_every > 0 &&
+            s->steps_since_permute >= (uint32_t)s->repermute_every)
+            repermute(s);
+        tl_status rc = launch_scan(s, true);
+        if (rc != TL_OK) return rc;
+        s->steps_since_permute++;
         if (s->algo == TL_ALGO_OR_OPT) {
-            launch_or_apply(s->pts.p, s->tmp.p, s->n, s->cand.p, s->grid * s->shard_count, s->state.p,
-                            s->ticket.p, s->log.p, s->log_cap, apply_grid, s->p->fast_sqrt, s->c->stream);
+            launch_or_apply(s->src, s->tmp.p, s->n, s->cand.p, s->grid * s->shard_count, s->state.p, s->ticket.p,
+                            s->log.p, s->log_cap, apply_grid, st);
             s->c->launches += 2;
             continue;
         }
         if (s->shard_count == 1) continue; // the scan kernel's last CTA applied the move
-        launch_apply_two_opt_recompute(s->pts.p, s->p->fast_sqrt, s->cand.p, s->grid * s->shard_count,
-                                       s->state.p, s->ticket.p, s->log.p, s->log_cap, apply_grid,
-                                       s->c->stream);
+        launch_apply_two_opt(s->src, s->cand.p, s->grid * s->shard_count, s->state.p, s->ticket.p, s->log.p,
+                             s->log_cap, apply_grid, st);
         s->c->launches++;
     }
     TL_CUDA_TRY(cudaGetLastError());
@@ -221,6 +277,31 @@ tl_status close_timing(tl_session *s)
     return TL_OK;
 }
 
+// host-side (delta, rank) reduction of the per-CTA records of one scan
+template <typename V>
+bool reduce_host(const std::vector<Best<V>> &hc, bool or_opt, tl_move *best)
+{
+    Best<V> v{(V)0, 0xffffffffu, 0xffffffffu, 0u};
+    auto rank_less = [&](const Best<V> &a, const Best<V> &b) {
+        if (or_opt && (a.aux >> 1) != (b.aux >> 1)) return (a.aux >> 1) < (b.aux >> 1);
+        if (a.i != b.i) return a.i < b.i;
+        if (a.j != b.j) return a.j < b.j;
+        return (a.aux & 1u) < (b.aux & 1u);
+    };
+    for (const Best<V> &o : hc) {
+        if (o.i == 0xffffffffu) continue;
+        if (v.i == 0xffffffffu || o.delta < v.delta || (o.delta == v.delta && rank_less(o, v))) v = o;
+    }
+    if (v.i == 0xffffffffu) return false;
+    if (best) {
+        if (or_opt)
+            *best = tl_move{(float)v.delta, v.i, v.j, (uint8_t)((v.aux >> 1) + 1), (uint8_t)(v.aux & 1u), 0};
+        else
+            *best = tl_move{(float)v.delta, v.i, v.j, 0, 0, 0};
+    }
+    return true;
+}
+
 } // namespace
 
 extern "C" {
@@ -231,11 +312,19 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     *out = nullptr;
     if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC && algo != TL_ALGO_TWO_OPT_REF &&
         algo != TL_ALGO_OR_OPT) {
-        set_error("tl_session_create: algo %d not available in this build", algo);
-        return TL_ERR_UNSUPPORTED;
+        set_error("tl_session_create: unknown algo %d", algo);
+        return TL_ERR_INVALID;
     }
-    if (path == TL_PATH_MATRIX || p->kind != PK_EUC_F32) {
-        set_error("tl_session_create: only the coordinate-recompute path on F32_EXACT problems is built yet");
+    if (path != TL_PATH_AUTO && path != TL_PATH_MATRIX && path != TL_PATH_RECOMPUTE) {
+        set_error("tl_session_create: unknown path %d", path);
+        return TL_ERR_INVALID;
+    }
+    // AUTO: recompute for f32 coordinate problems (bit-identical to the matrix and no n^2 memory),
+    // matrix for EXPLICIT problems (placeholder coordinates, tsplib.rs:257-262) and the nint metric
+    const bool want_matrix = path == TL_PATH_MATRIX || (path == TL_PATH_AUTO && p->kind != PK_EUC_F32);
+    if (!want_matrix && p->kind != PK_EUC_F32) {
+        set_error(p->kind == PK_EXPLICIT ? "recompute path is illegal for EXPLICIT problems (no coordinates)"
+                                         : "recompute path is not available for the NINT_I32 metric");
         return TL_ERR_UNSUPPORTED;
     }
     if (!tour_is_permutation(tour, p->n)) {
@@ -248,6 +337,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     s->p = p;
     s->c = c;
     s->algo = algo;
+    s->path_used = want_matrix ? TL_PATH_MATRIX : TL_PATH_RECOMPUTE;
     s->n = p->n;
     s->cyclic = algo == TL_ALGO_TWO_OPT_BEST_CYCLIC || algo == TL_ALGO_OR_OPT;
     s->trivial = p->n < 4;
@@ -261,22 +351,22 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         for (uint64_t sg = 1; sg <= 3; ++sg)
             if (n > sg + 1) s->pairs_per_scan += (n - sg + 1) * (n - sg - 1) * (sg > 1 ? 2 : 1);
     }
-    // pad so that every staged window [i0+K0, i0+K0+TI+BW] of a valid row stays in bounds
-    s->npad = p->n + std::max(kScanBW + kScanTI, 32 * kOrR + kOrR) + 64;
+    // pad so that every staged window of a valid row stays in bounds for every kernel
+    s->npad = p->n + std::max(std::max(kScanBW + kScanTI, kMatBW + kMatTI), 32 * kOrR + kOrR) + 64;
 
-    auto fail = [&](tl_status st) {
+    auto fail = [&](tl_status rc) {
         tl_session_destroy(s);
-        return st;
+        return rc;
     };
     DevBuf<uint32_t> d_tour;
-    if (d_tour.alloc(p->n) != cudaSuccess || s->pts.alloc(s->npad) != cudaSuccess ||
-        s->state.alloc(1) != cudaSuccess ||
-        s->ticket.alloc(1) != cudaSuccess || s->log.alloc(s->log_cap) != cudaSuccess ||
-        cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
+    if (d_tour.alloc(p->n) != cudaSuccess || s->state.alloc(1) != cudaSuccess || s->ticket.alloc(1) != cudaSuccess ||
+        s->log.alloc(s->log_cap) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
+        cudaEventCreate(&s->ev1) != cudaSuccess) {
         set_error("tl_session_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(TL_ERR_NOMEM);
     }
-    if (algo == TL_ALGO_OR_OPT && (s->tmp.alloc(s->npad) != cudaSuccess || s->rowinfo.alloc(s->npad) != cudaSuccess)) {
+    if (algo == TL_ALGO_OR_OPT &&
+        (s->tmp.alloc((size_t)s->npad * 16) != cudaSuccess || s->rowinfo.alloc((size_t)s->npad * 16) != cudaSuccess)) {
         set_error("tl_session_create: device allocation failed");
         return fail(TL_ERR_NOMEM);
     }
@@ -290,8 +380,40 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     cudaError_t e = cudaMemcpyAsync(d_tour.p, tour, (size_t)p->n * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->ticket.p, 0, 4, c->stream);
     if (e != cudaSuccess) { set_error("tl_session_create: %s", cudaGetErrorString(e)); return fail(TL_ERR_CUDA); }
-    launch_build_pts(p->d_xy, d_tour.p, p->n, s->npad, s->cyclic, p->fast_sqrt, s->pts.p, c->stream);
-    c->launches++;
+
+    if (want_matrix) {
+        s->ld = (p->n + 31u) & ~31u;
+        const size_t bytes = (size_t)p->n * s->ld * 4;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes > free_b - std::min<size_t>(free_b, (size_t)1 << 30)) {
+            set_error("the %u x %u distance matrix (%.1f GB) does not fit device memory (%.1f GB free); "
+                      "use TL_PATH_RECOMPUTE", p->n, s->ld, bytes / 1e9, free_b / 1e9);
+            return fail(TL_ERR_NOMEM);
+        }
+        bool ok = s->cs.alloc(s->npad) == cudaSuccess && s->M.alloc((size_t)p->n * s->ld) == cudaSuccess;
+        if (p->kind == PK_EXPLICIT)
+            ok = ok && s->slot_city.alloc(p->n) == cudaSuccess;
+        else
+            ok = ok && s->sxy.alloc(p->n) == cudaSuccess;
+        if (!ok) { set_error("tl_session_create: matrix allocation failed"); return fail(TL_ERR_NOMEM); }
+        s->src.kind = p->kind == PK_EUC_NINT ? SRC_MAT_I32 : SRC_MAT_F32;
+        s->src.cs = s->cs.p;
+        s->src.M = s->M.p;
+        s->src.ld = s->ld;
+        build_matrix(s, d_tour.p);
+        launch_build_cs(s->src, d_tour.p, p->n, s->npad, s->cyclic, c->stream);
+        c->launches++;
+        // re-lay the matrix in tour order only when it cannot live in L2 (gathers are cheap there)
+        s->repermute_every = bytes > ((size_t)96 << 20) ? 64 : 0;
+        if (const char *ev = getenv("TL_REPERMUTE_EVERY")) s->repermute_every = atoi(ev);
+    } else {
+        if (s->pts.alloc(s->npad) != cudaSuccess) { set_error("tl_session_create: device allocation failed"); return fail(TL_ERR_NOMEM); }
+        s->src.kind = p->fast_sqrt ? SRC_EUC_FAST : SRC_EUC_SAFE;
+        s->src.pts = s->pts.p;
+        launch_build_pts(p->d_xy, d_tour.p, p->n, s->npad, s->cyclic, p->fast_sqrt, s->pts.p, c->stream);
+        c->launches++;
+    }
     memset(&s->h, 0, sizeof s->h);
     s->h.max_moves = -1;
     s->h.cur_i = 0;
@@ -306,12 +428,13 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         s->h.scans = algo == TL_ALGO_OR_OPT ? 0 : 1;
         s->h.passes = (p->n == 3) ? 1 : 0;
     }
-    tl_status st = push_state(s); // also waits for d_tour's consumers
-    if (st != TL_OK) return fail(st);
+    tl_status rc = push_state(s); // also waits for d_tour's consumers
+    if (rc != TL_OK) return fail(rc);
     if (!s->trivial && algo != TL_ALGO_TWO_OPT_REF) {
-        st = upload_geometry(s);
-        if (st != TL_OK) return fail(st);
+        rc = upload_geometry(s);
+        if (rc != TL_OK) return fail(rc);
     }
+    if (cudaGetLastError() != cudaSuccess) { set_error("tl_session_create: kernel launch failed"); return fail(TL_ERR_CUDA); }
     *out = s;
     return TL_OK;
 }
@@ -347,40 +470,27 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
     if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_scan: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
     if (s->trivial) return TL_OK;
     DeviceGuard g(s->c->device);
+    tl_status rc = pull_state(s);
+    if (rc != TL_OK) return rc;
     // a scan of a finished session is still a scan: lift the no-op flag for this launch
     const int was_done = s->h.done;
-    if (was_done) { s->h.done = 0; tl_status st = push_state(s); if (st != TL_OK) return st; }
-    tl_status st = launch_scan(s, false);
-    if (st != TL_OK) return st;
+    if (was_done) { s->h.done = 0; rc = push_state(s); if (rc != TL_OK) return rc; }
+    rc = launch_scan(s, false);
+    if (rc != TL_OK) return rc;
     TL_CUDA_TRY(cudaGetLastError());
     std::vector<BestF> hc((size_t)s->grid * s->shard_count);
     TL_CUDA_TRY(cudaMemcpyAsync(hc.data(), s->cand.p, hc.size() * sizeof(BestF), cudaMemcpyDeviceToHost, s->c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(s->c->stream));
-    if (was_done) { s->h.done = was_done; st = push_state(s); if (st != TL_OK) return st; }
-    BestF v{0.0f, 0xffffffffu, 0xffffffffu, 0u};
-    if (s->algo == TL_ALGO_OR_OPT) {
-        auto rank_less = [](const BestF &a, const BestF &b) {
-            if ((a.aux >> 1) != (b.aux >> 1)) return (a.aux >> 1) < (b.aux >> 1);
-            if (a.i != b.i) return a.i < b.i;
-            if (a.j != b.j) return a.j < b.j;
-            return (a.aux & 1u) < (b.aux & 1u);
-        };
-        for (const BestF &o : hc) {
-            if (o.i == 0xffffffffu) continue;
-            if (v.i == 0xffffffffu || o.delta < v.delta || (o.delta == v.delta && rank_less(o, v))) v = o;
-        }
-        if (v.i != 0xffffffffu) {
-            *found = 1;
-            if (best) *best = tl_move{v.delta, v.i, v.j, (uint8_t)((v.aux >> 1) + 1), (uint8_t)(v.aux & 1u), 0};
-        }
-        return TL_OK;
+    if (was_done) { s->h.done = was_done; rc = push_state(s); if (rc != TL_OK) return rc; }
+    bool any;
+    if (s->src.is_int()) {
+        std::vector<BestI> hi(hc.size());
+        memcpy(hi.data(), hc.data(), hc.size() * sizeof(BestF));
+        any = reduce_host(hi, s->algo == TL_ALGO_OR_OPT, best);
+    } else {
+        any = reduce_host(hc, s->algo == TL_ALGO_OR_OPT, best);
     }
-    for (const BestF &o : hc)
-        if (o.delta < v.delta || (o.delta == v.delta && (o.i < v.i || (o.i == v.i && o.j < v.j)))) v = o;
-    if (v.i != 0xffffffffu) {
-        *found = 1;
-        if (best) *best = tl_move{v.delta, v.i, v.j, 0, 0, 0};
-    }
+    *found = any ? 1 : 0;
     return TL_OK;
 }
 
@@ -391,17 +501,17 @@ tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
     *avg_ms = 0.0;
     if (s->trivial) return TL_OK;
     DeviceGuard g(s->c->device);
-    tl_status st = pull_state(s);
-    if (st != TL_OK) return st;
+    tl_status rc = pull_state(s);
+    if (rc != TL_OK) return rc;
     const int was_done = s->h.done;
-    if (was_done) { s->h.done = 0; st = push_state(s); if (st != TL_OK) return st; }
+    if (was_done) { s->h.done = 0; rc = push_state(s); if (rc != TL_OK) return rc; }
     cudaEvent_t a, b;
     TL_CUDA_TRY(cudaEventCreate(&a));
     TL_CUDA_TRY(cudaEventCreate(&b));
-    st = launch_scan(s, false); // warm
-    if (st == TL_OK) {
+    rc = launch_scan(s, false); // warm
+    if (rc == TL_OK) {
         cudaEventRecord(a, s->c->stream);
-        for (uint32_t r = 0; r < reps && st == TL_OK; ++r) st = launch_scan(s, false);
+        for (uint32_t r = 0; r < reps && rc == TL_OK; ++r) rc = launch_scan(s, false);
         cudaEventRecord(b, s->c->stream);
         cudaEventSynchronize(b);
         float ms = 0.f;
@@ -410,10 +520,10 @@ tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);
-    if (st != TL_OK) return st;
+    if (rc != TL_OK) return rc;
     TL_CUDA_TRY(cudaGetLastError());
-    if (was_done) { s->h.done = was_done; st = push_state(s); }
-    return st;
+    if (was_done) { s->h.done = was_done; rc = push_state(s); }
+    return rc;
 }
 
 tl_status tl_session_enqueue(tl_session *s, uint32_t steps)
@@ -427,20 +537,21 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
 {
     if (!s) { set_error("tl_session_run: null session"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c->device);
-    tl_status st = pull_state(s);
-    if (st != TL_OK) return st;
+    tl_status rc = pull_state(s);
+    if (rc != TL_OK) return rc;
     if (s->trivial || s->h.converged) return close_timing(s);
     s->h.max_moves = max_moves;
     s->h.done = (max_moves >= 0 && (long long)s->h.moves >= max_moves) ? 1 : 0;
-    st = push_state(s);
-    if (st != TL_OK) return st;
+    rc = push_state(s);
+    if (rc != TL_OK) return rc;
     while (!s->h.done) {
         uint32_t batch = s->algo == TL_ALGO_TWO_OPT_REF ? 64 : 16;
-        if (max_moves >= 0 && s->algo != TL_ALGO_TWO_OPT_REF) batch = (uint32_t)std::min<int64_t>(batch, std::max<int64_t>(1, max_moves - (int64_t)s->h.moves));
-        st = enqueue_steps(s, batch);
-        if (st != TL_OK) return st;
-        st = pull_state(s);
-        if (st != TL_OK) return st;
+        if (max_moves >= 0 && s->algo != TL_ALGO_TWO_OPT_REF)
+            batch = (uint32_t)std::min<int64_t>(batch, std::max<int64_t>(1, max_moves - (int64_t)s->h.moves));
+        rc = enqueue_steps(s, batch);
+        if (rc != TL_OK) return rc;
+        rc = pull_state(s);
+        if (rc != TL_OK) return rc;
     }
     return close_timing(s);
 }
@@ -449,11 +560,9 @@ tl_status tl_session_tour(tl_session *s, uint32_t *tour_out)
 {
     if (!s || !tour_out) { set_error("tl_session_tour: null argument"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c->device);
-    tl_status st = pull_state(s);
-    if (st != TL_OK) return st;
     DevBuf<uint32_t> d;
     TL_CUDA_TRY(d.alloc(s->n));
-    launch_extract_tour(s->pts.p, s->n, d.p, s->c->stream);
+    launch_extract_tour(s->src, s->n, d.p, s->c->stream);
     s->c->launches++;
     TL_CUDA_TRY(cudaGetLastError());
     TL_CUDA_TRY(cudaMemcpyAsync(tour_out, d.p, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->c->stream));
@@ -465,15 +574,16 @@ tl_status tl_session_stats(tl_session *s, tl_stats *stats)
 {
     if (!s || !stats) { set_error("tl_session_stats: null argument"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c->device);
-    tl_status st = pull_state(s);
-    if (st != TL_OK) return st;
-    st = close_timing(s);
-    if (st != TL_OK) return st;
+    tl_status rc = pull_state(s);
+    if (rc != TL_OK) return rc;
+    rc = close_timing(s);
+    if (rc != TL_OK) return rc;
     memset(stats, 0, sizeof *stats);
     stats->passes = s->algo == TL_ALGO_TWO_OPT_REF ? s->h.passes : s->h.scans;
     stats->moves = s->h.moves;
     stats->evals = stats->passes * s->pairs_per_scan;
     stats->launches = s->c->launches - s->launches0;
+    stats->repermutes = s->repermutes;
     stats->device_ms = s->device_ms;
     stats->converged = s->h.converged;
     stats->path_used = s->path_used;
@@ -484,8 +594,8 @@ tl_status tl_session_log(tl_session *s, tl_move *log, size_t log_cap, size_t *n_
 {
     if (!s || !n_out) { set_error("tl_session_log: null argument"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c->device);
-    tl_status st = pull_state(s);
-    if (st != TL_OK) return st;
+    tl_status rc = pull_state(s);
+    if (rc != TL_OK) return rc;
     const size_t have = (size_t)std::min<uint64_t>(s->h.moves, s->log_cap);
     const size_t cnt = std::min(have, log_cap);
     if (cnt && log) {
@@ -501,8 +611,8 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
 {
     if (!p || !tour_inout) { set_error("tl_local_search: null argument"); return TL_ERR_INVALID; }
     tl_session *s = nullptr;
-    tl_status st = tl_session_create(p, algo, path, tour_inout, &s);
-    if (st != TL_OK) return st;
+    tl_status rc = tl_session_create(p, algo, path, tour_inout, &s);
+    if (rc != TL_OK) return rc;
     if (log && log_cap > s->log_cap) {
         DeviceGuard g(s->c->device);
         if (s->log.alloc(log_cap) != cudaSuccess) {
@@ -512,15 +622,15 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
         }
         s->log_cap = log_cap;
     }
-    st = tl_session_run(s, max_moves);
-    if (st == TL_OK) st = tl_session_tour(s, tour_inout);
-    if (st == TL_OK && stats) st = tl_session_stats(s, stats);
-    if (st == TL_OK && log) {
+    rc = tl_session_run(s, max_moves);
+    if (rc == TL_OK) rc = tl_session_tour(s, tour_inout);
+    if (rc == TL_OK && stats) rc = tl_session_stats(s, stats);
+    if (rc == TL_OK && log) {
         size_t got = 0;
-        st = tl_session_log(s, log, log_cap, &got);
+        rc = tl_session_log(s, log, log_cap, &got);
     }
     tl_session_destroy(s);
-    return st;
+    return rc;
 }
 
 // ---- not built yet -----------------------------------------------------------------

@@ -401,3 +401,142 @@ def test_or_opt_scan_only_10k(T, ctx):
     got, want = s.scan(), O.or_opt_find_best(P, t)
     assert got is not None and got[1:] == want[1:] and np.float32(got[0]) == np.float32(want[0])
     s.close()
+
+
+# ---- matrix-backed path: f32 matrix, TSPLIB nint int32 matrix, EXPLICIT problems -------------------
+
+def read_explicit(path):
+    """EXPLICIT TSPLIB -> packed strict lower triangle (tsplib.rs:264-318)."""
+    meta, toks, on = {}, [], False
+    for line in open(path):
+        s = line.strip().upper()
+        if s == "EOF":
+            break
+        if s.endswith("_SECTION"):
+            on = s == "EDGE_WEIGHT_SECTION"
+            continue
+        if on:
+            toks += [float(t) for t in s.split()]
+        elif ":" in s:
+            k, v = s.split(":", 1)
+            meta[k.strip()] = v.strip()
+    n, fmt = int(meta["DIMENSION"]), meta["EDGE_WEIGHT_FORMAT"]
+    if fmt == "FULL_MATRIX":
+        m = np.array(toks, dtype=np.float32).reshape(n, n)
+    elif fmt == "LOWER_DIAG_ROW":
+        m = np.zeros((n, n), dtype=np.float32)
+        k = 0
+        for i in range(n):
+            for j in range(i + 1):
+                m[i, j] = toks[k]
+                k += 1
+    else:
+        raise ValueError(fmt)
+    return n, np.array([m[i, j] for i in range(1, n) for j in range(i)], dtype=np.float32)
+
+
+ALGOS = ["best", "cyclic", "ref", "oropt"]
+
+
+def run_both(T, prob, P, algo, start, path, max_moves=-1):
+    code = {"best": T.ALGO_TWO_OPT_BEST, "cyclic": T.ALGO_TWO_OPT_BEST_CYCLIC, "ref": T.ALGO_TWO_OPT_REF,
+            "oropt": T.ALGO_OR_OPT}[algo]
+    if algo in ("best", "cyclic"):
+        want = O.two_opt_best(P, start, cyclic=algo == "cyclic", max_moves=max_moves, nthreads=4, log_cap=1 << 16)
+    elif algo == "ref":
+        want = O.two_opt_ref(P, start, log_cap=1 << 16)
+    else:
+        want = O.or_opt(P, start, max_moves=max_moves, log_cap=1 << 16)
+    got_t, st, mv = prob.local_search(code, start, path=path, max_moves=-1 if algo == "ref" else max_moves,
+                                      log_cap=1 << 16)
+    want_t, want_st, want_mv = want
+    assert [m[1:] for m in mv] == [m[1:] for m in want_mv], algo
+    assert [np.float32(m[0]) for m in mv] == [np.float32(m[0]) for m in want_mv], algo
+    assert (got_t.astype(np.int64) == want_t).all(), algo
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals), algo
+    return st
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_matrix_path_f32_equals_recompute_and_oracle(T, ctx, berlin52, algo):
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    st = run_both(T, T.Problem.euc2d(ctx, x, y), P, algo, O.nn_tour(P, 3), T.PATH_MATRIX)
+    assert st.path_used == T.PATH_MATRIX
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("n", [4, 7, 258, 700])
+def test_matrix_path_f32_synthetic(T, ctx, algo, n):
+    x, y = O.gen_uniform(n, 400 + n)
+    run_both(T, T.Problem.euc2d(ctx, x, y), O.Problem(x, y), algo, O.shuffle_tour(n, n), T.PATH_MATRIX, max_moves=150)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_nint_i32_matrix_path(T, ctx, algo):
+    """TSPLIB nint metric: exact integer deltas, plenty of ties."""
+    n = 600
+    gx, gy = O.gen_grid(n, 77)
+    P = O.Problem(tri=O.matrix_packed_nint(gx, gy), n=n)
+    prob = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32)
+    st = run_both(T, prob, P, algo, O.shuffle_tour(n, 5), T.PATH_AUTO, max_moves=200)
+    assert st.path_used == T.PATH_MATRIX
+
+
+def test_nint_berlin52_known_optimum(T, ctx, berlin52, golden_dir):
+    ids, x, y = berlin52
+    P = O.Problem(tri=O.matrix_packed_nint(x, y), n=52)
+    prob = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32)
+    for algo in ALGOS:
+        run_both(T, prob, P, algo, O.nn_tour(P, 3), T.PATH_AUTO)
+
+
+@pytest.mark.parametrize("name", ["gr17.tsp", "ring6_explicit.tsp"])
+@pytest.mark.parametrize("algo", ALGOS)
+def test_explicit_problems(T, ctx, golden_dir, name, algo):
+    n, tri = read_explicit(os.path.join(golden_dir, name))
+    P = O.Problem(tri=tri, n=n)
+    prob = T.Problem.explicit(ctx, tri, n)
+    run_both(T, prob, P, algo, np.arange(n), T.PATH_AUTO)
+    run_both(T, prob, P, algo, O.shuffle_tour(n, 3), T.PATH_AUTO)
+    with pytest.raises(T.TeelineError):  # no coordinates: the recompute path is illegal
+        prob.local_search(T.ALGO_TWO_OPT_BEST, np.arange(n), path=T.PATH_RECOMPUTE)
+
+
+def test_ring6_explicit_reaches_known_optimum(T, ctx, golden_dir):
+    n, tri = read_explicit(os.path.join(golden_dir, "ring6_explicit.tsp"))
+    prob = T.Problem.explicit(ctx, tri, n)
+    t, _, _ = prob.local_search(T.ALGO_TWO_OPT_BEST_CYCLIC, [0, 2, 4, 1, 3, 5])
+    t, _, _ = prob.local_search(T.ALGO_OR_OPT, t)
+    assert prob.tour_lengths(t)[0] <= 240.0
+
+
+def test_matrix_path_repermutation_keeps_results(T, ctx, monkeypatch):
+    """Re-laying the matrix in tour order must not change a single move."""
+    n = 1500
+    x, y = O.gen_uniform(n, 31)
+    P = O.Problem(x, y)
+    start = O.shuffle_tour(n, 8)
+    want_t, want_st, want_mv = O.two_opt_best(P, start, max_moves=90, nthreads=4, log_cap=1 << 12)
+    monkeypatch.setenv("TL_REPERMUTE_EVERY", "7")
+    prob = T.Problem.euc2d(ctx, x, y)
+    got_t, st, mv = prob.local_search(T.ALGO_TWO_OPT_BEST, start, path=T.PATH_MATRIX, max_moves=90, log_cap=1 << 12)
+    assert int(st.repermutes) >= 10
+    assert [m[1:] for m in mv] == [m[1:] for m in want_mv] and (got_t.astype(np.int64) == want_t).all()
+
+
+def test_matrix_scan_only_10k_f32_and_i32(T, ctx):
+    n = 10000
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    t = O.shuffle_tour(n, 2)
+    s = T.Problem.euc2d(ctx, x, y).session(T.ALGO_TWO_OPT_BEST, t, T.PATH_MATRIX)
+    got, want = s.scan(), O.two_opt_best_scan(P, t, nthreads=8)
+    assert got is not None and got[1:3] == want[1:3] and np.float32(got[0]) == np.float32(want[0])
+    s.close()
+    gx, gy = O.gen_grid(n, n)
+    Pi = O.Problem(tri=O.matrix_packed_nint(gx, gy), n=n)
+    s = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32).session(T.ALGO_TWO_OPT_BEST, t, T.PATH_AUTO)
+    got, want = s.scan(), O.two_opt_best_scan(Pi, t, nthreads=8)
+    assert got is not None and got[1:3] == want[1:3] and got[0] == want[0]
+    s.close()
