@@ -61,6 +61,13 @@ def gen_uniform(n: int, seed: int):
     return np.ascontiguousarray(xy[0::2]), np.ascontiguousarray(xy[1::2])
 
 
+def gen_grid(n: int, seed: int):
+    """Integer grid floor(u * 10^6) from the same stream (NINT_I32 workloads; oracle: tlo_gen_grid)."""
+    u = (splitmix64_stream(seed, 2 * n) >> np.uint64(40)).astype(np.float64)
+    g = np.floor(u / 16777216.0 * 1.0e6).astype(np.float32)
+    return np.ascontiguousarray(g[0::2]), np.ascontiguousarray(g[1::2])
+
+
 def shuffle_tour(n: int, seed: int) -> np.ndarray:
     """Fisher-Yates driven by splitmix64(seed) (oracle: tlo_shuffle_tour)."""
     r = splitmix64_stream(seed, n - 1)

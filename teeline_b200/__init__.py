@@ -152,6 +152,8 @@ class Problem:
 
     def two_opt_batch(self, tours, algo: int = ALGO_TWO_OPT_BEST, max_moves: int = -1):
         t = _u32(tours).copy()
+        if t.ndim != 2 or t.shape[1] != self.n:
+            raise ValueError("tours must be batch x n")
         st = Stats()
         lengths = np.empty(t.shape[0], dtype=np.float32)
         capi.check(self._lib.tl_two_opt_batch(self.h, algo, capi.ptr(t), t.shape[0], max_moves,

@@ -149,6 +149,18 @@ void launch_gather_slots(const float2 *xy, const uint32_t *tour, const Cs *cs, u
                          int32_t *slot_city, cudaStream_t st);
 void launch_reset_slots(const Src &src, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st);
 
+// K2-batch: one CTA per tour, tour records in shared memory
+constexpr int kBatchR = 5;              // diagonals per thread group (odd => conflict-free LDS.128)
+constexpr int kBatchMaxThreads = 256;
+constexpr int kBatchMaxSmem = 200 * 1024;
+size_t two_opt_batch_smem_bytes(uint32_t n);
+size_t two_opt_batch_counter_bytes();
+cudaError_t two_opt_batch_configure();
+int two_opt_batch_grid(uint32_t n, uint64_t batch, int sm_count, bool fast);
+// counters: {u64 moves, u64 scans, u32 next_tour, u32 unconverged}, zeroed by the caller
+void launch_two_opt_batch(const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
+                          long long max_moves, void *counters, int grid, bool fast, cudaStream_t st);
+
 // K4
 void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, const uint32_t *tours,
                              uint64_t batch, bool fast_sqrt, bool fast_mode, float *out, int sm_count,

@@ -24,6 +24,7 @@ cudaError_t configure_all_kernels()
     if (e == cudaSuccess) e = nn_tour_configure();
     if (e == cudaSuccess) e = or_scan_configure();
     if (e == cudaSuccess) e = scan_matrix_configure();
+    if (e == cudaSuccess) e = two_opt_batch_configure();
     return e;
 }
 
@@ -633,12 +634,88 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
     return rc;
 }
 
-// ---- not built yet -----------------------------------------------------------------
+// ---- batched multi-start 2-opt (GA / multi-start populations) ----------------------------------
 
-tl_status tl_two_opt_batch(tl_problem *, int32_t, uint32_t *, size_t, int64_t, tl_stats *, float *)
+tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, size_t batch, int64_t max_moves,
+                           tl_stats *stats, float *lengths_out)
 {
-    set_error("tl_two_opt_batch: not built yet");
-    return TL_ERR_UNSUPPORTED;
+    if (!p || (!tours_inout && batch)) { set_error("tl_two_opt_batch: null argument"); return TL_ERR_INVALID; }
+    if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC) {
+        set_error("tl_two_opt_batch: only TL_ALGO_TWO_OPT_BEST[_CYCLIC] is batched");
+        return TL_ERR_UNSUPPORTED;
+    }
+    if (p->kind != PK_EUC_F32) {
+        set_error("tl_two_opt_batch: needs an F32_EXACT coordinate problem");
+        return TL_ERR_UNSUPPORTED;
+    }
+    if (batch > 0xffffffffull) { set_error("tl_two_opt_batch: batch too large"); return TL_ERR_INVALID; }
+    if (two_opt_batch_smem_bytes(p->n) > (size_t)kBatchMaxSmem) {
+        set_error("tl_two_opt_batch: n = %u does not fit one CTA's shared memory; use tl_local_search per tour", p->n);
+        return TL_ERR_UNSUPPORTED;
+    }
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (batch == 0) return TL_OK;
+    for (size_t b = 0; b < batch; ++b) {
+        if (!tour_is_permutation(tours_inout + b * p->n, p->n)) {
+            set_error("tl_two_opt_batch: tour %zu is not a permutation of 0..%u", b, p->n - 1);
+            return TL_ERR_INVALID;
+        }
+    }
+    tl_ctx *c = p->ctx;
+    DeviceGuard g(c->device);
+    const uint32_t n = p->n;
+    const bool cyclic = algo == TL_ALGO_TWO_OPT_BEST_CYCLIC;
+    const uint64_t launches0 = c->launches;
+    DevBuf<uint32_t> d_t;
+    DevBuf<float> d_len;
+    DevBuf<unsigned char> d_ctr;
+    if (d_t.alloc(batch * n) != cudaSuccess || d_len.alloc(batch) != cudaSuccess ||
+        d_ctr.alloc(two_opt_batch_counter_bytes()) != cudaSuccess) {
+        set_error("tl_two_opt_batch: device allocation failed");
+        return TL_ERR_NOMEM;
+    }
+    struct { unsigned long long moves, scans; unsigned int next_tour, unconverged; } h{};
+    cudaEvent_t e0, e1;
+    TL_CUDA_TRY(cudaEventCreate(&e0));
+    TL_CUDA_TRY(cudaEventCreate(&e1));
+    cudaStream_t st = c->stream;
+    cudaError_t e = cudaMemcpyAsync(d_t.p, tours_inout, batch * n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_ctr.p, 0, two_opt_batch_counter_bytes(), st);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+    if (e == cudaSuccess && n >= 4) { // n < 4: nothing to scan, tours come back unchanged
+        const int grid = two_opt_batch_grid(n, batch, c->sm_count, p->fast_sqrt);
+        launch_two_opt_batch(p->d_xy, d_t.p, n, batch, cyclic, max_moves, d_ctr.p, grid, p->fast_sqrt, st);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && lengths_out) {
+        launch_tour_lengths_f32(p->d_xy, nullptr, n, d_t.p, batch, p->fast_sqrt, false, d_len.p, c->sm_count, st);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tours_inout, d_t.p, batch * n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && lengths_out) e = cudaMemcpyAsync(lengths_out, d_len.p, batch * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_ctr.p, sizeof h, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) { set_error("tl_two_opt_batch: %s", cudaGetErrorString(e)); return TL_ERR_CUDA; }
+    if (stats) {
+        const uint64_t nn = n;
+        const uint64_t pairs = n < 4 ? 0 : (cyclic ? nn * (nn - 3) / 2 : (nn - 3) * (nn - 2) / 2);
+        // n < 4 mirrors the single-tour session: one empty scan per tour, converged
+        stats->passes = n < 4 ? batch : h.scans;
+        stats->moves = h.moves;
+        stats->evals = stats->passes * pairs;
+        stats->launches = c->launches - launches0;
+        stats->device_ms = ms;
+        stats->converged = h.unconverged == 0 ? 1 : 0;
+        stats->path_used = TL_PATH_RECOMPUTE;
+    }
+    return TL_OK;
 }
 
 } // extern "C"

@@ -540,3 +540,95 @@ def test_matrix_scan_only_10k_f32_and_i32(T, ctx):
     got, want = s.scan(), O.two_opt_best_scan(Pi, t, nthreads=8)
     assert got is not None and got[1:3] == want[1:3] and got[0] == want[0]
     s.close()
+
+
+# ---- K2-batch: one CTA per tour, whole search in one launch (multi-start / GA population) ------------
+
+def check_batch(T, ctx, x, y, tours, cyclic=False, max_moves=-1):
+    P = O.Problem(x, y)
+    p = T.Problem.euc2d(ctx, x, y)
+    algo = T.ALGO_TWO_OPT_BEST_CYCLIC if cyclic else T.ALGO_TWO_OPT_BEST
+    got, st, lengths = p.two_opt_batch(tours, algo, max_moves=max_moves)
+    moves = passes = evals = 0
+    for b, start in enumerate(tours):
+        want_t, want_st, _ = O.two_opt_best(P, start, cyclic=cyclic, max_moves=max_moves, nthreads=4)
+        assert (got[b].astype(np.int64) == want_t).all(), f"tour {b} differs"
+        assert bits(lengths[b:b + 1])[0] == bits(np.float32(O.tour_length(P, want_t)))[0]
+        moves, passes, evals = moves + want_st.moves, passes + want_st.passes, evals + want_st.evals
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (moves, passes, evals)
+    assert int(st.launches) == 2  # the whole batch is ONE search launch + ONE length launch
+    return got, st
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 8, 12, 13, 14, 33, 100, 331])
+def test_batch_small_n_matches_oracle(T, ctx, n):
+    x, y = O.gen_uniform(n, 500 + n)
+    tours = np.stack([O.shuffle_tour(n, s) for s in range(1, 20)])
+    for cyclic in (False, True):
+        check_batch(T, ctx, x, y, tours, cyclic=cyclic)
+
+
+def test_batch_berlin52_population(T, ctx, berlin52):
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    tours = np.stack([O.nn_tour(P, 3)] + [O.shuffle_tour(52, s) for s in range(1, 300)])
+    got, st = check_batch(T, ctx, x, y, tours)
+    assert st.converged == 1
+    # tour 0 is the nn -> 2-opt(best) result of the single-tour path
+    t1, _, _ = T.Problem.euc2d(ctx, x, y).local_search(T.ALGO_TWO_OPT_BEST, tours[0])
+    assert (got[0] == t1).all()
+
+
+def test_batch_1k_bounded_and_ties(T, ctx):
+    x, y = O.gen_uniform(1000, 1000)
+    tours = np.stack([O.nn_tour(O.Problem(x, y), 3)] + [O.shuffle_tour(1000, s) for s in range(1, 8)])
+    _, st = check_batch(T, ctx, x, y, tours, max_moves=40)
+    assert st.converged == 0
+    rng = np.random.default_rng(3)
+    lx = rng.integers(0, 12, 400).astype(np.float32)
+    ly = rng.integers(0, 12, 400).astype(np.float32)  # lattice: many exactly equal deltas
+    tours = np.stack([O.shuffle_tour(400, s) for s in range(1, 9)])
+    check_batch(T, ctx, lx, ly, tours, max_moves=60)
+    check_batch(T, ctx, lx, ly, tours, cyclic=True, max_moves=60)
+
+
+def test_batch_1k_nn_start_converges_to_survey_probe(T, ctx):
+    x, y = O.gen_uniform(1000, 1000)
+    P = O.Problem(x, y)
+    tours = np.stack([O.nn_tour(P, 3)] * 3)
+    got, st = check_batch(T, ctx, x, y, tours)
+    assert f5(O.tour_length(P, got[0])) == "25282.04297" and int(st.moves) == 3 * 170
+
+
+def test_batch_full_size_properties(T, ctx):
+    """Config 5 shape (1024 tours x 1000 cities, bounded moves): every result is a permutation,
+    no tour got longer, lengths are the exact-order lengths, and a sample matches the oracle."""
+    n, B = 1000, 1024
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    p = T.Problem.euc2d(ctx, x, y)
+    tours = np.stack([O.shuffle_tour(n, s) for s in range(1, B + 1)])
+    before = p.tour_lengths(tours)
+    got, st, lengths = p.two_opt_batch(tours, T.ALGO_TWO_OPT_BEST, max_moves=25)
+    assert (np.sort(got, axis=1) == np.arange(n, dtype=np.uint32)[None, :]).all()
+    assert (lengths < before).all() and int(st.moves) == 25 * B
+    assert (bits(lengths) == bits(p.tour_lengths(got))).all()
+    for b in (0, 511, 1023):
+        want_t, _, _ = O.two_opt_best(P, tours[b], max_moves=25, nthreads=4)
+        assert (got[b].astype(np.int64) == want_t).all()
+
+
+def test_batch_edge_cases(T, ctx):
+    x, y = O.gen_uniform(3, 3)
+    p = T.Problem.euc2d(ctx, x, y)
+    got, st, lengths = p.two_opt_batch(np.array([[2, 0, 1], [0, 1, 2]]), T.ALGO_TWO_OPT_BEST)
+    assert got.tolist() == [[2, 0, 1], [0, 1, 2]] and int(st.moves) == 0 and st.converged == 1
+    x, y = O.gen_uniform(10, 1)
+    p = T.Problem.euc2d(ctx, x, y)
+    with pytest.raises(T.TeelineError):
+        p.two_opt_batch(np.array([[0, 1, 2, 3, 4, 5, 6, 7, 8, 8]]))
+    with pytest.raises(T.TeelineError):
+        p.two_opt_batch(np.arange(10)[None, :], T.ALGO_OR_OPT)
+    pn = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32)
+    with pytest.raises(T.TeelineError):
+        pn.two_opt_batch(np.arange(10)[None, :])
