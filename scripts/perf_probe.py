@@ -24,10 +24,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         s.close()
     print(json.dumps(out))
 else:
-    libs = [None] + sorted(glob.glob(os.path.join(ROOT, "variants", "*.so")))
+    libs = [None, "TL_NO_SCREEN"] + sorted(glob.glob(os.path.join(ROOT, "variants", "*.so")))
     for lib in libs:
         env = dict(os.environ)
-        if lib:
+        if lib == "TL_NO_SCREEN":
+            env["TL_NO_SCREEN"] = "1"
+        elif lib:
             env["TL_LIB"] = lib
         r = subprocess.run([sys.executable, __file__, "child"] + (sys.argv[1:] or ["10000", "100000"]), env=env, capture_output=True, text=True)
         print(os.path.basename(lib) if lib else "default", r.stdout.strip() or r.stderr[-400:], flush=True)

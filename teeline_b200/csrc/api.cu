@@ -94,6 +94,14 @@ static tl_status ctx_create_impl(int32_t device, void *stream, bool own, tl_ctx 
     } else {
         c->stream = reinterpret_cast<cudaStream_t>(stream);
     }
+    {
+        // keep freed blocks in the stream-ordered pool (host.hpp: g_alloc_stream)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaError_t ce = configure_all_kernels();
     if (ce != cudaSuccess) {
         set_error("kernel attribute setup failed: %s", cudaGetErrorString(ce));
@@ -115,7 +123,7 @@ tl_status tl_ctx_create_on_stream(int32_t device, void *cuda_stream, tl_ctx **ou
 void tl_ctx_destroy(tl_ctx *ctx)
 {
     if (!ctx) return;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     if (ctx->nccl_comm) nccl_comm_destroy(ctx->nccl_comm);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -124,7 +132,7 @@ void tl_ctx_destroy(tl_ctx *ctx)
 tl_status tl_ctx_sync(tl_ctx *ctx)
 {
     if (!ctx) { set_error("tl_ctx_sync: null ctx"); return TL_ERR_INVALID; }
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     TL_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return TL_OK;
 }
@@ -143,7 +151,7 @@ tl_status tl_ctx_attach_nccl(tl_ctx *ctx, const uint8_t id[TL_NCCL_ID_BYTES], in
         set_error("tl_ctx_attach_nccl: bad arguments");
         return TL_ERR_INVALID;
     }
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     if (ctx->nccl_comm) { nccl_comm_destroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
     tl_status s = nccl_comm_init(&ctx->nccl_comm, id, rank, world);
     if (s != TL_OK) return s;
@@ -168,21 +176,30 @@ tl_status tl_problem_create_euc2d(tl_ctx *ctx, uint32_t n, const float *x, const
         set_error("unknown dist_kind %d", dist_kind);
         return TL_ERR_INVALID;
     }
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     tl_problem *p = new tl_problem();
     p->ctx = ctx;
     p->n = n;
     p->kind = dist_kind == TL_DIST_NINT_I32 ? PK_EUC_NINT : PK_EUC_F32;
     p->fast_sqrt = coords_allow_fast_sqrt(x, y, n);
+    if (p->fast_sqrt) {
+        double x0 = x[0], x1 = x[0], y0 = y[0], y1 = y[0];
+        for (uint32_t i = 1; i < n; ++i) {
+            x0 = std::min<double>(x0, x[i]); x1 = std::max<double>(x1, x[i]);
+            y0 = std::min<double>(y0, y[i]); y1 = std::max<double>(y1, y[i]);
+        }
+        // |c| < 2^62 keeps this finite in double; 1e-6 covers the f32 roundings of the metric
+        p->dmax = (float)(std::sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0)) * (1.0 + 1e-6));
+    }
     std::vector<float2> h(n);
     for (uint32_t i = 0; i < n; ++i) h[i] = make_float2(x[i], y[i]);
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_xy), sizeof(float2) * n);
+    cudaError_t e = dev_alloc(reinterpret_cast<void **>(&p->d_xy), sizeof(float2) * n);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(p->d_xy, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         set_error("tl_problem_create_euc2d: %s", cudaGetErrorString(e));
-        if (p->d_xy) cudaFree(p->d_xy);
+        if (p->d_xy) dev_free(p->d_xy, ctx->stream);
         delete p;
         return TL_ERR_CUDA;
     }
@@ -195,19 +212,19 @@ tl_status tl_problem_create_explicit(tl_ctx *ctx, uint32_t n, const float *packe
     if (!ctx || !packed_tri || !out) { set_error("tl_problem_create_explicit: null argument"); return TL_ERR_INVALID; }
     *out = nullptr;
     if (n < 2) { set_error("distance matrix requires at least 2 points"); return TL_ERR_INVALID; }
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     const size_t cnt = (size_t)n * (n - 1) / 2;
     tl_problem *p = new tl_problem();
     p->ctx = ctx;
     p->n = n;
     p->kind = PK_EXPLICIT;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_tri), sizeof(float) * cnt);
+    cudaError_t e = dev_alloc(reinterpret_cast<void **>(&p->d_tri), sizeof(float) * cnt);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(p->d_tri, packed_tri, sizeof(float) * cnt, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         set_error("tl_problem_create_explicit: %s", cudaGetErrorString(e));
-        if (p->d_tri) cudaFree(p->d_tri);
+        if (p->d_tri) dev_free(p->d_tri, ctx->stream);
         delete p;
         return e == cudaErrorMemoryAllocation ? TL_ERR_NOMEM : TL_ERR_CUDA;
     }
@@ -218,9 +235,9 @@ tl_status tl_problem_create_explicit(tl_ctx *ctx, uint32_t n, const float *packe
 void tl_problem_destroy(tl_problem *p)
 {
     if (!p) return;
-    DeviceGuard g(p->ctx->device);
-    if (p->d_xy) cudaFree(p->d_xy);
-    if (p->d_tri) cudaFree(p->d_tri);
+    DeviceGuard g(p->ctx);
+    if (p->d_xy) dev_free(p->d_xy, p->ctx->stream);
+    if (p->d_tri) dev_free(p->d_tri, p->ctx->stream);
     delete p;
 }
 
@@ -228,7 +245,7 @@ static tl_status matrix_packed_impl(tl_problem *p, void *out, bool want_int)
 {
     if (!p || !out) { set_error("tl_dist_matrix_packed: null argument"); return TL_ERR_INVALID; }
     tl_ctx *c = p->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     const size_t cnt = (size_t)p->n * (p->n - 1) / 2;
     if (p->kind == PK_EXPLICIT) {
         if (want_int) { set_error("EXPLICIT problems hold f32 distances"); return TL_ERR_UNSUPPORTED; }
@@ -263,7 +280,7 @@ tl_status tl_knn(tl_problem *p, uint32_t k, uint32_t *out)
     if (k == 0) return TL_OK;
     if (k > 32) { set_error("tl_knn: k = %u > 32 is not supported", k); return TL_ERR_UNSUPPORTED; }
     tl_ctx *c = p->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     DevBuf<uint32_t> d;
     if (d.alloc((size_t)p->n * k) != cudaSuccess) { set_error("tl_knn: device allocation failed"); return TL_ERR_NOMEM; }
     launch_knn(p->d_xy, p->d_tri, p->n, k, metric_id(p), d.p, c->stream);
@@ -281,7 +298,7 @@ tl_status tl_nn_tour(tl_problem *p, uint32_t k, uint32_t *tour_out)
     (void)k;
     if (!p || !tour_out) { set_error("tl_nn_tour: null argument"); return TL_ERR_INVALID; }
     tl_ctx *c = p->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     if (nn_tour_smem_bytes(p->n) > 200 * 1024) { set_error("tl_nn_tour: n = %u too large for the visited bitmap", p->n); return TL_ERR_UNSUPPORTED; }
     const uint32_t kk = std::min<uint32_t>(32, p->n - 1);
     DevBuf<uint32_t> d_knn, d_tour;
@@ -307,7 +324,7 @@ tl_status tl_tour_lengths(tl_problem *p, const uint32_t *tours, size_t batch, in
     if (p->kind == PK_EUC_NINT) { set_error("NINT_I32 problem: use tl_tour_lengths_i64"); return TL_ERR_UNSUPPORTED; }
     if (batch == 0) return TL_OK;
     tl_ctx *c = p->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     DevBuf<uint32_t> d_t;
     DevBuf<float> d_o;
     if (d_t.alloc(batch * p->n) != cudaSuccess || d_o.alloc(batch) != cudaSuccess) {
@@ -330,7 +347,7 @@ tl_status tl_tour_lengths_i64(tl_problem *p, const uint32_t *tours, size_t batch
     if (p->kind != PK_EUC_NINT) { set_error("tl_tour_lengths_i64 needs a NINT_I32 problem"); return TL_ERR_UNSUPPORTED; }
     if (batch == 0) return TL_OK;
     tl_ctx *c = p->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     DevBuf<uint32_t> d_t;
     DevBuf<long long> d_o;
     if (d_t.alloc(batch * p->n) != cudaSuccess || d_o.alloc(batch) != cudaSuccess) {
@@ -351,7 +368,7 @@ tl_status tl_tour_lengths_i64(tl_problem *p, const uint32_t *tours, size_t batch
 tl_status tl_selftest_sqrt(tl_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches)
 {
     if (!ctx || !mismatches || hi_bits < lo_bits) { set_error("tl_selftest_sqrt: bad arguments"); return TL_ERR_INVALID; }
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     DevBuf<unsigned long long> d;
     TL_CUDA_TRY(d.alloc(1));
     TL_CUDA_TRY(cudaMemsetAsync(d.p, 0, 8, ctx->stream));
@@ -368,7 +385,7 @@ tl_status tl_selftest_sqrt(tl_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint
 tl_status tl_microbench_fp32(tl_ctx *ctx, double *ffma_per_s, double *mufu_per_s)
 {
     if (!ctx || !ffma_per_s || !mufu_per_s) { set_error("tl_microbench_fp32: null argument"); return TL_ERR_INVALID; }
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     DevBuf<float> sink;
     TL_CUDA_TRY(sink.alloc(1));
     cudaEvent_t e0, e1;

@@ -5,7 +5,8 @@ namespace tl {
 
 namespace {
 
-// sqrt_rn_fast == sqrt_rn_safe for every bit pattern in [lo, hi]
+// sqrt_rn_fast == sqrt_rn_safe for every bit pattern in [lo, hi], and the screening sqrt stays
+// within 2^-22 relative of the exact one (the bound the scan kernels' filter margin is built on)
 __global__ void __launch_bounds__(256)
     selftest_sqrt_kernel(uint32_t lo, uint32_t hi, unsigned long long *mismatch)
 {
@@ -16,6 +17,22 @@ __global__ void __launch_bounds__(256)
         const float x = __uint_as_float(lo + (uint32_t)t);
         const float a = sqrt_rn_fast(x), b = sqrt_rn_safe(x);
         bad += (__float_as_uint(a) != __float_as_uint(b));
+        if (x > 0.0f) { // screening sqrt: within 2^-22 of the exact one (common.cuh)
+            const double sc = (double)sqrt_screen_pos(x);
+            bad += !(fabs(sc - (double)b) <= (double)b * (1.0 / 4194304.0));
+        }
+        // screening distance on a pseudo-random coordinate pair derived from the bit pattern
+        uint32_t h = (lo + (uint32_t)t) * 2654435761u;
+        float c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            c[k] = (float)(h >> 8) * (1.0f / 16384.0f); // [0, 1024) on a 2^-14 grid
+        }
+        if ((t & 7) == 0) { c[2] = c[0]; c[3] = c[1]; } // coincident points
+        const float de = dist_f32<true>(c[0], c[1], c[2], c[3]);
+        const double ds = (double)dist_f32_screen(c[0], c[1], c[2], c[3]);
+        bad += !(fabs(ds - (double)de) <= (double)de * (1.54 / 4194304.0) + 8.9e-16);
     }
     if (bad) atomicAdd(mismatch, bad);
 }

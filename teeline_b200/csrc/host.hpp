@@ -30,23 +30,45 @@ struct tl_problem {
     uint32_t n = 0;
     ProblemKind kind = PK_EUC_F32;
     bool fast_sqrt = false; // coordinates guarantee dx^2+dy^2 in {0} U [2^-101, FLT_MAX]
+    float dmax = 0.0f;      // upper bound on any city-to-city distance (bounding-box diagonal, rounded up)
     float2 *d_xy = nullptr; // city-ordered coordinates (coordinate problems)
     float *d_tri = nullptr; // packed triangle (EXPLICIT problems)
 };
 
 namespace tl {
 
+// Stream that device allocations made by the calling host thread are ordered on: the stream of
+// the context whose entry point is executing (set by DeviceGuard).  All device memory comes from
+// the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync; release threshold raised in
+// tl_ctx_create so freed blocks are reused instead of returned to the driver): a local-search
+// call makes ~10 allocations, and cudaMalloc/cudaFree would cost more than the search itself.
+inline thread_local cudaStream_t g_alloc_stream = nullptr;
+
+inline cudaError_t dev_alloc(void **p, size_t bytes) { return cudaMallocAsync(p, bytes, g_alloc_stream); }
+inline void dev_free(void *p, cudaStream_t st) { cudaFreeAsync(p, st); }
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
-    explicit DeviceGuard(int dev)
+    cudaStream_t prev_stream = nullptr;
+    explicit DeviceGuard(int dev) { enter(dev); prev_stream = g_alloc_stream; }
+    explicit DeviceGuard(const tl_ctx *c)
     {
-        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        enter(c->device);
+        prev_stream = g_alloc_stream;
+        g_alloc_stream = c->stream;
     }
     ~DeviceGuard()
     {
+        g_alloc_stream = prev_stream;
         if (prev >= 0) cudaSetDevice(prev);
+    }
+
+  private:
+    void enter(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
     }
 };
 
@@ -54,16 +76,18 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t count = 0;
+    cudaStream_t st = nullptr; // stream the block was allocated on (and is freed on)
     cudaError_t alloc(size_t c)
     {
         release();
         count = c;
         if (c == 0) return cudaSuccess;
-        return cudaMalloc(reinterpret_cast<void **>(&p), c * sizeof(T));
+        st = g_alloc_stream;
+        return dev_alloc(reinterpret_cast<void **>(&p), c * sizeof(T));
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) dev_free(p, st);
         p = nullptr;
         count = 0;
     }

@@ -62,7 +62,48 @@ __device__ __forceinline__ int find_band(const int32_t *__restrict__ band_first,
     return lo;
 }
 
+// Tail of a fused step, run by the last CTA of the scan: reduce the per-CTA records, reverse the
+// segment in place, update the loop state.  Kept out of line so that its registers (the batched
+// reversal holds 8 records) do not weigh on the scan loop's allocation.
 template <bool FAST>
+__device__ __noinline__ void fused_apply_tail(Pt *__restrict__ pts, const BestF *__restrict__ blockbest, BestF *red,
+                                              DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
+                                              uint64_t log_cap)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __threadfence();
+    StateHeader hdr{};
+    if (threadIdx.x == 0) hdr = load_state_header(state); // in flight with the candidate loads
+    BestF v{0.0f, 0xffffffffu, 0xffffffffu, 0u};
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+        // L2 read: the records were written by other CTAs of this launch
+        const float4 raw = __ldcg(reinterpret_cast<const float4 *>(blockbest) + c);
+        const BestF o{raw.x, __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    warp_argmin_2opt(v.delta, v.i, v.j);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    v = red[0];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) {
+        const BestF o = red[w];
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    const bool found = v.i != 0xffffffffu;
+    if (found) reverse_segment_inplace(EucPol<FAST>{pts}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        finish_best_step(state, hdr, found, v.delta, v.i, v.j, log, log_cap);
+    }
+}
+
+// SCREEN (FAST only): the hot loop evaluates deltas with the screening distance (no Newton step,
+// 3 FP32 instructions fewer per move); a row step whose smallest screened delta is within the
+// rigorous error margin of the running best is re-evaluated exactly, so every value that is
+// compared, selected or returned is the exact f32 delta (common.cuh: dist_f32_screen).
+template <bool FAST, bool SCREEN>
 __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
     two_opt_scan_recompute_kernel(Pt *__restrict__ pts, const ScanGeom g,
                                   const int32_t *__restrict__ band_first, BestF *__restrict__ blockbest,
@@ -70,7 +111,9 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
                                   uint64_t log_cap, int fuse_apply)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (state->done) return;
+    // PDL: let the next step's launch start as soon as SMs free up; everything up to
+    // griddep_wait() (barrier set-up, band look-up tables) is independent of the previous step
+    griddep_launch_dependents();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Pt *srow = reinterpret_cast<Pt *>(smem_raw) + warp * WARP_PTS;
@@ -81,18 +124,33 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
 
     if (lane == 0) mbar_init(bar, 1);
     mbar_fence_init();
+    const int total_warps = gridDim.x * WARPS;
+    const int item0 = g.item_begin + blockIdx.x * WARPS + warp;
+    int b_next = 0, bf_next = 0; // band of this warp's first work item (geometry only)
+    if (item0 < g.item_end) {
+        b_next = find_band(band_first, g.nbands, item0);
+        bf_next = __ldg(&band_first[b_next]);
+    }
     __syncthreads();
+    griddep_wait(); // the previous step's move is applied and visible from here on
+    // uniform across the grid: only a fused tail writes it, after every other CTA has finished
+    const int done = *reinterpret_cast<const volatile int *>(&state->done);
+    if (done) return;
 
     uint32_t phase = 0;
     float best = 0.0f;
     uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
+    float thr = SCREEN ? g.screen_margin : 0.0f; // best + margin
 
-    const int total_warps = gridDim.x * WARPS;
-    for (int item = g.item_begin + blockIdx.x * WARPS + warp; item < g.item_end; item += total_warps) {
-        const int b = find_band(band_first, g.nbands, item);
+    for (int item = item0; item < g.item_end; item += total_warps) {
+        if (item != item0) {
+            b_next = find_band(band_first, g.nbands, item);
+            bf_next = __ldg(&band_first[b_next]);
+        }
+        const int b = b_next;
         const int K0 = 2 + b * BW;
         const int H = g.jmax - K0 + 1; // rows 0 .. H-1 exist on the band's first diagonal
-        const int r_begin = (item - __ldg(&band_first[b])) * g.chunk;
+        const int r_begin = (item - bf_next) * g.chunk;
         const int r_end = min(r_begin + g.chunk, H);
         const int lane_k0 = K0 + lane * R; // first diagonal of this lane
 
@@ -120,7 +178,7 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const Pt c = scol[lane * R + r];
-                    E[r] = dist_f32<FAST>(rp0.x, rp0.y, c.x, c.y);
+                    E[r] = SCREEN ? dist_f32_screen(rp0.x, rp0.y, c.x, c.y) : dist_f32<FAST>(rp0.x, rp0.y, c.x, c.y);
                     const Pt w = scol[lane * R + r + 1];
                     wx[r] = w.x;
                     wy[r] = w.y;
@@ -137,10 +195,9 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
                 float dl[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
                     const int ph = (r + U) % R;
-                    const float en = dist_f32<FAST>(rp.x, rp.y, wx[ph], wy[ph]);
+                    const float en = SCREEN ? dist_f32_screen(rp.x, rp.y, wx[ph], wy[ph])
+                                            : dist_f32<FAST>(rp.x, rp.y, wx[ph], wy[ph]);
                     const float cur = __fadd_rn(rp.sp, ws[ph]);
                     const float nw = __fadd_rn(E[r], en);
                     dl[r] = __fsub_rn(nw, cur);
@@ -149,17 +206,26 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
                 float m = dl[0];
 #pragma unroll
                 for (int r = 1; r < R; ++r) m = fminf(m, dl[r]);
-                if (m < best) { // rare: an improving move better than this thread's best
+                if (m < thr) { // rare: a move that may beat this thread's best
                     const uint32_t i = (uint32_t)(i0 + tau);
+                    const Pt pi = srow[tau];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const uint32_t j = i + (uint32_t)(lane_k0 + r);
+                        float d = dl[r];
+                        if (SCREEN) { // exact re-evaluation from the staged points
+                            const Pt pj = scol[tau + lane * R + r], pj1 = scol[tau + lane * R + r + 1];
+                            const float e1 = dist_f32<FAST>(pi.x, pi.y, pj.x, pj.y);
+                            const float e2 = dist_f32<FAST>(rp.x, rp.y, pj1.x, pj1.y);
+                            d = __fsub_rn(__fadd_rn(e1, e2), __fadd_rn(rp.sp, pj1.sp));
+                        }
                         // the cyclic neighbourhood excludes (0, n-1): both edges share p_0
                         const bool excluded = g.cyclic && i == 0 && j == (uint32_t)(g.n - 1);
-                        if (dl[r] < best && !excluded) {
-                            best = dl[r];
+                        if (d < best && !excluded) {
+                            best = d;
                             bi = i;
                             bj = j;
+                            thr = SCREEN ? __fadd_rn(best, g.screen_margin) : best;
                         }
                     }
                 }
@@ -201,30 +267,7 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
-    BestF v{0.0f, 0xffffffffu, 0xffffffffu, 0u};
-    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
-        // L2 read: the records were written by other CTAs of this launch
-        const float4 raw = __ldcg(reinterpret_cast<const float4 *>(blockbest) + c);
-        const BestF o{raw.x, __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
-        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
-    }
-    warp_argmin_2opt(v.delta, v.i, v.j);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    v = red[0];
-#pragma unroll
-    for (int w = 1; w < WARPS; ++w) {
-        const BestF o = red[w];
-        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
-    }
-    const bool found = v.i != 0xffffffffu;
-    if (found) reverse_segment_inplace(EucPol<FAST>{pts}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
-    if (threadIdx.x == 0) {
-        *ticket = 0u;
-        finish_best_step(state, found, v.delta, v.i, v.j, log, log_cap);
-    }
+    fused_apply_tail<FAST>(pts, blockbest, red, state, ticket, log, log_cap);
 }
 
 // tour-ordered point records from city coordinates and a tour
@@ -262,13 +305,16 @@ size_t scan_recompute_smem_bytes()
 
 cudaError_t scan_recompute_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(two_opt_scan_recompute_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)scan_recompute_smem_bytes());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(two_opt_scan_recompute_kernel<false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)scan_recompute_smem_bytes());
+    const int bytes = (int)scan_recompute_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(two_opt_scan_recompute_kernel<true, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(two_opt_scan_recompute_kernel<true, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(two_opt_scan_recompute_kernel<false, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
 }
 
 void launch_scan_recompute(Pt *pts, const ScanGeom &g, const int32_t *band_first, BestF *blockbest,
@@ -276,12 +322,21 @@ void launch_scan_recompute(Pt *pts, const ScanGeom &g, const int32_t *band_first
                            bool fuse_apply, int grid, bool fast, cudaStream_t st)
 {
     const size_t smem = scan_recompute_smem_bytes();
-    if (fast)
-        two_opt_scan_recompute_kernel<true><<<grid, WARPS * 32, smem, st>>>(pts, g, band_first, blockbest, state,
-                                                                          ticket, log, log_cap, fuse_apply);
-    else
-        two_opt_scan_recompute_kernel<false><<<grid, WARPS * 32, smem, st>>>(pts, g, band_first, blockbest, state,
-                                                                           ticket, log, log_cap, fuse_apply);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(WARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int fuse = fuse_apply ? 1 : 0;
+    auto kern = (fast && g.screen_margin >= 0.0f) ? two_opt_scan_recompute_kernel<true, true>
+                : fast                           ? two_opt_scan_recompute_kernel<true, false>
+                                                 : two_opt_scan_recompute_kernel<false, false>;
+    cudaLaunchKernelEx(&cfg, kern, pts, g, band_first, blockbest, state, ticket, log, (uint64_t)log_cap, fuse);
 }
 
 void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic,

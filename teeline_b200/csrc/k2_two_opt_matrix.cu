@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
                                uint64_t log_cap, int fuse_apply)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (state->done) return;
+    griddep_launch_dependents(); // PDL, as in k2_two_opt.cu
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per-warp staging of (slot, entering-edge bits) pairs, 8 bytes each => conflict-free LDS.64
     int2 *srow = reinterpret_cast<int2 *>(smem_raw) + warp * WARP_RECS;
@@ -74,12 +74,24 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     V best = (V)0;
     uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
     const int total_warps = gridDim.x * WARPS;
+    const int item0 = g.item_begin + blockIdx.x * WARPS + warp;
+    int b_next = 0, bf_next = 0; // band of this warp's first work item (geometry only)
+    if (item0 < g.item_end) {
+        b_next = find_band_m(band_first, g.nbands, item0);
+        bf_next = __ldg(&band_first[b_next]);
+    }
+    griddep_wait(); // the previous step's move is applied and visible from here on
+    if (*reinterpret_cast<const volatile int *>(&state->done)) return; // grid-uniform
 
-    for (int item = g.item_begin + blockIdx.x * WARPS + warp; item < g.item_end; item += total_warps) {
-        const int b = find_band_m(band_first, g.nbands, item);
+    for (int item = item0; item < g.item_end; item += total_warps) {
+        if (item != item0) {
+            b_next = find_band_m(band_first, g.nbands, item);
+            bf_next = __ldg(&band_first[b_next]);
+        }
+        const int b = b_next;
         const int K0 = 2 + b * BW;
         const int H = g.jmax - K0 + 1;
-        const int r_begin = (item - __ldg(&band_first[b])) * g.chunk;
+        const int r_begin = (item - bf_next) * g.chunk;
         const int r_end = min(r_begin + g.chunk, H);
         const int ntiles = (r_end - r_begin + TI - 1) / TI;
         const int tile_rows = ntiles > 0 ? (r_end - r_begin + ntiles - 1) / ntiles : 0;
@@ -180,6 +192,8 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    StateHeader hdr{};
+    if (threadIdx.x == 0) hdr = load_state_header(state); // in flight with the candidate loads
     Best<V> v{(V)0, 0xffffffffu, 0xffffffffu, 0u};
     for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
         const int4 raw = __ldcg(reinterpret_cast<const int4 *>(blockbest) + c);
@@ -200,7 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     if (found) reverse_segment_inplace(MatPol<V>{cs, M, ld}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0) {
         *ticket = 0u;
-        finish_best_step(state, found, (float)v.delta, v.i, v.j, log, log_cap);
+        finish_best_step(state, hdr, found, (float)v.delta, v.i, v.j, log, log_cap);
     }
 }
 
@@ -273,14 +287,23 @@ void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_f
                         int grid, cudaStream_t st)
 {
     const size_t smem = scan_matrix_smem_bytes();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(WARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int fuse = fuse_apply ? 1 : 0;
     if (src.is_int())
-        two_opt_scan_matrix_kernel<int32_t><<<grid, WARPS * 32, smem, st>>>(
-            (const int32_t *)src.M, src.ld, src.cs, g, band_first, (BestI *)blockbest, state, ticket, log, log_cap,
-            fuse_apply);
+        cudaLaunchKernelEx(&cfg, two_opt_scan_matrix_kernel<int32_t>, (const int32_t *)src.M, src.ld, src.cs, g,
+                           band_first, (BestI *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse);
     else
-        two_opt_scan_matrix_kernel<float><<<grid, WARPS * 32, smem, st>>>(
-            (const float *)src.M, src.ld, src.cs, g, band_first, (BestF *)blockbest, state, ticket, log, log_cap,
-            fuse_apply);
+        cudaLaunchKernelEx(&cfg, two_opt_scan_matrix_kernel<float>, (const float *)src.M, src.ld, src.cs, g,
+                           band_first, (BestF *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse);
 }
 
 void launch_build_cs(const Src &src, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st)

@@ -24,6 +24,7 @@ struct ScanGeom {
     int32_t item_begin; // this launch scans items [item_begin, item_end)
     int32_t item_end;
     int32_t cyclic;
+    float screen_margin; // recompute path: Dmax * kScreenMarginScale, < 0 disables screening
 };
 
 // device-resident loop state, updated by the apply kernels

@@ -12,6 +12,7 @@
 #include "host.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 using namespace tl;
@@ -91,6 +92,12 @@ void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
     g.cyclic = s->cyclic;
     g.jmax = s->cyclic ? n - 1 : n - 2;
     g.kmax = n - 2;
+    // screening needs the fast-sqrt domain and a finite distance bound (common.cuh)
+    const float margin = s->p->dmax * kScreenMarginScale;
+    g.screen_margin = (s->p->fast_sqrt && std::isfinite(margin) && s->p->dmax >= kScreenMinDmax &&
+                       !getenv("TL_NO_SCREEN"))
+                          ? margin
+                          : -1.0f;
     g.nbands = (g.kmax - 2) / bw + 1;
     auto H = [&](int b) { return g.jmax - (2 + b * bw) + 1; };
     // one work item per resident warp, times the shard count so that every rank of a sharded
@@ -333,7 +340,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         return TL_ERR_INVALID;
     }
     tl_ctx *c = p->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     tl_session *s = new tl_session();
     s->p = p;
     s->c = c;
@@ -443,7 +450,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
 void tl_session_destroy(tl_session *s)
 {
     if (!s) return;
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     cudaStreamSynchronize(s->c->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -457,7 +464,7 @@ tl_status tl_session_set_shard(tl_session *s, int32_t index, int32_t count)
         if (count > 1) { set_error("Mode R does not shard (replicas only)"); return TL_ERR_UNSUPPORTED; }
         return TL_OK;
     }
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     s->shard_index = index;
     s->shard_count = count;
     if (s->trivial) return TL_OK;
@@ -470,7 +477,7 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
     *found = 0;
     if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_scan: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
     if (s->trivial) return TL_OK;
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
     if (rc != TL_OK) return rc;
     // a scan of a finished session is still a scan: lift the no-op flag for this launch
@@ -501,7 +508,7 @@ tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
     if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_time_scans: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
     *avg_ms = 0.0;
     if (s->trivial) return TL_OK;
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
     if (rc != TL_OK) return rc;
     const int was_done = s->h.done;
@@ -530,14 +537,14 @@ tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
 tl_status tl_session_enqueue(tl_session *s, uint32_t steps)
 {
     if (!s) { set_error("tl_session_enqueue: null session"); return TL_ERR_INVALID; }
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     return enqueue_steps(s, steps);
 }
 
 tl_status tl_session_run(tl_session *s, int64_t max_moves)
 {
     if (!s) { set_error("tl_session_run: null session"); return TL_ERR_INVALID; }
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
     if (rc != TL_OK) return rc;
     if (s->trivial || s->h.converged) return close_timing(s);
@@ -546,9 +553,10 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
     rc = push_state(s);
     if (rc != TL_OK) return rc;
     while (!s->h.done) {
-        uint32_t batch = s->algo == TL_ALGO_TWO_OPT_REF ? 64 : 16;
-        if (max_moves >= 0 && s->algo != TL_ALGO_TWO_OPT_REF)
-            batch = (uint32_t)std::min<int64_t>(batch, std::max<int64_t>(1, max_moves - (int64_t)s->h.moves));
+        // one host round trip per batch; steps enqueued past convergence are no-op launches
+        uint32_t batch = s->algo == TL_ALGO_TWO_OPT_REF ? 64 : 32;
+        if (max_moves >= 0 && s->algo != TL_ALGO_TWO_OPT_REF) // every step applies exactly one move
+            batch = (uint32_t)std::min<int64_t>(256, std::max<int64_t>(1, max_moves - (int64_t)s->h.moves));
         rc = enqueue_steps(s, batch);
         if (rc != TL_OK) return rc;
         rc = pull_state(s);
@@ -560,7 +568,7 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
 tl_status tl_session_tour(tl_session *s, uint32_t *tour_out)
 {
     if (!s || !tour_out) { set_error("tl_session_tour: null argument"); return TL_ERR_INVALID; }
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     DevBuf<uint32_t> d;
     TL_CUDA_TRY(d.alloc(s->n));
     launch_extract_tour(s->src, s->n, d.p, s->c->stream);
@@ -574,7 +582,7 @@ tl_status tl_session_tour(tl_session *s, uint32_t *tour_out)
 tl_status tl_session_stats(tl_session *s, tl_stats *stats)
 {
     if (!s || !stats) { set_error("tl_session_stats: null argument"); return TL_ERR_INVALID; }
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
     if (rc != TL_OK) return rc;
     rc = close_timing(s);
@@ -594,7 +602,7 @@ tl_status tl_session_stats(tl_session *s, tl_stats *stats)
 tl_status tl_session_log(tl_session *s, tl_move *log, size_t log_cap, size_t *n_out)
 {
     if (!s || !n_out) { set_error("tl_session_log: null argument"); return TL_ERR_INVALID; }
-    DeviceGuard g(s->c->device);
+    DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
     if (rc != TL_OK) return rc;
     const size_t have = (size_t)std::min<uint64_t>(s->h.moves, s->log_cap);
@@ -615,7 +623,7 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
     tl_status rc = tl_session_create(p, algo, path, tour_inout, &s);
     if (rc != TL_OK) return rc;
     if (log && log_cap > s->log_cap) {
-        DeviceGuard g(s->c->device);
+        DeviceGuard g(s->c);
         if (s->log.alloc(log_cap) != cudaSuccess) {
             tl_session_destroy(s);
             set_error("tl_local_search: move log of %zu entries does not fit", log_cap);
@@ -662,7 +670,7 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
         }
     }
     tl_ctx *c = p->ctx;
-    DeviceGuard g(c->device);
+    DeviceGuard g(c);
     const uint32_t n = p->n;
     const bool cyclic = algo == TL_ALGO_TWO_OPT_BEST_CYCLIC;
     const uint64_t launches0 = c->launches;

@@ -21,39 +21,74 @@ __device__ __forceinline__ void reverse_segment_inplace(const Pol &P, uint32_t m
     using Rec = typename Pol::Rec;
     const uint32_t L = mj - mi; // segment mi+1 .. mj, L >= 2
     const uint32_t nxy = L / 2, nsp = (L - 1) / 2;
-    for (uint32_t t = tid; t < nxy; t += nthreads) {
-        const uint32_t a = mi + 1 + t, b = mj - t;
-        const Rec A = P.load(a), B = P.load(b);
-        if (t == 0) {
-            const Rec P0 = P.load(mi), P1 = P.load(mj + 1);
-            const V e1 = P.dist(P0, B); // new edge (p_i, p_j)
-            const V e2 = P.dist(A, P1); // new edge (p_i+1, p_j+1)
-            if (delta_out)
-                *delta_out = (float)Val<V>::sub(Val<V>::add(e1, e2), Val<V>::add(Pol::sp(A), Pol::sp(P1)));
-            P.store_sp(a, e1);
-            P.store_sp(mj + 1, e2);
+    // U swaps per thread per round: all loads of a round are issued before its first store, so a
+    // round costs one memory round trip instead of U (a thread's own records never alias)
+    constexpr int U = 4;
+    Rec P0{}, P1{}; // the segment's outer neighbours, needed by thread 0 only: load them up front
+    if (tid == 0) {
+        P0 = P.load(mi);
+        P1 = P.load(mj + 1);
+    }
+    for (uint32_t t0 = tid; t0 < nxy; t0 += nthreads * U) {
+        Rec A[U], B[U];
+        V sa[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t t = t0 + u * nthreads;
+            if (t < nxy) {
+                A[u] = P.load(mi + 1 + t);
+                B[u] = P.load(mj - t);
+                if (t < nsp) sa[u] = Pol::sp(P.load(mi + 2 + t));
+            }
         }
-        P.store_id(a, B);
-        P.store_id(b, A);
-        if (t < nsp) {
-            const uint32_t a2 = a + 1; // mi+2+t <-> mj-t
-            const V sa = Pol::sp(P.load(a2));
-            P.store_sp(a2, Pol::sp(B));
-            P.store_sp(b, sa);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t t = t0 + u * nthreads;
+            if (t >= nxy) continue;
+            const uint32_t a = mi + 1 + t, b = mj - t;
+            if (t == 0) {
+                const V e1 = P.dist(P0, B[u]); // new edge (p_i, p_j)
+                const V e2 = P.dist(A[u], P1); // new edge (p_i+1, p_j+1)
+                if (delta_out)
+                    *delta_out = (float)Val<V>::sub(Val<V>::add(e1, e2), Val<V>::add(Pol::sp(A[u]), Pol::sp(P1)));
+                P.store_sp(a, e1);
+                P.store_sp(mj + 1, e2);
+            }
+            P.store_id(a, B[u]);
+            P.store_id(b, A[u]);
+            if (t < nsp) { // mi+2+t <-> mj-t
+                P.store_sp(a + 1, Pol::sp(B[u]));
+                P.store_sp(b, sa[u]);
+            }
         }
     }
 }
 
-// Loop-state update after a Mode B step (one thread).
-__device__ __forceinline__ void finish_best_step(DevState *state, bool found, float delta, uint32_t mi,
-                                                 uint32_t mj, tl_move *__restrict__ log, uint64_t log_cap)
+// Loop-state update after a Mode B step (one thread).  The header of DevState,
+// {moves, scans} and {max_moves, done, converged}, is read with two independent 16-byte loads
+// (load_state_header) that the caller issues early, off the critical path.
+struct StateHeader {
+    ulonglong2 h0;
+    longlong2 h1;
+};
+__device__ __forceinline__ StateHeader load_state_header(const DevState *state)
 {
-    state->scans += 1;
+    StateHeader h;
+    h.h0 = __ldcg(reinterpret_cast<const ulonglong2 *>(state));
+    h.h1 = __ldcg(reinterpret_cast<const longlong2 *>(state) + 1);
+    return h;
+}
+__device__ __forceinline__ void finish_best_step(DevState *state, const StateHeader &h, bool found, float delta,
+                                                 uint32_t mi, uint32_t mj, tl_move *__restrict__ log,
+                                                 uint64_t log_cap)
+{
+    const unsigned long long m = h.h0.x;
+    const long long max_moves = h.h1.x;
+    state->scans = h.h0.y + 1;
     if (found) {
-        const unsigned long long m = state->moves;
         if (log && m < log_cap) log[m] = tl_move{delta, mi, mj, 0, 0, 0};
         state->moves = m + 1;
-        if (state->max_moves >= 0 && (long long)(m + 1) >= state->max_moves) state->done = 1;
+        if (max_moves >= 0 && (long long)(m + 1) >= max_moves) state->done = 1;
     } else {
         state->done = 1;
         state->converged = 1;
@@ -95,7 +130,7 @@ __global__ void __launch_bounds__(256)
         const unsigned int tk = atomicAdd(ticket, 1u);
         if (tk == gridDim.x - 1) { // last block: everyone has read `state` by now
             *ticket = 0u;
-            finish_best_step(state, found, (float)v.delta, v.i, v.j, log, log_cap);
+            finish_best_step(state, load_state_header(state), found, (float)v.delta, v.i, v.j, log, log_cap);
             __threadfence();
         }
     }
