@@ -12,8 +12,8 @@
 // diagonals K0 + l + 32 r, r < R, so for fixed r the 32 lanes of a warp read 32 consecutive
 // columns of one matrix row: a single 128-byte request when slot == position.  The (slot, s_j)
 // pairs of the columns are staged per warp in shared memory (compacted to 8 bytes) and read with
-// conflict-free 64-bit LDS; the loads of the next row are issued before the current row is
-// consumed (register double buffer) to keep enough bytes in flight for HBM.
+// conflict-free 64-bit LDS; the loads of row step tau+D are issued when step tau is consumed (a
+// D-deep register ring, rotated by unrolling) to keep enough bytes in flight for HBM.
 //
 // Roofline: HBM bandwidth, 4 B per move.
 #include "kernels.cuh"
@@ -33,6 +33,16 @@ constexpr int WARPS = kMatWarps;
 constexpr int ROWS_CAP = TI + 1;      // positions i0 .. i0+cnt
 constexpr int COLS_CAP = TI + BW + 1; // positions i0+K0 .. i0+K0+cnt+BW
 constexpr int WARP_RECS = ROWS_CAP + COLS_CAP;
+constexpr int D = kMatD;              // row steps of matrix loads kept in flight per thread
+
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (N > 0) {
+        static_for<N - 1>(f);
+        f(std::integral_constant<int, N - 1>{});
+    }
+}
 
 __device__ __forceinline__ int find_band_m(const int32_t *__restrict__ band_first, int nbands, int item)
 {
@@ -54,6 +64,42 @@ __device__ __forceinline__ V ld_stream(const V *p)
     int32_t v;
     asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
     return Val<V>::from_bits(v);
+}
+
+// Tail of a fused step (last CTA only), out of line so that it does not weigh on the scan loop's
+// register allocation: reduce the per-CTA records, reverse the segment, update the loop state.
+template <typename V>
+__device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, uint32_t ld, Cs *__restrict__ cs,
+                                                     const Best<V> *__restrict__ blockbest, Best<V> *red,
+                                                     DevState *state, unsigned int *ticket,
+                                                     tl_move *__restrict__ log, uint64_t log_cap)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __threadfence();
+    StateHeader hdr{};
+    if (threadIdx.x == 0) hdr = load_state_header(state); // in flight with the candidate loads
+    Best<V> v{(V)0, 0xffffffffu, 0xffffffffu, 0u};
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+        const int4 raw = __ldcg(reinterpret_cast<const int4 *>(blockbest) + c);
+        const Best<V> o{Val<V>::from_bits(raw.x), (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    warp_argmin_2opt(v.delta, v.i, v.j);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    v = red[0];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) {
+        const Best<V> o = red[w];
+        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    const bool found = v.i != 0xffffffffu;
+    if (found) reverse_segment_inplace(MatPol<V>{cs, M, ld}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        finish_best_step(state, hdr, found, (float)v.delta, v.i, v.j, log, log_cap);
+    }
 }
 
 template <typename V>
@@ -111,43 +157,37 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
 
             // E[r] = d(p_i, p_j) carried down diagonal k_r = K0 + lane + 32 r; the record of
             // position j+1 at row i0+tau sits at scol[tau + 1 + lane + 32 r].
-            V E[R], nxt[R];
-            int32_t spc[R];
+            // buf[d] holds the matrix elements of row step (tau % D == d), loaded D steps ahead:
+            // D * R independent 4-byte loads per thread stay in flight, which is what it takes to
+            // cover HBM latency at 24 warps per SM (Little: ~40 KB per SM at 6.5 TB/s).
+            V E[R], buf[D][R];
             {
                 const V *row0 = M + (size_t)srow[0].x * ld;
-                const V *row1 = M + (size_t)srow[1].x * ld;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    E[r] = ld_stream(row0 + scol[lane + 32 * r].x);
-                    const int2 c1 = scol[1 + lane + 32 * r];
-                    nxt[r] = ld_stream(row1 + c1.x);
-                    spc[r] = c1.y;
-                }
+                for (int r = 0; r < R; ++r) E[r] = ld_stream(row0 + scol[lane + 32 * r].x);
             }
-#pragma unroll 1
-            for (int tau = 0; tau < cnt; ++tau) {
-                const int2 rp = srow[tau + 1]; // slot of p_i+1 and s_i
+            auto issue = [&](auto Dc, int t) { // loads of row step t into buf[Dc]
+                constexpr int d = decltype(Dc)::value;
+                const V *rown = M + (size_t)srow[t + 1].x * ld;
+#pragma unroll
+                for (int r = 0; r < R; ++r) buf[d][r] = ld_stream(rown + scol[t + 1 + lane + 32 * r].x);
+            };
+            static_for<D>([&](auto Dc) {
+                constexpr int d = decltype(Dc)::value;
+                if (d < cnt) issue(Dc, d);
+            });
+            auto step = [&](auto Dc, int tau) {
+                constexpr int d = decltype(Dc)::value;
                 V en[R];
-                int32_t spn[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    en[r] = nxt[r];
-                    spn[r] = spc[r];
-                }
-                if (tau + 1 < cnt) { // issue the next row's loads before consuming this one
-                    const V *rown = M + (size_t)srow[tau + 2].x * ld;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int2 c2 = scol[tau + 2 + lane + 32 * r];
-                        nxt[r] = ld_stream(rown + c2.x);
-                        spc[r] = c2.y;
-                    }
-                }
-                const V si = Val<V>::from_bits(rp.y);
+                for (int r = 0; r < R; ++r) en[r] = buf[d][r];
+                if (tau + D < cnt) issue(Dc, tau + D); // refill this slot before consuming the row
+                const V si = Val<V>::from_bits(srow[tau + 1].y); // s_i
                 V dl[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const V cur = Val<V>::add(si, Val<V>::from_bits(spn[r]));
+                    const V sj = Val<V>::from_bits(scol[tau + 1 + lane + 32 * r].y);
+                    const V cur = Val<V>::add(si, sj);
                     const V nw = Val<V>::add(E[r], en[r]);
                     dl[r] = Val<V>::sub(nw, cur);
                     E[r] = en[r];
@@ -168,7 +208,13 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
                         }
                     }
                 }
-            }
+            };
+            int t = 0;
+#pragma unroll 1
+            for (; t + D <= cnt; t += D) static_for<D>([&](auto Dc) { step(Dc, t + decltype(Dc)::value); });
+            static_for<D>([&](auto Dc) {
+                if (t + decltype(Dc)::value < cnt) step(Dc, t + decltype(Dc)::value);
+            });
         }
     }
 
@@ -191,31 +237,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
-    StateHeader hdr{};
-    if (threadIdx.x == 0) hdr = load_state_header(state); // in flight with the candidate loads
-    Best<V> v{(V)0, 0xffffffffu, 0xffffffffu, 0u};
-    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
-        const int4 raw = __ldcg(reinterpret_cast<const int4 *>(blockbest) + c);
-        const Best<V> o{Val<V>::from_bits(raw.x), (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
-        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
-    }
-    warp_argmin_2opt(v.delta, v.i, v.j);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    v = red[0];
-#pragma unroll
-    for (int w = 1; w < WARPS; ++w) {
-        const Best<V> o = red[w];
-        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
-    }
-    const bool found = v.i != 0xffffffffu;
-    if (found) reverse_segment_inplace(MatPol<V>{cs, M, ld}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
-    if (threadIdx.x == 0) {
-        *ticket = 0u;
-        finish_best_step(state, hdr, found, (float)v.delta, v.i, v.j, log, log_cap);
-    }
+    fused_apply_tail_matrix<V>(M, ld, cs, blockbest, red, state, ticket, log, log_cap);
 }
 
 // cs[q] = {slot q, entering edge M[slot q-1][slot q], city}; wrap copy at n when cyclic; -inf padding

@@ -136,7 +136,14 @@ constexpr int kMatR = 8;                 // diagonals per lane (strided by 32 =>
 constexpr int kMatBW = 32 * kMatR;
 constexpr int kMatTI = 64;
 constexpr int kMatWarps = 8;
-constexpr int kMatMinBlocks = 3;
+#ifndef TL_MAT_MINB
+#define TL_MAT_MINB 3
+#endif
+constexpr int kMatMinBlocks = TL_MAT_MINB;
+#ifndef TL_MAT_D
+#define TL_MAT_D 2
+#endif
+constexpr int kMatD = TL_MAT_D;          // prefetch depth in row steps
 size_t scan_matrix_smem_bytes();
 cudaError_t scan_matrix_configure();
 void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_first, void *blockbest,
