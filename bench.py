@@ -255,6 +255,31 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     scan_ms = sess.time_scans(max(10, min(args.steps, 200)))
     stats_path = int(st.path_used)
 
+    # --- the matrix-backed paths on the same workload (BASELINE configs[2]: "int32 matrix-backed"):
+    #     f32 matrix of the same instance, and the TSPLIB nint int32 matrix of the integer-grid instance
+    other_paths = {}
+    if rank == 0 and args.workload != "n100k":
+        for label, kind in (("matrix_f32", T.DIST_F32_EXACT), ("matrix_nint_i32", T.DIST_NINT_I32)):
+            if stats_path == T.PATH_MATRIX and kind == T.DIST_F32_EXACT:
+                continue
+            gx, gy = (x, y) if kind == T.DIST_F32_EXACT else gen_grid(n, seed)
+            p2 = T.Problem.euc2d(ctx, gx, gy, kind)
+            s2 = p2.session(T.ALGO_TWO_OPT_BEST, p2.nn_tour(3), T.PATH_MATRIX)
+            s2.enqueue(args.warmup)
+            torch.cuda.synchronize()
+            k = min(args.steps, 100)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            s2.enqueue(k)
+            a1.record()
+            torch.cuda.synchronize()
+            step_ms2 = a0.elapsed_time(a1) / k
+            scan_ms2 = s2.time_scans(k)
+            other_paths[label] = {"ms_per_step": step_ms2, "value": P / (step_ms2 * 1e-3), "kernel_ms": scan_ms2,
+                                  "kernel": "two_opt_scan_matrix_kernel", "scan_moves_per_s": P / (scan_ms2 * 1e-3)}
+            s2.close()
+            p2.close()
+
     # --- end to end through the C ABI with host buffers (pinned), copies inside the timed region
     e2e_moves = args.e2e_moves
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
@@ -299,21 +324,35 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    traffic = {}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+
+    def hbm_roofline(kernel_ms, key):
+        achieved = 4.0 * P / (kernel_ms * 1e-3) / 1e9  # 4 algorithmic bytes per move
+        t = traffic.get(key, {}) if args.workload == "n10k" else {}
+        return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": t.get("bytes_per_launch"), "traffic_source": t.get("source"), "peak_source": peak_src,
+                "kernel": "two_opt_scan_matrix_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_move": 4,
+                "algorithmic_bytes_per_launch": 4 * P}
+
+    for label, o in other_paths.items():
+        o["roofline"] = hbm_roofline(o["kernel_ms"], label)
     if stats_path == T.PATH_MATRIX:
-        achieved = 4.0 * P / (scan_ms * 1e-3) / 1e9  # 4 algorithmic bytes per move
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "kernel": "two_opt_scan_matrix_kernel", "kernel_ms": scan_ms,
-                    "algorithmic_bytes_per_move": 4}
+        roofline = hbm_roofline(scan_ms, "matrix_f32")
     else:
         ffma, mufu = ctx.microbench_fp32()
         flops = 15.0 * P / (scan_ms * 1e-3)  # 13 FP32 ops + 2 sqrt per move
         roofline = {"bound": "fp32_issue", "achieved": flops / 1e12, "peak": ffma / 1e12, "unit": "TFLOP/s",
-                    "frac": flops / ffma, "traffic": None,
+                    "frac": flops / ffma,
                     "peak_source": "measured here: dependent-free FFMA stream, lane-instructions/s "
                                    "(tl_microbench_fp32); MEASURED_PEAKS.json has no FP32 figure",
                     "kernel": "two_opt_scan_recompute_kernel", "kernel_ms": scan_ms,
                     "algorithmic_flop_per_move": 15, "mufu_peak_per_s": mufu,
+                    "traffic": traffic.get("recompute", {}).get("bytes_per_launch") if args.workload == "n10k" else None,
+                    "traffic_source": traffic.get("recompute", {}).get("source"),
                     "note": "coordinate-recompute path: ~0 bytes/move, bound by FP32 issue, not HBM or tensor"}
     roofline["kernel_share_of_step"] = scan_ms / (ms / args.steps)
 
@@ -347,6 +386,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "other_paths": other_paths,
         "moves_applied": real_steps,
     }
     print(json.dumps(line), flush=True)

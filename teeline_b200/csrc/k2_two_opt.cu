@@ -126,10 +126,10 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
     mbar_fence_init();
     const int total_warps = gridDim.x * WARPS;
     const int item0 = g.item_begin + blockIdx.x * WARPS + warp;
-    int b_next = 0, bf_next = 0; // band of this warp's first work item (geometry only)
+    int t_next = 0, tf_next = 0; // table slot of this warp's first work item (geometry only)
     if (item0 < g.item_end) {
-        b_next = find_band(band_first, g.nbands, item0);
-        bf_next = __ldg(&band_first[b_next]);
+        t_next = find_band(band_first, g.ntab, item0);
+        tf_next = __ldg(&band_first[t_next]);
     }
     __syncthreads();
     griddep_wait(); // the previous step's move is applied and visible from here on
@@ -144,13 +144,15 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
 
     for (int item = item0; item < g.item_end; item += total_warps) {
         if (item != item0) {
-            b_next = find_band(band_first, g.nbands, item);
-            bf_next = __ldg(&band_first[b_next]);
+            t_next = find_band(band_first, g.ntab, item);
+            tf_next = __ldg(&band_first[t_next]);
         }
-        const int b = b_next;
+        // chunk major: slot = row chunk, offset = band; band major: slot = band, offset = row chunk
+        const int b = g.chunk_major ? item - tf_next : t_next;
+        const int cidx = g.chunk_major ? t_next : item - tf_next;
         const int K0 = 2 + b * BW;
         const int H = g.jmax - K0 + 1; // rows 0 .. H-1 exist on the band's first diagonal
-        const int r_begin = (item - bf_next) * g.chunk;
+        const int r_begin = cidx * g.chunk;
         const int r_end = min(r_begin + g.chunk, H);
         const int lane_k0 = K0 + lane * R; // first diagonal of this lane
 
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
                 float m = dl[0];
 #pragma unroll
                 for (int r = 1; r < R; ++r) m = fminf(m, dl[r]);
-                if (m < thr) { // rare: a move that may beat this thread's best
+                if (m <= thr) { // rare: a move that may beat (or tie with) this thread's best
                     const uint32_t i = (uint32_t)(i0 + tau);
                     const Pt pi = srow[tau];
 #pragma unroll
@@ -221,7 +223,9 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
                         }
                         // the cyclic neighbourhood excludes (0, n-1): both edges share p_0
                         const bool excluded = g.cyclic && i == 0 && j == (uint32_t)(g.n - 1);
-                        if (d < best && !excluded) {
+                        // full (delta, i, j) order: a warp that is handed several work items does
+                        // not visit them in (i, j) order
+                        if (d < 0.0f && !excluded && better_2opt(d, i, j, best, bi, bj)) {
                             best = d;
                             bi = i;
                             bj = j;

@@ -121,23 +121,25 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
     const int total_warps = gridDim.x * WARPS;
     const int item0 = g.item_begin + blockIdx.x * WARPS + warp;
-    int b_next = 0, bf_next = 0; // band of this warp's first work item (geometry only)
+    int t_next = 0, tf_next = 0; // table slot of this warp's first work item (geometry only)
     if (item0 < g.item_end) {
-        b_next = find_band_m(band_first, g.nbands, item0);
-        bf_next = __ldg(&band_first[b_next]);
+        t_next = find_band_m(band_first, g.ntab, item0);
+        tf_next = __ldg(&band_first[t_next]);
     }
     griddep_wait(); // the previous step's move is applied and visible from here on
     if (*reinterpret_cast<const volatile int *>(&state->done)) return; // grid-uniform
 
     for (int item = item0; item < g.item_end; item += total_warps) {
         if (item != item0) {
-            b_next = find_band_m(band_first, g.nbands, item);
-            bf_next = __ldg(&band_first[b_next]);
+            t_next = find_band_m(band_first, g.ntab, item);
+            tf_next = __ldg(&band_first[t_next]);
         }
-        const int b = b_next;
+        // chunk major: slot = row chunk, offset = band; band major: slot = band, offset = row chunk
+        const int b = g.chunk_major ? item - tf_next : t_next;
+        const int cidx = g.chunk_major ? t_next : item - tf_next;
         const int K0 = 2 + b * BW;
         const int H = g.jmax - K0 + 1;
-        const int r_begin = (item - bf_next) * g.chunk;
+        const int r_begin = cidx * g.chunk;
         const int r_end = min(r_begin + g.chunk, H);
         const int ntiles = (r_end - r_begin + TI - 1) / TI;
         const int tile_rows = ntiles > 0 ? (r_end - r_begin + ntiles - 1) / ntiles : 0;
@@ -195,13 +197,14 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
                 V m = dl[0];
 #pragma unroll
                 for (int r = 1; r < R; ++r) m = Val<V>::vmin(m, dl[r]);
-                if (m < best) { // rare; within a thread the scan order is (i, j) ascending
+                if (m <= best) { // rare: a move that may beat (or tie with) this thread's best
                     const uint32_t i = (uint32_t)(i0 + tau);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const uint32_t j = i + (uint32_t)(K0 + lane + 32 * r);
                         const bool excluded = g.cyclic && i == 0 && j == (uint32_t)(g.n - 1);
-                        if (!excluded && dl[r] < best) {
+                        // full (delta, i, j) order: work items are not visited in (i, j) order
+                        if (!excluded && dl[r] < (V)0 && better_2opt(dl[r], i, j, best, bi, bj)) {
                             best = dl[r];
                             bi = i;
                             bj = j;

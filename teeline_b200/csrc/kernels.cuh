@@ -12,14 +12,19 @@ namespace tl {
 // The (i,j) triangle is cut into BANDS of BW = 32*R consecutive diagonals
 // k = j - i (k starts at 2, so no triangular mask is ever needed).  Band b has
 // rows i = 0 .. jmax - K0_b.  Each band is cut into work items of `chunk` rows;
-// one warp processes one item at a time, so within a thread the scan order is
-// (i ascending, j ascending) = the reference's order, and a strict '<' keeps the
-// lowest (i,j) among equal deltas.
+// one warp processes one item, so within a thread the scan order is (i ascending,
+// j ascending) = the reference's order.  Items are numbered ROW-CHUNK MAJOR
+// (chunk_major = 1): item = first[c] + b for row chunk c and band b, so the 8 warps
+// of a CTA work on the same rows of 8 adjacent bands -- on the matrix path they read
+// 8 adjacent 1 KB pieces of the same matrix row, which HBM likes far better than
+// 8 unrelated rows.  (chunk_major = 0: band major, item = first[b] + c.)
 struct ScanGeom {
     int32_t n;
     int32_t jmax;       // n-2 (reference neighbourhood) or n-1 (cyclic)
     int32_t kmax;       // n-2
     int32_t nbands;
+    int32_t ntab;       // entries in the `first` look-up table (row chunks, or bands)
+    int32_t chunk_major;
     int32_t chunk;      // rows per work item
     int32_t item_begin; // this launch scans items [item_begin, item_end)
     int32_t item_end;

@@ -117,15 +117,33 @@ void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
             lo = mid + 1;
     }
     g.chunk = lo;
-    band_first_h.assign(g.nbands + 1, 0);
-    for (int b = 0; b < g.nbands; ++b) band_first_h[b + 1] = band_first_h[b] + (H(b) + g.chunk - 1) / g.chunk;
-    s->nitems = band_first_h[g.nbands];
+    g.chunk_major = getenv("TL_BAND_MAJOR") ? 0 : 1;
+    if (g.chunk_major) {
+        // first[c] = items before row chunk c; chunk c holds the bands that still have rows there
+        // (H is decreasing in b, so they are bands 0 .. nb(c)-1)
+        const int nchunks = (H(0) + g.chunk - 1) / g.chunk;
+        band_first_h.assign(nchunks + 1, 0);
+        int nb = g.nbands;
+        for (int c = 0; c < nchunks; ++c) {
+            while (nb > 0 && H(nb - 1) <= c * g.chunk) --nb;
+            band_first_h[c + 1] = band_first_h[c] + nb;
+        }
+        g.ntab = nchunks;
+        s->nitems = band_first_h[nchunks];
+    } else {
+        band_first_h.assign(g.nbands + 1, 0);
+        for (int b = 0; b < g.nbands; ++b) band_first_h[b + 1] = band_first_h[b] + (H(b) + g.chunk - 1) / g.chunk;
+        g.ntab = g.nbands;
+        s->nitems = band_first_h[g.nbands];
+    }
     const int64_t per = ((int64_t)s->nitems + s->shard_count - 1) / s->shard_count;
     g.item_begin = (int32_t)std::min<int64_t>(s->nitems, per * s->shard_index);
     g.item_end = (int32_t)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
     // same grid on every rank so the all-gather is symmetric
     const int64_t blocks = (per + warps - 1) / warps;
     s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * minb));
+    // test hook: a small grid makes every warp walk several work items
+    if (const char *cap = getenv("TL_MAX_GRID")) s->grid = std::max(1, std::min(s->grid, atoi(cap)));
 }
 
 // Or-opt work decomposition: column blocks of 32*kOrR insertion edges x row chunks.

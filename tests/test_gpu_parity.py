@@ -632,3 +632,39 @@ def test_batch_edge_cases(T, ctx):
     pn = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32)
     with pytest.raises(T.TeelineError):
         pn.two_opt_batch(np.arange(10)[None, :])
+
+
+@pytest.mark.parametrize("path", ["recompute", "matrix"])
+def test_k2_best_ties_when_warps_walk_several_work_items(T, ctx, monkeypatch, path):
+    """A tiny grid makes every warp process many work items, out of (i,j) order; ties on a lattice
+    must still resolve to the lowest (i,j)."""
+    monkeypatch.setenv("TL_MAX_GRID", "2")
+    rng = np.random.default_rng(11)
+    n = 900
+    x = rng.integers(0, 15, n).astype(np.float32)
+    y = rng.integers(0, 15, n).astype(np.float32)
+    P = O.Problem(x, y)
+    start = O.shuffle_tour(n, 6)
+    want_t, want_st, want_mv = O.two_opt_best(P, start, max_moves=60, nthreads=4, log_cap=1 << 12)
+    p = T.Problem.euc2d(ctx, x, y)
+    got_t, st, mv = p.local_search(T.ALGO_TWO_OPT_BEST, start, path=getattr(T, "PATH_" + path.upper()), max_moves=60,
+                                   log_cap=1 << 12)
+    assert [m[1:3] for m in mv] == [m[1:3] for m in want_mv] and (got_t.astype(np.int64) == want_t).all()
+    monkeypatch.setenv("TL_BAND_MAJOR", "1")
+    got_t, st, mv = p.local_search(T.ALGO_TWO_OPT_BEST, start, path=getattr(T, "PATH_" + path.upper()), max_moves=60,
+                                   log_cap=1 << 12)
+    assert [m[1:3] for m in mv] == [m[1:3] for m in want_mv] and (got_t.astype(np.int64) == want_t).all()
+
+
+def test_mode_r_10k_full_size_matches_oracle(T, ctx):
+    """BASELINE config 3 size, reference-exact mode: 2 636 moves, 7 passes, 349 825 021 evaluations
+    (SURVEY.md section 6 probe) -- same tour as the CPU oracle."""
+    n = 10000
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    start = O.nn_tour(P, 3)
+    want_t, want_st, _ = O.two_opt_ref(P, start)
+    got_t, st, _ = T.Problem.euc2d(ctx, x, y).local_search(T.ALGO_TWO_OPT_REF, start)
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (2636, 7, 349825021) == (want_st.moves, want_st.passes, want_st.evals)
+    assert f5(O.tour_length(P, got_t)) == "78726.51562"
