@@ -61,7 +61,8 @@ enum {
     TL_ALGO_TWO_OPT_REF = 0,         /* "Mode R": first-improvement, two_opt.rs:26-61 (bit-exact) */
     TL_ALGO_TWO_OPT_BEST = 1,        /* "Mode B": best-improvement, same neighbourhood            */
     TL_ALGO_TWO_OPT_BEST_CYCLIC = 2, /* Mode B incl. closing edge (two-opt-algo.ts:71-99)         */
-    TL_ALGO_OR_OPT = 3               /* or_opt.rs:80-184 (best-improvement, bit-exact)            */
+    TL_ALGO_OR_OPT = 3,              /* or_opt.rs:80-184 (best-improvement, bit-exact)            */
+    TL_ALGO_THREE_OPT = 4            /* three_opt.rs:16-218 (best-improvement over triples, bit-exact) */
 };
 
 /* where distances come from during the scan */
@@ -79,10 +80,12 @@ enum {
 
 typedef struct {
     float delta;      /* f32 delta of the applied move (exact int value for NINT_I32)          */
-    uint32_t i, j;    /* 2-opt: path[i+1..=j] reversed.  Or-opt: segment start, insert-after j */
-    uint8_t seg_len;  /* Or-opt: 1..3; 0 for 2-opt                                             */
+    uint32_t i, j;    /* 2-opt: path[i+1..=j] reversed.  Or-opt: segment start, insert-after j.
+                         3-opt: the first two cut positions                                     */
+    uint8_t seg_len;  /* Or-opt: 1..3; 3-opt: reconnection case 1..7; 0 for 2-opt              */
     uint8_t reversed; /* Or-opt: segment re-inserted reversed                                  */
     uint16_t pad;
+    uint32_t k;       /* 3-opt: the third cut position; 0 otherwise                            */
 } tl_move;
 
 typedef struct {
@@ -153,7 +156,7 @@ tl_status tl_tour_lengths_i64(tl_problem *p, const uint32_t *tours, size_t batch
 /* ---- local search, one call ------------------------------------------------------ */
 
 /* Replaces the body of two_opt::solve (two_opt.rs:17-61) / or_opt::solve
- * (or_opt.rs:31-74).  tour_inout: n positions, start tour in, local optimum out.
+ * (or_opt.rs:31-74) / three_opt::solve (three_opt.rs:24-52).  tour_inout: n positions, start tour in, local optimum out.
  * max_moves < 0: run to the local optimum.  log (nullable) receives the applied
  * moves in order, up to log_cap. */
 tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *tour_inout,

@@ -219,6 +219,32 @@ def or_opt(p: Problem, tour, max_moves: int = -1, log_cap: int = 0):
     return t, st, _moves(log, st, log_cap)
 
 
+def three_opt_find_best(p: Problem, tour, nthreads: int = 1):
+    """three_opt.rs:58-131.  Returns (delta = -savings, i, j, k, case) or None, and the triples evaluated."""
+    t = _tour(tour)
+    mv, k, kase, ev = Move(), C.c_int32(), C.c_int32(), C.c_int64()
+    found = lib().tlo_three_opt_find_best(p.ref, _p(t), C.c_int(nthreads), C.byref(mv), C.byref(k),
+                                          C.byref(kase), C.byref(ev))
+    return ((mv.delta, mv.i, mv.j, k.value, kase.value) if found else None), ev.value
+
+
+def three_opt_apply(tour, i: int, j: int, k: int, case: int) -> np.ndarray:
+    t = _tour(tour).copy()
+    lib().tlo_three_opt_apply(_p(t), C.c_int32(i), C.c_int32(j), C.c_int32(k), C.c_int32(case))
+    return t
+
+
+def three_opt(p: Problem, tour, max_moves: int = -1, nthreads: int = 1, log_cap: int = 0):
+    """three_opt::solve.  Returns (tour, stats, moves) with moves = (delta, i, j, k, case)."""
+    t = _tour(tour).copy()
+    st, log = Stats(), _log(log_cap)
+    ks = np.zeros(max(log_cap, 1), dtype=np.int32)
+    lib().tlo_three_opt(p.ref, _p(t), C.c_int64(max_moves), C.c_int(nthreads), C.byref(st), log, _p(ks),
+                        C.c_int64(log_cap))
+    mv = [(log[m].delta, log[m].i, log[m].j, int(ks[m]), log[m].seg_len) for m in range(min(st.moves, log_cap))]
+    return t, st, mv
+
+
 def gen_uniform(n: int, seed: int):
     x = np.empty(n, dtype=np.float32)
     y = np.empty(n, dtype=np.float32)

@@ -284,6 +284,118 @@ void tlo_or_opt(const tlo_problem *p, int32_t *tour, int64_t max_moves, tlo_stat
     }
 }
 
+/* ---- 3-opt (three_opt.rs) -------------------------------------------------------------- */
+
+/* apply_3opt, three_opt.rs:182-218: middle = path[i+1..=k] rebuilt from seg1 = path[i+1..=j],
+ * seg2 = path[j+1..=k] */
+void tlo_three_opt_apply(int32_t *path, int32_t i, int32_t j, int32_t k, int32_t kase)
+{
+    const int32_t l1 = j - i, l2 = k - j;
+    int32_t *s1 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(l1 > 0 ? l1 : 1));
+    int32_t *s2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(l2 > 0 ? l2 : 1));
+    memcpy(s1, path + i + 1, sizeof(int32_t) * (size_t)l1);
+    memcpy(s2, path + j + 1, sizeof(int32_t) * (size_t)l2);
+    int32_t *o = path + i + 1;
+    /* which segment comes first, and which are reversed */
+    const int first2 = kase >= 4;
+    const int rev1 = kase == 1 || kase == 3 || kase == 5 || kase == 7;
+    const int rev2 = kase == 2 || kase == 3 || kase == 6 || kase == 7;
+    for (int part = 0; part < 2; ++part) {
+        const int use2 = first2 ? part == 0 : part == 1;
+        const int32_t *s = use2 ? s2 : s1;
+        const int32_t len = use2 ? l2 : l1;
+        const int rev = use2 ? rev2 : rev1;
+        for (int32_t t = 0; t < len; ++t) *o++ = rev ? s[len - 1 - t] : s[t];
+    }
+    free(s1);
+    free(s2);
+}
+
+typedef struct {
+    const tlo_problem *p;
+    const int32_t *path;
+    int32_t r0, r1;
+    tlo_move mv;
+    int32_t k, kase;
+    int64_t evals;
+    int found;
+} three_job;
+
+static void *three_worker(void *arg)
+{
+    three_job *jb = (three_job *)arg;
+    jb->evals = 0;
+    jb->found = IS_INT(jb->p)
+                    ? three_opt_scan_rows_i(jb->p, jb->path, jb->r0, jb->r1, &jb->mv, &jb->k, &jb->kase, &jb->evals)
+                    : three_opt_scan_rows_f(jb->p, jb->path, jb->r0, jb->r1, &jb->mv, &jb->k, &jb->kase, &jb->evals);
+    return NULL;
+}
+
+/* find_best_move; nthreads > 1 splits the rows of i (same result: the merge keeps the larger
+ * savings, and on equal savings the lower row block, i.e. the first found in scan order) */
+int tlo_three_opt_find_best(const tlo_problem *p, const int32_t *path, int nthreads, tlo_move *mv,
+                            int32_t *k_out, int32_t *case_out, int64_t *evals)
+{
+    const int32_t n = p->n;
+    if (n < 4) return 0;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    three_job jobs[64];
+    pthread_t th[64];
+    /* row i has ~(n-i)^2/2 triples: equal-work cuts i_t = n (1 - (1 - t/T)^(1/3)) */
+    for (int t = 0; t < nthreads; ++t) {
+        const double f0 = 1.0 - cbrt(1.0 - (double)t / nthreads), f1 = 1.0 - cbrt(1.0 - (double)(t + 1) / nthreads);
+        jobs[t].p = p;
+        jobs[t].path = path;
+        jobs[t].r0 = (int32_t)(f0 * (n - 2));
+        jobs[t].r1 = t + 1 == nthreads ? n - 2 : (int32_t)(f1 * (n - 2));
+    }
+    for (int t = 0; t < nthreads; ++t) {
+        if (nthreads == 1) three_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, three_worker, &jobs[t]);
+    }
+    int found = 0;
+    if (evals) *evals = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        if (nthreads > 1) pthread_join(th[t], NULL);
+        if (evals) *evals += jobs[t].evals;
+        /* delta = -savings: strictly smaller delta = strictly larger savings; ties keep the earlier block */
+        if (jobs[t].found && (!found || jobs[t].mv.delta < mv->delta)) {
+            found = 1;
+            *mv = jobs[t].mv;
+            *k_out = jobs[t].k;
+            *case_out = jobs[t].kase;
+        }
+    }
+    return found;
+}
+
+/* three_opt::solve, three_opt.rs:16-52: log[].seg_len carries the case, log[].reversed is unused,
+ * the third index k is returned through ks[] (nullable) */
+void tlo_three_opt(const tlo_problem *p, int32_t *path, int64_t max_moves, int nthreads, tlo_stats *st,
+                   tlo_move *log, int32_t *ks, int64_t log_cap)
+{
+    st->passes = st->moves = st->evals = 0;
+    if (p->n < 4) return;
+    for (;;) {
+        if (max_moves >= 0 && st->moves >= max_moves) break;
+        tlo_move mv;
+        int32_t k = 0, kase = 0;
+        int64_t ev = 0;
+        const int found = tlo_three_opt_find_best(p, path, nthreads, &mv, &k, &kase, &ev);
+        st->passes++;
+        st->evals += ev;
+        if (!found) break;
+        tlo_three_opt_apply(path, mv.i, mv.j, k, kase);
+        if (log && st->moves < log_cap) {
+            log[st->moves] = mv;
+            log[st->moves].seg_len = kase;
+            if (ks) ks[st->moves] = k;
+        }
+        st->moves++;
+    }
+}
+
 /* ---- synthetic inputs --------------------------------------------------------- */
 
 uint64_t tlo_splitmix64(uint64_t *state)

@@ -105,6 +105,16 @@ void tlo_or_opt_apply(int32_t *tour, int32_t n, int32_t i, int32_t seg_len, int3
 void tlo_or_opt(const tlo_problem *p, int32_t *tour, int64_t max_moves, tlo_stats *st,
                 tlo_move *log, int64_t log_cap);
 
+/* ---- 3-opt (three_opt.rs:16-218) ------------------------------
+ * Best-improvement over triples i < j < k with 7 reconnection cases; mv->i, mv->j, *k_out,
+ * *case_out (1..7); mv->delta = -savings.  Golden: NN -> 3-opt on berlin52 = 7742.65
+ * (docs/benchmarks.md:29). */
+int tlo_three_opt_find_best(const tlo_problem *p, const int32_t *path, int nthreads, tlo_move *mv,
+                            int32_t *k_out, int32_t *case_out, int64_t *evals);
+void tlo_three_opt_apply(int32_t *path, int32_t i, int32_t j, int32_t k, int32_t kase);
+void tlo_three_opt(const tlo_problem *p, int32_t *path, int64_t max_moves, int nthreads, tlo_stats *st,
+                   tlo_move *log, int32_t *ks, int64_t log_cap);
+
 /* ---- synthetic inputs (BASELINE.md "Synthetic inputs") */
 uint64_t tlo_splitmix64(uint64_t *state);
 /* x,y = (splitmix64 >> 40) * (1000 / 2^24) as f32; x then y per city. */

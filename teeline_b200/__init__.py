@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi as capi
-from ._capi import (ALGO_OR_OPT, ALGO_TWO_OPT_BEST, ALGO_TWO_OPT_BEST_CYCLIC, ALGO_TWO_OPT_REF,
+from ._capi import (ALGO_OR_OPT, ALGO_THREE_OPT, ALGO_TWO_OPT_BEST, ALGO_TWO_OPT_BEST_CYCLIC, ALGO_TWO_OPT_REF,
                     DIST_F32_EXACT, DIST_NINT_I32, LEN_EXACT, LEN_FAST, PATH_AUTO, PATH_MATRIX,
                     PATH_RECOMPUTE, Move, Stats, TeelineError)
 
@@ -147,7 +147,8 @@ class Problem:
         log = (Move * max(log_cap, 1))()
         capi.check(self._lib.tl_local_search(self.h, algo, path, capi.ptr(t), max_moves, C.byref(st),
                                              log if log_cap else None, log_cap))
-        moves = [log[k].astuple() for k in range(min(int(st.moves), log_cap))]
+        three = algo == ALGO_THREE_OPT
+        moves = [log[k].astuple3() if three else log[k].astuple() for k in range(min(int(st.moves), log_cap))]
         return t, st, moves
 
     def two_opt_batch(self, tours, algo: int = ALGO_TWO_OPT_BEST, max_moves: int = -1):
@@ -180,6 +181,7 @@ class Session:
 
     def __init__(self, problem: Problem, algo: int, path: int, tour):
         self.problem = problem
+        self.algo = algo
         self._lib = problem._lib
         t = _u32(tour)
         h = C.c_void_p()
@@ -192,7 +194,9 @@ class Session:
     def scan(self):
         mv, found = Move(), C.c_int32()
         capi.check(self._lib.tl_session_scan(self.h, C.byref(mv), C.byref(found)))
-        return mv.astuple() if found.value else None
+        if not found.value:
+            return None
+        return mv.astuple3() if self.algo == ALGO_THREE_OPT else mv.astuple()
 
     def time_scans(self, reps: int) -> float:
         """Average scan-kernel launch duration in ms (CUDA events on the context's stream)."""
@@ -220,7 +224,8 @@ class Session:
         log = (Move * max(cap, 1))()
         got = C.c_size_t()
         capi.check(self._lib.tl_session_log(self.h, log, cap, C.byref(got)))
-        return [log[k].astuple() for k in range(got.value)]
+        three = self.algo == ALGO_THREE_OPT
+        return [log[k].astuple3() if three else log[k].astuple() for k in range(got.value)]
 
     def close(self):
         if getattr(self, "h", None):

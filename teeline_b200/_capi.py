@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("TL_LIB") or os.path.join(_HERE, "libteeline_cuda.so")
 # enums (teeline_cuda.h)
 TL_OK = 0
 DIST_F32_EXACT, DIST_NINT_I32 = 0, 1
-ALGO_TWO_OPT_REF, ALGO_TWO_OPT_BEST, ALGO_TWO_OPT_BEST_CYCLIC, ALGO_OR_OPT = 0, 1, 2, 3
+ALGO_TWO_OPT_REF, ALGO_TWO_OPT_BEST, ALGO_TWO_OPT_BEST_CYCLIC, ALGO_OR_OPT, ALGO_THREE_OPT = 0, 1, 2, 3, 4
 PATH_AUTO, PATH_MATRIX, PATH_RECOMPUTE = 0, 1, 2
 LEN_EXACT, LEN_FAST = 0, 1
 NCCL_ID_BYTES = 128
@@ -38,10 +38,14 @@ EXPORTS = [
 
 class Move(C.Structure):
     _fields_ = [("delta", C.c_float), ("i", C.c_uint32), ("j", C.c_uint32), ("seg_len", C.c_uint8),
-                ("reversed", C.c_uint8), ("pad", C.c_uint16)]
+                ("reversed", C.c_uint8), ("pad", C.c_uint16), ("k", C.c_uint32)]
 
     def astuple(self):
         return (float(self.delta), int(self.i), int(self.j), int(self.seg_len), int(self.reversed))
+
+    def astuple3(self):
+        """3-opt view: (delta, i, j, k, case)."""
+        return (float(self.delta), int(self.i), int(self.j), int(self.k), int(self.seg_len))
 
 
 class Stats(C.Structure):

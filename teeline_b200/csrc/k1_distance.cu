@@ -7,7 +7,8 @@
 //
 // Roofline: HBM write, 4 B per pair.  Each thread produces 4 consecutive packed
 // entries and stores them with one 128-bit STG; coordinate reads are L1/L2 hits
-// (lo runs over consecutive cities, hi is warp-uniform most of the time).
+// (lo runs over consecutive cities, hi is warp-uniform most of the time).  The
+// packed index is inverted with fp64 once per thread, then advanced incrementally.
 #include "kernels.cuh"
 
 namespace tl {
@@ -22,30 +23,38 @@ __device__ __forceinline__ void packed_index_to_pair(uint64_t t, uint32_t &hi, u
     lo = (uint32_t)(t - h * (h - 1) / 2);
 }
 
+// Every CTA owns one contiguous piece of the packed array (`per_cta` entries, a multiple of 1024).
+// A thread produces 4 consecutive entries per step (one 128-bit store) and moves 1024 entries
+// ahead; its (hi, lo) pair is found once with the closed form and then advanced incrementally
+// (rows are longer than 1024 almost everywhere, so the wrap loop runs 0-1 times).
 template <bool FAST, bool NINT>
 __global__ void __launch_bounds__(256) k1_packed_kernel(const float2 *__restrict__ xy, uint32_t n,
-                                                        uint64_t total, void *__restrict__ out)
+                                                        uint64_t total, uint64_t per_cta,
+                                                        void *__restrict__ out)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
-    for (uint64_t t0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; t0 < total;
-         t0 += stride) {
-        uint32_t hi, lo;
-        packed_index_to_pair(t0, hi, lo);
+    const uint64_t begin = (uint64_t)blockIdx.x * per_cta;
+    const uint64_t end = min(begin + per_cta, total);
+    uint64_t t0 = begin + (uint64_t)threadIdx.x * 4;
+    if (t0 >= end) return;
+    uint32_t hi, lo;
+    packed_index_to_pair(t0, hi, lo);
+    for (; t0 < end; t0 += 1024) {
         float2 ph = __ldg(&xy[hi]);
         uint32_t v[4];
+        uint32_t h = hi, l = lo;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (t0 + e < total) {
-                const float2 pl = __ldg(&xy[lo]);
+                const float2 pl = __ldg(&xy[l]);
                 // the reference evaluates cities[hi].distance(cities[lo])
                 if (NINT)
                     v[e] = (uint32_t)dist_nint(ph.x, ph.y, pl.x, pl.y);
                 else
                     v[e] = __float_as_uint(dist_f32<FAST>(ph.x, ph.y, pl.x, pl.y));
-                if (++lo == hi) {
-                    ++hi;
-                    lo = 0;
-                    if (hi < n) ph = __ldg(&xy[hi]);
+                if (++l == h) {
+                    ++h;
+                    l = 0;
+                    if (h < n) ph = __ldg(&xy[h]);
                 }
             } else {
                 v[e] = 0;
@@ -56,6 +65,12 @@ __global__ void __launch_bounds__(256) k1_packed_kernel(const float2 *__restrict
             *reinterpret_cast<uint4 *>(o) = make_uint4(v[0], v[1], v[2], v[3]);
         } else {
             for (int e = 0; e < 4 && t0 + e < total; ++e) o[e] = v[e];
+        }
+        // 1024 entries ahead: row hi holds hi entries
+        lo += 1024;
+        while (lo >= hi) {
+            lo -= hi;
+            ++hi;
         }
     }
 }
@@ -132,17 +147,18 @@ void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, bool nint, void *
                       cudaStream_t st)
 {
     const uint64_t total = (uint64_t)n * (n - 1) / 2;
-    const uint64_t thr = (total + 3) / 4;
-    uint64_t blocks = (thr + 255) / 256;
-    const uint64_t cap = (uint64_t)sm_count * 32; // grid-stride: a multiple of the SM count
-    if (blocks > cap) blocks = cap;
+    // a multiple of the SM count, at least 4 steps of 1024 entries per CTA when there is enough work
+    uint64_t blocks = (uint64_t)sm_count * 16;
+    uint64_t per_cta = ((total + blocks - 1) / blocks + 1023) / 1024 * 1024;
+    if (per_cta < 4096) per_cta = 4096;
+    blocks = (total + per_cta - 1) / per_cta;
     if (blocks == 0) blocks = 1;
     if (nint)
-        k1_packed_kernel<false, true><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, out);
+        k1_packed_kernel<false, true><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
     else if (fast)
-        k1_packed_kernel<true, false><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, out);
+        k1_packed_kernel<true, false><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
     else
-        k1_packed_kernel<false, false><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, out);
+        k1_packed_kernel<false, false><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
 }
 
 void launch_k1_square(const float2 *sxy, uint32_t n, uint32_t ld, bool fast, bool nint, void *out,

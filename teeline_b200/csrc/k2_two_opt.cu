@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
     const int item0 = g.item_begin + blockIdx.x * WARPS + warp;
     int t_next = 0, tf_next = 0; // table slot of this warp's first work item (geometry only)
     if (item0 < g.item_end) {
-        t_next = find_band(band_first, g.ntab, item0);
+        t_next = find_band(band_first, g.nbands, item0);
         tf_next = __ldg(&band_first[t_next]);
     }
     __syncthreads();
@@ -144,12 +144,11 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
 
     for (int item = item0; item < g.item_end; item += total_warps) {
         if (item != item0) {
-            t_next = find_band(band_first, g.ntab, item);
+            t_next = find_band(band_first, g.nbands, item);
             tf_next = __ldg(&band_first[t_next]);
         }
-        // chunk major: slot = row chunk, offset = band; band major: slot = band, offset = row chunk
-        const int b = g.chunk_major ? item - tf_next : t_next;
-        const int cidx = g.chunk_major ? t_next : item - tf_next;
+        const int b = t_next;
+        const int cidx = item - tf_next; // row chunk within the band
         const int K0 = 2 + b * BW;
         const int H = g.jmax - K0 + 1; // rows 0 .. H-1 exist on the band's first diagonal
         const int r_begin = cidx * g.chunk;

@@ -10,12 +10,13 @@
 // shared memory as tour-ordered 16-byte records (x, y, city, entering-edge length), so a scan
 // touches no global memory at all; CTAs pull tours from a global ticket counter (tours converge
 // after different move counts, so a static split would leave SMs idle at the tail).
-// Scan: diagonals k = j - i again (one new distance per move).  A thread owns a GROUP of R
-// consecutive diagonals and walks all its rows with the (R+1)-point register window of
-// k2_two_opt.cu.  Long groups (small k) are paired with short ones (large k): thread t takes
-// group t and then group G-1-t, so every thread walks the same number of rows (the triangle is
-// folded into a rectangle).  The lanes of a warp sit on the same row i (warp-broadcast LDS.128 of
-// the row point) and on windows R records apart (odd R => conflict-free LDS.128).
+// Scan: diagonals k = j - i again (one new distance per move), cut like the single-tour kernel
+// into bands of 32*R diagonals x chunks of rows.  The work items of one scan are handed to the
+// CTA's warps through a shared-memory ticket (an item is ~60 rows, so a warp's last item costs a
+// few percent of a scan, whatever n is).  A lane owns R consecutive diagonals and walks its rows
+// with the (R+1)-point register window of k2_two_opt.cu, reading the records straight from
+// shared memory: the lanes of a warp sit on the same row i (warp-broadcast LDS.128 of the row
+// point) and on windows R records apart (odd R => conflict-free LDS.128).
 // Argmin: (delta, i, j) lexicographic through warp shuffles and shared memory -- independent of
 // which thread saw a candidate first.  Apply: the in-place reversal of two_opt_apply.cuh on the
 // shared-memory records.
@@ -28,6 +29,7 @@
 
 #include <math_constants.h>
 
+#include <algorithm>
 #include <type_traits>
 
 namespace tl {
@@ -35,6 +37,7 @@ namespace tl {
 namespace {
 
 constexpr int R = kBatchR;
+constexpr int BW = 32 * R; // diagonals per band
 
 template <int N, typename F>
 __device__ __forceinline__ void static_for(F &&f)
@@ -51,24 +54,31 @@ struct BatchCounters {
     unsigned int unconverged;
 };
 
-template <bool FAST>
-__global__ void __launch_bounds__(kBatchMaxThreads, 2)
+// SCREEN: as in k2_two_opt.cu -- the walk evaluates deltas with the screening distance and
+// re-evaluates exactly (from the shared-memory records) whenever a row step comes within the
+// rigorous margin of the running best.  MAXT / MINB: launch bounds; small tours run 128 threads
+// with 7 resident CTAs per SM (1036 tours in flight on 148 SMs), large ones 256 threads.
+template <bool FAST, bool SCREEN, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
     two_opt_batch_kernel(const float2 *__restrict__ xy, uint32_t *__restrict__ tours, uint32_t n, uint32_t batch,
-                         int cyclic, long long max_moves, BatchCounters *__restrict__ ctr)
+                         int cyclic, long long max_moves, float screen_margin, int chunk,
+                         BatchCounters *__restrict__ ctr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Pt *pts = reinterpret_cast<Pt *>(smem_raw);
-    __shared__ BestF red[kBatchMaxThreads / 32];
+    __shared__ BestF red[MAXT / 32];
     __shared__ BestF s_best;
-    __shared__ unsigned int s_tour;
+    __shared__ unsigned int s_tour, s_item;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int nwarps = nthreads >> 5;
     const int jmax = cyclic ? (int)n - 1 : (int)n - 2;
-    const int ndiag = (int)n - 3;            // k = 2 .. n-2
-    const int G = (ndiag + R - 1) / R;       // groups of R diagonals
-    const int npairs = (G + 1) / 2;          // folded: group g with group G-1-g
-    const uint32_t npad = n + R + 2;
+    const int nbands = ((int)n - 3 + BW - 1) / BW; // diagonals k = 2 .. n-2 in bands of BW
+    auto band_rows = [&](int b) { return jmax - (2 + b * BW) + 1; };
+    auto band_items = [&](int b) { return (band_rows(b) + chunk - 1) / chunk; };
+    int nitems = 0;
+    for (int b = 0; b < nbands; ++b) nitems += band_items(b);
+    const uint32_t npad = n + BW + 2;
 
     unsigned long long my_moves = 0, my_scans = 0;
     unsigned int my_unconverged = 0;
@@ -100,6 +110,7 @@ __global__ void __launch_bounds__(kBatchMaxThreads, 2)
             }
             pts[q] = p;
         }
+        if (tid == 0) s_item = 0;
         __syncthreads();
 
         long long moves = 0;
@@ -107,31 +118,44 @@ __global__ void __launch_bounds__(kBatchMaxThreads, 2)
         while (max_moves < 0 || moves < max_moves) {
             float best = 0.0f;
             uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
+            float thr = SCREEN ? screen_margin : 0.0f; // best + margin
 
-            // one group of R diagonals starting at k0, rows 0 .. H-1
-            auto walk = [&](int k0, int H) {
+            for (;;) {
+                int item = 0;
+                if (lane == 0) item = (int)atomicAdd(&s_item, 1u);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= nitems) break;
+                int bnd = 0;
+                while (item >= band_items(bnd)) item -= band_items(bnd++);
+                const int K0 = 2 + bnd * BW;
+                const int r_begin = item * chunk, r_end = min(r_begin + chunk, band_rows(bnd));
+                const int k0 = K0 + lane * R; // first diagonal of this lane
+                const Pt *srow = pts + r_begin;
+                const Pt *scol = pts + r_begin + k0;
+
                 float E[R], wx[R], wy[R], ws[R];
                 {
-                    const Pt rp0 = pts[0];
+                    const Pt rp0 = srow[0];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const Pt c = pts[k0 + r];
-                        E[r] = dist_f32<FAST>(rp0.x, rp0.y, c.x, c.y);
-                        const Pt w = pts[k0 + r + 1];
+                        const Pt c = scol[r];
+                        E[r] = SCREEN ? dist_f32_screen(rp0.x, rp0.y, c.x, c.y) : dist_f32<FAST>(rp0.x, rp0.y, c.x, c.y);
+                        const Pt w = scol[r + 1];
                         wx[r] = w.x;
                         wy[r] = w.y;
                         ws[r] = w.sp;
                     }
                 }
-                auto step = [&](auto Uc, int i) {
+                auto step = [&](auto Uc, int tau) {
                     constexpr int U = decltype(Uc)::value;
-                    const Pt rp = pts[i + 1];          // (x,y) of i+1 and s_i: same address in every lane
-                    const Pt nx = pts[i + k0 + R + 1]; // next window point
+                    const Pt rp = srow[tau + 1];     // (x,y) of i+1 and s_i: same address in every lane
+                    const Pt nx = scol[tau + R + 1]; // next window point
                     float dl[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const int ph = (r + U) % R;
-                        const float en = dist_f32<FAST>(rp.x, rp.y, wx[ph], wy[ph]);
+                        const float en = SCREEN ? dist_f32_screen(rp.x, rp.y, wx[ph], wy[ph])
+                                                : dist_f32<FAST>(rp.x, rp.y, wx[ph], wy[ph]);
                         const float cur = __fadd_rn(rp.sp, ws[ph]);
                         const float nw = __fadd_rn(E[r], en);
                         dl[r] = __fsub_rn(nw, cur);
@@ -140,17 +164,26 @@ __global__ void __launch_bounds__(kBatchMaxThreads, 2)
                     float m = dl[0];
 #pragma unroll
                     for (int r = 1; r < R; ++r) m = fminf(m, dl[r]);
-                    if (m <= best) { // rare near a local optimum
+                    if (m <= thr) { // rare near a local optimum
+                        const Pt pi = srow[tau];
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const uint32_t ii = (uint32_t)i, jj = (uint32_t)(i + k0 + r);
+                            const uint32_t ii = (uint32_t)(r_begin + tau), jj = ii + (uint32_t)(k0 + r);
+                            float d = dl[r];
+                            if (SCREEN) { // exact re-evaluation from the shared-memory records
+                                const Pt pj = scol[tau + r], pj1 = scol[tau + r + 1];
+                                const float e1 = dist_f32<FAST>(pi.x, pi.y, pj.x, pj.y);
+                                const float e2 = dist_f32<FAST>(rp.x, rp.y, pj1.x, pj1.y);
+                                d = __fsub_rn(__fadd_rn(e1, e2), __fadd_rn(rp.sp, pj1.sp));
+                            }
                             // the cyclic neighbourhood excludes (0, n-1): both edges share p_0
                             const bool excluded = cyclic && ii == 0 && jj == n - 1;
-                            // a thread visits its groups out of (i,j) order: full lexicographic compare
-                            if (dl[r] < 0.0f && !excluded && better_2opt(dl[r], ii, jj, best, bi, bj)) {
-                                best = dl[r];
+                            // items are not visited in (i,j) order: full lexicographic compare
+                            if (d < 0.0f && !excluded && better_2opt(d, ii, jj, best, bi, bj)) {
+                                best = d;
                                 bi = ii;
                                 bj = jj;
+                                thr = SCREEN ? __fadd_rn(best, screen_margin) : best;
                             }
                         }
                     }
@@ -158,22 +191,13 @@ __global__ void __launch_bounds__(kBatchMaxThreads, 2)
                     wy[U] = nx.y;
                     ws[U] = nx.sp;
                 };
+                const int cnt = r_end - r_begin;
                 int t = 0;
 #pragma unroll 1
-                for (; t + R <= H; t += R) static_for<R>([&](auto Uc) { step(Uc, t + decltype(Uc)::value); });
+                for (; t + R <= cnt; t += R) static_for<R>([&](auto Uc) { step(Uc, t + decltype(Uc)::value); });
                 static_for<R>([&](auto Uc) {
-                    if (t + decltype(Uc)::value < H) step(Uc, t + decltype(Uc)::value);
+                    if (t + decltype(Uc)::value < cnt) step(Uc, t + decltype(Uc)::value);
                 });
-            };
-
-            for (int pr = tid; pr < npairs; pr += nthreads) {
-                const int ga = pr, gb = G - 1 - pr;
-                const int ka = 2 + ga * R;
-                walk(ka, jmax - ka + 1);
-                if (gb != ga) {
-                    const int kb = 2 + gb * R;
-                    walk(kb, jmax - kb + 1);
-                }
             }
 
             // CTA argmin, (delta, i, j) lexicographic
@@ -183,7 +207,10 @@ __global__ void __launch_bounds__(kBatchMaxThreads, 2)
             if (warp == 0) {
                 BestF v = lane < nwarps ? red[lane] : BestF{0.0f, 0xffffffffu, 0xffffffffu, 0u};
                 warp_argmin_2opt(v.delta, v.i, v.j);
-                if (lane == 0) s_best = v;
+                if (lane == 0) {
+                    s_best = v;
+                    s_item = 0; // every warp has left the item loop: re-arm the ticket for the next scan
+                }
             }
             __syncthreads();
             const BestF v = s_best;
@@ -210,58 +237,79 @@ __global__ void __launch_bounds__(kBatchMaxThreads, 2)
 
 } // namespace
 
-size_t two_opt_batch_smem_bytes(uint32_t n) { return (size_t)(n + R + 2) * sizeof(Pt); }
+size_t two_opt_batch_smem_bytes(uint32_t n) { return (size_t)(n + BW + 2) * sizeof(Pt); }
 size_t two_opt_batch_counter_bytes() { return sizeof(BatchCounters); }
+
+namespace {
+
+constexpr int kSmallT = 128, kSmallMinB = 7; // 7 x 148 = 1036 tours in flight
+constexpr int kLargeT = kBatchMaxThreads, kLargeMinB = 3;
+
+// small configuration: 7 tours fit one SM
+bool use_small(uint32_t n) { return two_opt_batch_smem_bytes(n) * kSmallMinB <= 200 * 1024; }
+
+// rows per work item: ~16 items per warp and scan, at least 8 rows
+int chunk_rows(uint32_t n, int cyclic, int threads)
+{
+    const int jmax = cyclic ? (int)n - 1 : (int)n - 2;
+    const int nbands = ((int)n - 3 + BW - 1) / BW;
+    long long rows = 0;
+    for (int b = 0; b < nbands; ++b) rows += jmax - (2 + b * BW) + 1;
+    const long long want = 16LL * (threads / 32);
+    return (int)std::max<long long>(8, (rows + want - 1) / want);
+}
+
+template <typename K>
+cudaError_t set_smem(K kern)
+{
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBatchMaxSmem);
+}
+
+using BatchKernel = void (*)(const float2 *, uint32_t *, uint32_t, uint32_t, int, long long, float, int, BatchCounters *);
+
+BatchKernel pick_kernel(bool small, bool fast, bool screen)
+{
+    if (small) {
+        if (fast && screen) return two_opt_batch_kernel<true, true, kSmallT, kSmallMinB>;
+        if (fast) return two_opt_batch_kernel<true, false, kSmallT, kSmallMinB>;
+        return two_opt_batch_kernel<false, false, kSmallT, kSmallMinB>;
+    }
+    if (fast && screen) return two_opt_batch_kernel<true, true, kLargeT, kLargeMinB>;
+    if (fast) return two_opt_batch_kernel<true, false, kLargeT, kLargeMinB>;
+    return two_opt_batch_kernel<false, false, kLargeT, kLargeMinB>;
+}
+
+} // namespace
 
 cudaError_t two_opt_batch_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(two_opt_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kBatchMaxSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(two_opt_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kBatchMaxSmem);
+    cudaError_t e = cudaSuccess;
+    for (int small = 0; small < 2 && e == cudaSuccess; ++small)
+        for (int v = 0; v < 3 && e == cudaSuccess; ++v) e = set_smem(pick_kernel(small, v > 0, v == 2));
     return e;
 }
 
-int two_opt_batch_threads(uint32_t n)
-{
-    const int ndiag = (int)n - 3;
-    const int G = (ndiag + R - 1) / R;
-    const int npairs = (G + 1) / 2;
-    int t = ((npairs + 31) / 32) * 32;
-    if (t < 32) t = 32;
-    if (t > kBatchMaxThreads) {
-        // several rounds per thread: pick the thread count that wastes the fewest slots
-        const int rounds = (npairs + kBatchMaxThreads - 1) / kBatchMaxThreads;
-        t = (((npairs + rounds - 1) / rounds + 31) / 32) * 32;
-    }
-    return t;
-}
+int two_opt_batch_threads(uint32_t n) { return use_small(n) ? kSmallT : kLargeT; }
 
-int two_opt_batch_grid(uint32_t n, uint64_t batch, int sm_count, bool fast)
+int two_opt_batch_grid(uint32_t n, uint64_t batch, int sm_count, bool fast, bool screen)
 {
     int per_sm = 1;
-    const int threads = two_opt_batch_threads(n);
-    const size_t smem = two_opt_batch_smem_bytes(n);
-    if (fast)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, two_opt_batch_kernel<true>, threads, smem);
-    else
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, two_opt_batch_kernel<false>, threads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(use_small(n), fast, screen),
+                                                  two_opt_batch_threads(n), two_opt_batch_smem_bytes(n));
     if (per_sm < 1) per_sm = 1;
     const uint64_t cap = (uint64_t)sm_count * per_sm;
     return (int)(batch < cap ? batch : cap);
 }
 
 void launch_two_opt_batch(const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
-                          long long max_moves, void *counters, int grid, bool fast, cudaStream_t st)
+                          long long max_moves, float screen_margin, void *counters, int grid, bool fast,
+                          cudaStream_t st)
 {
+    const bool screen = fast && screen_margin >= 0.0f;
     const int threads = two_opt_batch_threads(n);
-    const size_t smem = two_opt_batch_smem_bytes(n);
-    auto *ctr = reinterpret_cast<BatchCounters *>(counters);
-    if (fast)
-        two_opt_batch_kernel<true><<<grid, threads, smem, st>>>(xy, tours, n, (uint32_t)batch, cyclic, max_moves, ctr);
-    else
-        two_opt_batch_kernel<false><<<grid, threads, smem, st>>>(xy, tours, n, (uint32_t)batch, cyclic, max_moves, ctr);
+    pick_kernel(use_small(n), fast, screen)<<<grid, threads, two_opt_batch_smem_bytes(n), st>>>(
+        xy, tours, n, (uint32_t)batch, cyclic, max_moves, screen_margin, chunk_rows(n, cyclic, threads),
+        reinterpret_cast<BatchCounters *>(counters));
 }
 
 } // namespace tl

@@ -91,11 +91,12 @@ __device__ __forceinline__ void warp_argmin_or(Best<V> &v)
 template <class Pol>
 __global__ void __launch_bounds__(256)
     or_rowinfo_kernel(Pol P, uint32_t n, uint32_t npad, Quad<typename Pol::V> *__restrict__ info,
-                      const DevState *__restrict__ state)
+                      const DevState *__restrict__ state, unsigned int *__restrict__ work_ticket)
 {
     using V = typename Pol::V;
     using Rec = typename Pol::Rec;
     if (state->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *work_ticket = 0u; // re-arm the scan's work queue
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += gridDim.x * blockDim.x) {
         V v[3] = {Val<V>::pos_inf(), Val<V>::pos_inf(), Val<V>::pos_inf()};
         if (i < n) {
@@ -121,7 +122,8 @@ template <class Pol>
 __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
     or_opt_scan_kernel(Pol P, const Quad<typename Pol::V> *__restrict__ info, uint32_t n, int chunk,
                        int items_per_cb, int item_begin, int item_end,
-                       Best<typename Pol::V> *__restrict__ blockbest, const DevState *__restrict__ state)
+                       Best<typename Pol::V> *__restrict__ blockbest, const DevState *__restrict__ state,
+                       unsigned int *__restrict__ work_ticket)
 {
     using V = typename Pol::V;
     using Rec = typename Pol::Rec;
@@ -141,9 +143,15 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
     uint32_t phase = 0;
 
     BestV best{Val<V>::or_threshold(), kNone, kNone, 0u}; // or_opt.rs:86: best_delta = -1e-3
-    const int total_warps = gridDim.x * WARPS;
 
-    for (int item = item_begin + blockIdx.x * WARPS + warp; item < item_end; item += total_warps) {
+    // Work items (column block x row chunk) are pulled from a global ticket: the tiles next to the
+    // diagonal run the masked step and cost about twice the others, so a static one-item-per-warp
+    // split would make the whole scan wait for them.
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = item_begin + (int)atomicAdd(work_ticket, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= item_end) break;
         const int cb = item / items_per_cb;
         const int r_begin = (item - cb * items_per_cb) * chunk;
         const int r_end = min(r_begin + chunk, (int)n);
@@ -406,21 +414,23 @@ cudaError_t or_scan_configure()
 }
 
 void launch_or_rowinfo(const Src &src, uint32_t n, uint32_t npad, void *info, const DevState *state,
-                       cudaStream_t st)
+                       unsigned int *work_ticket, cudaStream_t st)
 {
     const int grid = (int)((npad + 255) / 256);
     TL_DISPATCH_POL(src, (or_rowinfo_kernel<<<grid, 256, 0, st>>>(
-                             P, n, npad, reinterpret_cast<Quad<typename decltype(P)::V> *>(info), state)));
+                             P, n, npad, reinterpret_cast<Quad<typename decltype(P)::V> *>(info), state,
+                             work_ticket)));
 }
 
 void launch_or_scan(const Src &src, const void *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
-                    int item_end, void *blockbest, const DevState *state, int grid, cudaStream_t st)
+                    int item_end, void *blockbest, const DevState *state, unsigned int *work_ticket, int grid,
+                    cudaStream_t st)
 {
     const size_t smem = or_scan_smem_bytes();
     TL_DISPATCH_POL(src, (or_opt_scan_kernel<<<grid, WARPS * 32, smem, st>>>(
                              P, reinterpret_cast<const Quad<typename decltype(P)::V> *>(info), n, chunk,
                              items_per_cb, item_begin, item_end,
-                             reinterpret_cast<Best<typename decltype(P)::V> *>(blockbest), state)));
+                             reinterpret_cast<Best<typename decltype(P)::V> *>(blockbest), state, work_ticket)));
 }
 
 void launch_or_apply(const Src &src, void *tmp, uint32_t n, const void *cand, int ncand, DevState *state,

@@ -5,11 +5,11 @@
 // (ant_colony.rs:138,221) and every other `distances.tour_length(..)` consumer.
 //
 // EXACT mode is bit-equal to the reference: total = d(last, first); then
-// total += d(w0, w1) over windows(2), sequentially in f32.  One warp per tour: the
-// 32 lanes compute 32 consecutive edge lengths in parallel (coalesced tour reads,
-// coordinates gathered through L1), then the warp folds them IN ORDER with a
-// shuffle broadcast per edge, so the only serial chain is the f32 add itself.
-// FAST mode sums the same f32 edge lengths in f64 with a warp tree.
+// total += d(w0, w1) over windows(2), sequentially in f32.  Edge lengths are computed
+// 32 at a time by a warp (coalesced tour reads, coordinates gathered through L1) and
+// folded IN ORDER by the lane that owns the tour, so the only serial chain is the f32
+// add itself and 32 tours advance side by side (one CTA per 32 tours).
+// FAST mode sums the same f32 edge lengths in f64, in the same order.
 // A position >= n makes the tour's length 0.0, like the reference's unknown-id case
 // (distance_matrix.rs:221-231).
 //
@@ -34,49 +34,97 @@ __device__ __forceinline__ float edge_f32(const float2 *__restrict__ xy, const f
     return dist_f32<FAST>(p.x, p.y, q.x, q.y);
 }
 
+// One CTA (8 warps) per group of 32 tours.  Per block of 8 chunks x 32 edges:
+//  (1) warp w computes chunk w for all 32 tours: per tour, the 32 lanes read 32 consecutive tour
+//      entries (one coalesced 128-byte request), gather the coordinates and compute 32 edge
+//      lengths in parallel, parked in shared memory (8 tours' loads are issued together);
+//  (2) warp 0 folds them IN ORDER, one LANE per tour: one LDS + one FADD per edge with all 32
+//      lanes busy -- 2 warp instructions per 32 edges instead of 64 for a warp-per-tour shuffle
+//      chain.  The serial f32 chain (the reference's sum order) is kept; 32 chains run side by
+//      side and the edge computation of the other 7 warps overlaps other CTAs' folds.
 template <bool FAST, bool FASTMODE>
 __global__ void __launch_bounds__(256)
     tour_lengths_f32_kernel(const float2 *__restrict__ xy, const float *__restrict__ tri, uint32_t n,
                             const uint32_t *__restrict__ tours, uint64_t batch, float *__restrict__ out)
 {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    for (uint64_t b = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < batch; b += warps) {
-        const uint32_t *t = tours + b * n;
-        if (n < 2) {
-            if (lane == 0) out[b] = 0.0f;
-            continue;
-        }
-        bool bad = false;
-        const uint32_t first = __ldg(&t[0]), last = __ldg(&t[n - 1]);
-        bad = first >= n || last >= n;
-        float acc = bad ? 0.0f : edge_f32<FAST>(xy, tri, last, first); // closing edge first
+    __shared__ float slen[8][32][33]; // [chunk slot][tour][edge], padded: conflict-free both ways
+    __shared__ unsigned int s_bad;    // bit e: tour e of the group has an out-of-range entry
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t groups = (batch + 31) / 32;
+    const uint32_t nchunks = n < 2 ? 0 : (n - 1 + 31) / 32;
+    for (uint64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const uint64_t b0 = g * 32;
+        const uint32_t ntours = (uint32_t)min((uint64_t)32, batch - b0);
+        const uint64_t mine = b0 + lane; // warp 0: the tour this lane accumulates
+        const bool have = warp == 0 && (uint32_t)lane < ntours;
+        float acc = 0.0f;
         double dacc = 0.0;
-        for (uint32_t k0 = 0; k0 + 1 < n; k0 += 32) {
-            const uint32_t k = k0 + lane;
-            float e = 0.0f;
-            if (k + 1 < n) {
-                const uint32_t a = __ldg(&t[k]), c = __ldg(&t[k + 1]);
-                if (a >= n || c >= n)
-                    bad = true;
-                else
-                    e = edge_f32<FAST>(xy, tri, a, c);
-            }
-            if (FASTMODE) {
-                dacc += (double)e;
-            } else {
-                const uint32_t cnt = min(32u, n - 1 - k0);
-#pragma unroll 8
-                for (uint32_t s = 0; s < cnt; ++s) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, e, (int)s));
-            }
+        bool bad = false;
+        uint32_t badbits = 0;
+        __syncthreads(); // the previous group is finished with s_bad and slen
+        if (threadIdx.x == 0) s_bad = 0u;
+        if (have && n >= 2) { // closing edge first (distance_matrix.rs:240)
+            const uint32_t first = __ldg(&tours[mine * n]), last = __ldg(&tours[mine * n + n - 1]);
+            bad = first >= n || last >= n;
+            const float e0 = bad ? 0.0f : edge_f32<FAST>(xy, tri, last, first);
+            acc = e0;
+            dacc = (double)e0;
         }
-        bad = __any_sync(0xffffffffu, bad);
-        if (FASTMODE) {
+        for (uint32_t c0 = 0; c0 < nchunks; c0 += 8) {
+            __syncthreads(); // warp 0 has folded the previous block
+            const uint32_t ch = c0 + warp;
+            if (ch < nchunks) {
+                const uint32_t k0 = ch * 32;
+                const uint32_t cnt = min(32u, n - 1 - k0); // edges k0 .. k0+cnt-1 in this chunk
+                // U tours per round: all index loads of a round are issued before the first gather
+                constexpr int U = 8;
+                for (uint32_t e0 = 0; e0 < ntours; e0 += U) {
+                    uint32_t a[U], c[U];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, off);
-            acc = (float)(dacc + (double)acc);
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t e = min(e0 + u, ntours - 1); // clamp: duplicates are harmless
+                        const uint32_t *t = tours + (b0 + e) * n + k0;
+                        // entries k0+lane and k0+lane+1 (the last lane reads one entry further)
+                        a[u] = ((uint32_t)lane <= cnt) ? __ldg(&t[lane]) : 0u;
+                        c[u] = (lane == 31 && cnt == 32) ? __ldg(&t[32]) : 0u;
+                    }
+                    float len[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t nb = __shfl_down_sync(0xffffffffu, a[u], 1);
+                        if (lane != 31) c[u] = nb;
+                        const bool in = (uint32_t)lane < cnt;
+                        const bool oob = in && (a[u] >= n || c[u] >= n);
+                        if (oob) badbits |= 1u << (e0 + u < ntours ? e0 + u : ntours - 1);
+                        len[u] = (in && !oob) ? edge_f32<FAST>(xy, tri, a[u], c[u]) : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (e0 + u < ntours) slen[warp][e0 + u][lane] = len[u];
+                }
+            }
+            __syncthreads();
+            if (have) {
+                const uint32_t nslots = min(8u, nchunks - c0);
+                for (uint32_t w = 0; w < nslots; ++w) {
+                    const uint32_t cnt = min(32u, n - 1 - (c0 + w) * 32);
+                    if (FASTMODE) {
+#pragma unroll 8
+                        for (uint32_t s2 = 0; s2 < cnt; ++s2) dacc += (double)slen[w][lane][s2];
+                    } else {
+#pragma unroll 8
+                        for (uint32_t s2 = 0; s2 < cnt; ++s2) acc = __fadd_rn(acc, slen[w][lane][s2]);
+                    }
+                }
+            }
         }
-        if (lane == 0) out[b] = bad ? 0.0f : acc;
+        badbits = __reduce_or_sync(0xffffffffu, badbits);
+        if (lane == 0 && badbits) atomicOr(&s_bad, badbits);
+        __syncthreads();
+        if (have) {
+            bad = bad || ((s_bad >> lane) & 1u);
+            out[mine] = (bad || n < 2) ? 0.0f : (FASTMODE ? (float)dacc : acc);
+        }
     }
 }
 
@@ -112,7 +160,7 @@ void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, con
                              uint64_t batch, bool fast_sqrt, bool fast_mode, float *out, int sm_count,
                              cudaStream_t st)
 {
-    uint64_t blocks = (batch + 7) / 8;
+    uint64_t blocks = (batch + 31) / 32; // one CTA per 32 tours
     const uint64_t cap = (uint64_t)sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return;

@@ -12,19 +12,16 @@ namespace tl {
 // The (i,j) triangle is cut into BANDS of BW = 32*R consecutive diagonals
 // k = j - i (k starts at 2, so no triangular mask is ever needed).  Band b has
 // rows i = 0 .. jmax - K0_b.  Each band is cut into work items of `chunk` rows;
-// one warp processes one item, so within a thread the scan order is (i ascending,
-// j ascending) = the reference's order.  Items are numbered ROW-CHUNK MAJOR
-// (chunk_major = 1): item = first[c] + b for row chunk c and band b, so the 8 warps
-// of a CTA work on the same rows of 8 adjacent bands -- on the matrix path they read
-// 8 adjacent 1 KB pieces of the same matrix row, which HBM likes far better than
-// 8 unrelated rows.  (chunk_major = 0: band major, item = first[b] + c.)
+// a warp normally processes exactly one item (the host sizes `chunk` for that), in
+// (i ascending, j ascending) order = the reference's order; when it has to take
+// several, the (delta, i, j) comparison in the kernels' slow path keeps the argmin
+// exact.  Items are numbered band major: item = first[b] + c for band b, row chunk c
+// (row-chunk major was measured and is slower: profiles/r01g_probe.txt).
 struct ScanGeom {
     int32_t n;
     int32_t jmax;       // n-2 (reference neighbourhood) or n-1 (cyclic)
     int32_t kmax;       // n-2
     int32_t nbands;
-    int32_t ntab;       // entries in the `first` look-up table (row chunks, or bands)
-    int32_t chunk_major;
     int32_t chunk;      // rows per work item
     int32_t item_begin; // this launch scans items [item_begin, item_end)
     int32_t item_end;
@@ -110,9 +107,8 @@ void launch_extract_tour(const Src &src, uint32_t n, uint32_t *tour, cudaStream_
 
 // K2 Mode R (reference-exact first improvement)
 constexpr int kRefWindow0 = 8; // rows scanned per launch right after a hit
-void launch_find_first(const Src &src, uint32_t n, DevState *state, int grid, cudaStream_t st);
-void launch_apply_first(const Src &src, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
-                        uint64_t log_cap, int grid, cudaStream_t st);
+void launch_ref_step(const Src &src, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
+                     uint64_t log_cap, int grid, cudaStream_t st);
 
 // K3 Or-opt (recompute path)
 constexpr int kOrR = 8;          // columns per lane
@@ -122,11 +118,21 @@ constexpr int kOrMinBlocks = 2;
 size_t or_scan_smem_bytes();
 cudaError_t or_scan_configure();
 void launch_or_rowinfo(const Src &src, uint32_t n, uint32_t npad, void *info, const DevState *state,
-                       cudaStream_t st);
+                       unsigned int *work_ticket, cudaStream_t st);
 void launch_or_scan(const Src &src, const void *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
-                    int item_end, void *blockbest, const DevState *state, int grid, cudaStream_t st);
+                    int item_end, void *blockbest, const DevState *state, unsigned int *work_ticket, int grid,
+                    cudaStream_t st);
 void launch_or_apply(const Src &src, void *tmp, uint32_t n, const void *cand, int ncand, DevState *state,
                      unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid, cudaStream_t st);
+
+// K6 3-opt (three_opt.rs): row_first[i] = work items before row i (an item = row i x 32 values of j)
+constexpr int kThreeWarps = 8;
+constexpr int kThreeMinBlocks = 4;
+void launch_three_scan(const Src &src, uint32_t n, const int32_t *row_first, int item_begin, int item_end,
+                       void *blockbest, const DevState *state, unsigned int *work_ticket, int grid, cudaStream_t st);
+void launch_three_apply(const Src &src, void *tmp, uint32_t n, const void *cand, int ncand, DevState *state,
+                        unsigned int *ticket, unsigned int *work_ticket, tl_move *log, uint64_t log_cap, int grid,
+                        cudaStream_t st);
 
 // K5 / N1
 void launch_knn(const float2 *xy, const float *tri, uint32_t n, uint32_t k, int metric_id, uint32_t *out,
@@ -169,10 +175,12 @@ constexpr int kBatchMaxSmem = 200 * 1024;
 size_t two_opt_batch_smem_bytes(uint32_t n);
 size_t two_opt_batch_counter_bytes();
 cudaError_t two_opt_batch_configure();
-int two_opt_batch_grid(uint32_t n, uint64_t batch, int sm_count, bool fast);
-// counters: {u64 moves, u64 scans, u32 next_tour, u32 unconverged}, zeroed by the caller
+int two_opt_batch_grid(uint32_t n, uint64_t batch, int sm_count, bool fast, bool screen);
+// counters: {u64 moves, u64 scans, u32 next_tour, u32 unconverged}, zeroed by the caller;
+// screen_margin < 0 disables screening (common.cuh: kScreenMarginScale)
 void launch_two_opt_batch(const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
-                          long long max_moves, void *counters, int grid, bool fast, cudaStream_t st);
+                          long long max_moves, float screen_margin, void *counters, int grid, bool fast,
+                          cudaStream_t st);
 
 // K4
 void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, const uint32_t *tours,

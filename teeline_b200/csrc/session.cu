@@ -54,6 +54,7 @@ struct tl_session {
 
     DevBuf<unsigned char> tmp;     // Or-opt: relocated range staging (npad records of 16 B)
     DevBuf<unsigned char> rowinfo; // Or-opt: per-row removal gains (npad x 16 B)
+    DevBuf<unsigned int> or_ticket; // Or-opt: work queue of the scan kernel
     int or_chunk = 0, or_items_per_cb = 0, or_item_begin = 0, or_item_end = 0;
 
     ScanGeom geom{};
@@ -117,25 +118,9 @@ void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
             lo = mid + 1;
     }
     g.chunk = lo;
-    g.chunk_major = getenv("TL_BAND_MAJOR") ? 0 : 1;
-    if (g.chunk_major) {
-        // first[c] = items before row chunk c; chunk c holds the bands that still have rows there
-        // (H is decreasing in b, so they are bands 0 .. nb(c)-1)
-        const int nchunks = (H(0) + g.chunk - 1) / g.chunk;
-        band_first_h.assign(nchunks + 1, 0);
-        int nb = g.nbands;
-        for (int c = 0; c < nchunks; ++c) {
-            while (nb > 0 && H(nb - 1) <= c * g.chunk) --nb;
-            band_first_h[c + 1] = band_first_h[c] + nb;
-        }
-        g.ntab = nchunks;
-        s->nitems = band_first_h[nchunks];
-    } else {
-        band_first_h.assign(g.nbands + 1, 0);
-        for (int b = 0; b < g.nbands; ++b) band_first_h[b + 1] = band_first_h[b] + (H(b) + g.chunk - 1) / g.chunk;
-        g.ntab = g.nbands;
-        s->nitems = band_first_h[g.nbands];
-    }
+    band_first_h.assign(g.nbands + 1, 0);
+    for (int b = 0; b < g.nbands; ++b) band_first_h[b + 1] = band_first_h[b] + (H(b) + g.chunk - 1) / g.chunk;
+    s->nitems = band_first_h[g.nbands];
     const int64_t per = ((int64_t)s->nitems + s->shard_count - 1) / s->shard_count;
     g.item_begin = (int32_t)std::min<int64_t>(s->nitems, per * s->shard_index);
     g.item_end = (int32_t)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
@@ -152,9 +137,10 @@ void build_or_geometry(tl_session *s)
     const int n = (int)s->n;
     const int cw = 32 * kOrR;
     const int ncb = (n + cw - 1) / cw;
-    const int64_t target = (int64_t)s->c->sm_count * kOrMinBlocks * kOrWarps * s->shard_count;
+    // ~4 items per resident warp (times the shard count): the scan kernel hands them out dynamically
+    const int64_t target = (int64_t)s->c->sm_count * kOrMinBlocks * kOrWarps * s->shard_count * 4;
     const int per_cb = (int)std::max<int64_t>(1, target / ncb);
-    s->or_chunk = std::max(8, (n + per_cb - 1) / per_cb);
+    s->or_chunk = std::max(16, (n + per_cb - 1) / per_cb);
     s->or_items_per_cb = (n + s->or_chunk - 1) / s->or_chunk;
     s->nitems = ncb * s->or_items_per_cb;
     const int64_t per = ((int64_t)s->nitems + s->shard_count - 1) / s->shard_count;
@@ -164,8 +150,28 @@ void build_or_geometry(tl_session *s)
     s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * kOrMinBlocks));
 }
 
+// 3-opt work decomposition: an item is row i x 32 consecutive j; row_first[i] = items before row i.
+tl_status upload_three_geometry(tl_session *s)
+{
+    const int n = (int)s->n;
+    std::vector<int32_t> rf(n - 1, 0); // rows i = 0 .. n-3, plus the total
+    for (int i = 0; i + 2 < n; ++i) rf[i + 1] = rf[i] + (n - 2 - i + 31) / 32;
+    s->nitems = rf[n - 2];
+    const int64_t per = ((int64_t)s->nitems + s->shard_count - 1) / s->shard_count;
+    s->or_item_begin = (int)std::min<int64_t>(s->nitems, per * s->shard_index);
+    s->or_item_end = (int)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
+    const int64_t blocks = (per + kThreeWarps - 1) / kThreeWarps;
+    s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * kThreeMinBlocks));
+    TL_CUDA_TRY(s->band_first.alloc(rf.size()));
+    TL_CUDA_TRY(cudaMemcpyAsync(s->band_first.p, rf.data(), rf.size() * 4, cudaMemcpyHostToDevice, s->c->stream));
+    TL_CUDA_TRY(s->cand.alloc((size_t)s->grid * s->shard_count));
+    TL_CUDA_TRY(cudaStreamSynchronize(s->c->stream)); // rf is a local
+    return TL_OK;
+}
+
 tl_status upload_geometry(tl_session *s)
 {
+    if (s->algo == TL_ALGO_THREE_OPT) return upload_three_geometry(s);
     if (s->algo == TL_ALGO_OR_OPT) {
         build_or_geometry(s);
         TL_CUDA_TRY(s->cand.alloc((size_t)s->grid * s->shard_count));
@@ -225,10 +231,15 @@ tl_status launch_scan(tl_session *s, bool fuse)
 {
     BestF *mine = s->cand.p + (size_t)s->shard_index * s->grid;
     cudaStream_t st = s->c->stream;
-    if (s->algo == TL_ALGO_OR_OPT) {
-        launch_or_rowinfo(s->src, s->n, s->npad, s->rowinfo.p, s->state.p, st);
+    if (s->algo == TL_ALGO_THREE_OPT) {
+        TL_CUDA_TRY(cudaMemsetAsync(s->or_ticket.p, 0, 4, st)); // re-arm the work queue
+        launch_three_scan(s->src, s->n, s->band_first.p, s->or_item_begin, s->or_item_end, mine, s->state.p,
+                          s->or_ticket.p, s->grid, st);
+        s->c->launches++;
+    } else if (s->algo == TL_ALGO_OR_OPT) {
+        launch_or_rowinfo(s->src, s->n, s->npad, s->rowinfo.p, s->state.p, s->or_ticket.p, st);
         launch_or_scan(s->src, s->rowinfo.p, s->n, s->or_chunk, s->or_items_per_cb, s->or_item_begin,
-                       s->or_item_end, mine, s->state.p, s->grid, st);
+                       s->or_item_end, mine, s->state.p, s->or_ticket.p, s->grid, st);
         s->c->launches += 2;
     } else if (s->matrix()) {
         launch_scan_matrix(s->src, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p, s->log_cap,
@@ -260,17 +271,18 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
     const int apply_grid =
         (int)std::max<uint32_t>(1, std::min<uint32_t>((s->n / 2 + 255) / 256, (uint32_t)s->c->sm_count));
     if (s->algo == TL_ALGO_TWO_OPT_REF) {
-        const int find_grid = s->c->sm_count * 2;
+        // one unit (row x 256 columns) per CTA: the first window (8 rows) is covered in one shot
+        const int units0 = kRefWindow0 * (int)((s->n + 255) / 256);
+        const int ref_grid = std::max(1, std::min(units0, s->c->sm_count * 4));
         for (uint32_t k = 0; k < steps; ++k) {
-            launch_find_first(s->src, s->n, s->state.p, find_grid, st);
-            launch_apply_first(s->src, s->n, s->state.p, s->ticket.p, s->log.p, s->log_cap, apply_grid, st);
-            s->c->launches += 2;
+            launch_ref_step(s->src, s->n, s->state.p, s->ticket.p, s->log.p, s->log_cap, ref_grid, st);
+            s->c->launches += 1;
         }
         TL_CUDA_TRY(cudaGetLastError());
         return TL_OK;
     }
     for (uint32_t k = 0; k < steps; ++k) {
-        if (s->matrix() && s->algo != TL_ALGO_OR_OPT && s->repermute_every > 0 &&
+        if (s->matrix() && s->algo != TL_ALGO_OR_OPT && s->algo != TL_ALGO_THREE_OPT && s->repermute_every > 0 &&
             s->steps_since_permute >= (uint32_t)s->repermute_every)
             repermute(s);
         tl_status rc = launch_scan(s, true);
@@ -279,6 +291,12 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
         if (s->algo == TL_ALGO_OR_OPT) {
             launch_or_apply(s->src, s->tmp.p, s->n, s->cand.p, s->grid * s->shard_count, s->state.p, s->ticket.p,
                             s->log.p, s->log_cap, apply_grid, st);
+            s->c->launches += 2;
+            continue;
+        }
+        if (s->algo == TL_ALGO_THREE_OPT) {
+            launch_three_apply(s->src, s->tmp.p, s->n, s->cand.p, s->grid * s->shard_count, s->state.p, s->ticket.p,
+                               s->or_ticket.p, s->log.p, s->log_cap, apply_grid, st);
             s->c->launches += 2;
             continue;
         }
@@ -304,6 +322,26 @@ tl_status close_timing(tl_session *s)
 }
 
 // host-side (delta, rank) reduction of the per-CTA records of one scan
+// 3-opt records: delta = savings (larger is better), aux = k * 8 + case; ties to the lowest (i, j, k)
+template <typename V>
+bool reduce_host_three(const std::vector<Best<V>> &hc, tl_move *best)
+{
+    Best<V> v{(V)0, 0xffffffffu, 0xffffffffu, 0u};
+    auto better = [](const Best<V> &a, const Best<V> &b) {
+        if (a.delta != b.delta) return a.delta > b.delta;
+        if (a.i != b.i) return a.i < b.i;
+        if (a.j != b.j) return a.j < b.j;
+        return (a.aux >> 3) < (b.aux >> 3);
+    };
+    for (const Best<V> &o : hc) {
+        if (o.i == 0xffffffffu) continue;
+        if (v.i == 0xffffffffu || better(o, v)) v = o;
+    }
+    if (v.i == 0xffffffffu) return false;
+    if (best) *best = tl_move{-(float)v.delta, v.i, v.j, (uint8_t)(v.aux & 7u), 0, 0, v.aux >> 3};
+    return true;
+}
+
 template <typename V>
 bool reduce_host(const std::vector<Best<V>> &hc, bool or_opt, tl_move *best)
 {
@@ -337,7 +375,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     if (!p || !tour || !out) { set_error("tl_session_create: null argument"); return TL_ERR_INVALID; }
     *out = nullptr;
     if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC && algo != TL_ALGO_TWO_OPT_REF &&
-        algo != TL_ALGO_OR_OPT) {
+        algo != TL_ALGO_OR_OPT && algo != TL_ALGO_THREE_OPT) {
         set_error("tl_session_create: unknown algo %d", algo);
         return TL_ERR_INVALID;
     }
@@ -365,7 +403,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     s->algo = algo;
     s->path_used = want_matrix ? TL_PATH_MATRIX : TL_PATH_RECOMPUTE;
     s->n = p->n;
-    s->cyclic = algo == TL_ALGO_TWO_OPT_BEST_CYCLIC || algo == TL_ALGO_OR_OPT;
+    s->cyclic = algo == TL_ALGO_TWO_OPT_BEST_CYCLIC || algo == TL_ALGO_OR_OPT || algo == TL_ALGO_THREE_OPT;
     s->trivial = p->n < 4;
     s->launches0 = c->launches;
     s->log_cap = 1u << 16;
@@ -376,6 +414,10 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         s->pairs_per_scan = 0;
         for (uint64_t sg = 1; sg <= 3; ++sg)
             if (n > sg + 1) s->pairs_per_scan += (n - sg + 1) * (n - sg - 1) * (sg > 1 ? 2 : 1);
+    }
+    if (algo == TL_ALGO_THREE_OPT && !s->trivial) {
+        // triples i < j < k minus the skipped (i == 0, k == n-1) ones (three_opt.rs:79-83)
+        s->pairs_per_scan = n * (n - 1) * (n - 2) / 6 - (n - 2);
     }
     // pad so that every staged window of a valid row stays in bounds for every kernel
     s->npad = p->n + std::max(std::max(kScanBW + kScanTI, kMatBW + kMatTI), 32 * kOrR + kOrR) + 64;
@@ -391,14 +433,16 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         set_error("tl_session_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(TL_ERR_NOMEM);
     }
-    if (algo == TL_ALGO_OR_OPT &&
-        (s->tmp.alloc((size_t)s->npad * 16) != cudaSuccess || s->rowinfo.alloc((size_t)s->npad * 16) != cudaSuccess)) {
+    if ((algo == TL_ALGO_OR_OPT || algo == TL_ALGO_THREE_OPT) &&
+        (s->tmp.alloc((size_t)s->npad * 16) != cudaSuccess || s->rowinfo.alloc((size_t)s->npad * 16) != cudaSuccess ||
+         s->or_ticket.alloc(1) != cudaSuccess)) {
         set_error("tl_session_create: device allocation failed");
         return fail(TL_ERR_NOMEM);
     }
-    // or_opt::solve ignores the seed and returns identity order when n < 4 (or_opt.rs:31-34)
+    // or_opt::solve and three_opt::solve ignore the seed and return identity order when n < 4
+    // (or_opt.rs:31-34, three_opt.rs:25-28)
     std::vector<uint32_t> ident;
-    if (algo == TL_ALGO_OR_OPT && s->trivial) {
+    if ((algo == TL_ALGO_OR_OPT || algo == TL_ALGO_THREE_OPT) && s->trivial) {
         ident.resize(p->n);
         for (uint32_t k = 0; k < p->n; ++k) ident[k] = k;
         tour = ident.data();
@@ -451,7 +495,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         // loop runs one empty pass for n == 3 and is skipped for n < 3 (two_opt.rs:17,29 underflow)
         s->h.done = 1;
         s->h.converged = 1;
-        s->h.scans = algo == TL_ALGO_OR_OPT ? 0 : 1;
+        s->h.scans = (algo == TL_ALGO_OR_OPT || algo == TL_ALGO_THREE_OPT) ? 0 : 1;
         s->h.passes = (p->n == 3) ? 1 : 0;
     }
     tl_status rc = push_state(s); // also waits for d_tour's consumers
@@ -509,12 +553,13 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
     TL_CUDA_TRY(cudaStreamSynchronize(s->c->stream));
     if (was_done) { s->h.done = was_done; rc = push_state(s); if (rc != TL_OK) return rc; }
     bool any;
+    const bool three = s->algo == TL_ALGO_THREE_OPT;
     if (s->src.is_int()) {
         std::vector<BestI> hi(hc.size());
         memcpy(hi.data(), hc.data(), hc.size() * sizeof(BestF));
-        any = reduce_host(hi, s->algo == TL_ALGO_OR_OPT, best);
+        any = three ? reduce_host_three(hi, best) : reduce_host(hi, s->algo == TL_ALGO_OR_OPT, best);
     } else {
-        any = reduce_host(hc, s->algo == TL_ALGO_OR_OPT, best);
+        any = three ? reduce_host_three(hc, best) : reduce_host(hc, s->algo == TL_ALGO_OR_OPT, best);
     }
     *found = any ? 1 : 0;
     return TL_OK;
@@ -709,8 +754,11 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
     if (e == cudaSuccess) e = cudaMemsetAsync(d_ctr.p, 0, two_opt_batch_counter_bytes(), st);
     if (e == cudaSuccess) e = cudaEventRecord(e0, st);
     if (e == cudaSuccess && n >= 4) { // n < 4: nothing to scan, tours come back unchanged
-        const int grid = two_opt_batch_grid(n, batch, c->sm_count, p->fast_sqrt);
-        launch_two_opt_batch(p->d_xy, d_t.p, n, batch, cyclic, max_moves, d_ctr.p, grid, p->fast_sqrt, st);
+        const float m = p->dmax * kScreenMarginScale;
+        const float margin =
+            (p->fast_sqrt && std::isfinite(m) && p->dmax >= kScreenMinDmax && !getenv("TL_NO_SCREEN")) ? m : -1.0f;
+        const int grid = two_opt_batch_grid(n, batch, c->sm_count, p->fast_sqrt, margin >= 0.0f);
+        launch_two_opt_batch(p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p, grid, p->fast_sqrt, st);
         c->launches++;
         e = cudaGetLastError();
     }

@@ -194,6 +194,7 @@ int run_solvers()
     std::printf("  2opt | two_opt               first-improvement 2-opt, bit-exact with two_opt.rs\n");
     std::printf("  2opt_best | two_opt_best     best-improvement 2-opt (extension)\n");
     std::printf("  or_opt | or-opt              Or-opt, bit-exact with or_opt.rs\n");
+    std::printf("  3opt | three_opt             best-improvement 3-opt, bit-exact with three_opt.rs\n");
     std::printf("presets: fast (nn,2opt)\n");
     return 0;
 }

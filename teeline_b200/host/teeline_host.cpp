@@ -141,7 +141,8 @@ bool auto_expand_with_shuffle(Solvers s)
 }
 bool is_accelerated(Solvers s)
 {
-    return s == Solvers::NearestNeighbor || s == Solvers::TwoOpt || s == Solvers::OrOpt || s == Solvers::TwoOptBest;
+    return s == Solvers::NearestNeighbor || s == Solvers::TwoOpt || s == Solvers::OrOpt || s == Solvers::TwoOptBest ||
+           s == Solvers::ThreeOpt;
 }
 
 // ---- DistanceMatrix ----------------------------------------------------------------------------------
@@ -465,7 +466,17 @@ Solution run_local_search(const TspProblem &problem, int algo, int path, const P
             const tl_move &mv = log[k];
             ProgressMessage m;
             m.kind = ProgressMessage::PathUpdate;
-            if (algo == TL_ALGO_OR_OPT) {
+            if (algo == TL_ALGO_THREE_OPT) { // apply_3opt, three_opt.rs:182-218; send_path sends 0.0
+                std::vector<uint32_t> s1(cur.begin() + mv.i + 1, cur.begin() + mv.j + 1);
+                std::vector<uint32_t> s2(cur.begin() + mv.j + 1, cur.begin() + mv.k + 1);
+                const int kase = mv.seg_len;
+                if (kase == 1 || kase == 3 || kase == 5 || kase == 7) std::reverse(s1.begin(), s1.end());
+                if (kase == 2 || kase == 3 || kase == 6 || kase == 7) std::reverse(s2.begin(), s2.end());
+                const std::vector<uint32_t> &a = kase >= 4 ? s2 : s1, &b = kase >= 4 ? s1 : s2;
+                std::copy(a.begin(), a.end(), cur.begin() + mv.i + 1);
+                std::copy(b.begin(), b.end(), cur.begin() + mv.i + 1 + a.size());
+                m.total = 0.0f;
+            } else if (algo == TL_ALGO_OR_OPT) {
                 std::vector<uint32_t> seg(cur.begin() + mv.i, cur.begin() + mv.i + mv.seg_len);
                 cur.erase(cur.begin() + mv.i, cur.begin() + mv.i + mv.seg_len);
                 const size_t at = mv.j >= mv.i + mv.seg_len ? mv.j - mv.seg_len + 1 : mv.j + 1;
@@ -526,6 +537,19 @@ Solution solve(const TspProblem &problem, const HeuristicOptions &, const Progre
 
 } // namespace or_opt
 
+namespace three_opt {
+
+Solution solve(const TspProblem &problem, const HeuristicOptions &, const ProgressSender *progress_tx,
+               const std::vector<size_t> *init_tour)
+{
+    // n < 4: identity order, seed ignored, no progress messages (three_opt.rs:25-28)
+    if (problem.cities.size() < 4) return Solution::from_parts(ids_of(problem.cities), problem.cities, problem.distances);
+    const std::vector<size_t> start = init_tour ? *init_tour : ids_of(problem.cities);
+    return run_local_search(problem, TL_ALGO_THREE_OPT, TL_PATH_AUTO, progress_tx, start, "three_opt");
+}
+
+} // namespace three_opt
+
 namespace nearest_neighbor {
 
 Solution solve(const TspProblem &problem, const HeuristicOptions &opts, const ProgressSender *progress_tx,
@@ -579,6 +603,7 @@ Result<Solution> solve_with_context(Solvers solver, const TspProblem &problem, c
     switch (solver) {
     case Solvers::NearestNeighbor: return Result<Solution>::ok(nearest_neighbor::solve(problem, h, tx, init_tour));
     case Solvers::OrOpt: return Result<Solution>::ok(or_opt::solve(problem, h, tx, init_tour));
+    case Solvers::ThreeOpt: return Result<Solution>::ok(three_opt::solve(problem, h, tx, init_tour));
     case Solvers::TwoOpt:
         if (opts.cuda_mode.empty() && opts.cuda_path.empty())
             return Result<Solution>::ok(two_opt::solve(problem, h, tx, init_tour));
@@ -588,7 +613,7 @@ Result<Solution> solve_with_context(Solvers solver, const TspProblem &problem, c
     case Solvers::Unspecified: return Result<Solution>::err("solver not specified");
     default:
         return Result<Solution>::err(std::string("solver ") + solver_name(solver) +
-                                     " is outside the accelerated local-search path of this build (nn, 2opt, or_opt)");
+                                     " is outside the accelerated local-search path of this build (nn, 2opt, or_opt, 3opt)");
     }
 }
 

@@ -12,8 +12,9 @@
 //   TspProblem, Solution         src/tsp/mod.rs:1732-1814
 //   HeuristicOptions, AppOptions src/tsp/mod.rs:597-683, :1586-1596
 //   ProgressMessage              src/tsp/progress.rs:3-11
-//   two_opt::solve / or_opt::solve / nearest_neighbor::solve
-//                                src/tsp/two_opt.rs:7-67, or_opt.rs:19-74, nearest_neighbor.rs:8-76
+//   two_opt::solve / or_opt::solve / three_opt::solve / nearest_neighbor::solve
+//                                src/tsp/two_opt.rs:7-67, or_opt.rs:19-74, three_opt.rs:16-52,
+//                                nearest_neighbor.rs:8-76
 //   solve_with_context, solve_problem, validate_tour, find_solver
 //                                src/tsp/mod.rs:1620-1723
 //   pipeline::*                  src/tsp/pipeline.rs:11-132
@@ -202,6 +203,10 @@ Solution solve_with(const TspProblem &problem, const std::string &mode, const st
                     const ProgressSender *progress_tx, const std::vector<size_t> *init_tour);
 }
 namespace or_opt {
+Solution solve(const TspProblem &problem, const HeuristicOptions &opts, const ProgressSender *progress_tx,
+               const std::vector<size_t> *init_tour);
+}
+namespace three_opt { // src/tsp/three_opt.rs:16-52
 Solution solve(const TspProblem &problem, const HeuristicOptions &opts, const ProgressSender *progress_tx,
                const std::vector<size_t> *init_tour);
 }

@@ -28,7 +28,7 @@ def test_header_and_exports_agree(lib):
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_capi.Move) == 16
+    assert C.sizeof(_capi.Move) == 20  # float, 2 x u32, 2 x u8, u16, u32 k
     assert C.sizeof(_capi.Stats) == 56
 
 

@@ -650,10 +650,6 @@ def test_k2_best_ties_when_warps_walk_several_work_items(T, ctx, monkeypatch, pa
     got_t, st, mv = p.local_search(T.ALGO_TWO_OPT_BEST, start, path=getattr(T, "PATH_" + path.upper()), max_moves=60,
                                    log_cap=1 << 12)
     assert [m[1:3] for m in mv] == [m[1:3] for m in want_mv] and (got_t.astype(np.int64) == want_t).all()
-    monkeypatch.setenv("TL_BAND_MAJOR", "1")
-    got_t, st, mv = p.local_search(T.ALGO_TWO_OPT_BEST, start, path=getattr(T, "PATH_" + path.upper()), max_moves=60,
-                                   log_cap=1 << 12)
-    assert [m[1:3] for m in mv] == [m[1:3] for m in want_mv] and (got_t.astype(np.int64) == want_t).all()
 
 
 def test_mode_r_10k_full_size_matches_oracle(T, ctx):
@@ -668,3 +664,69 @@ def test_mode_r_10k_full_size_matches_oracle(T, ctx):
     assert (got_t.astype(np.int64) == want_t).all()
     assert (int(st.moves), int(st.passes), int(st.evals)) == (2636, 7, 349825021) == (want_st.moves, want_st.passes, want_st.evals)
     assert f5(O.tour_length(P, got_t)) == "78726.51562"
+
+
+# ---- K6 3-opt (three_opt.rs) -------------------------------------------------
+
+def check_three_opt(T, ctx, P, prob, start, max_moves=-1, path=None):
+    want_t, want_st, want_mv = O.three_opt(P, start, max_moves=max_moves, nthreads=8, log_cap=1 << 12)
+    got_t, st, mv = prob.local_search(T.ALGO_THREE_OPT, start, path=T.PATH_AUTO if path is None else path,
+                                      max_moves=max_moves, log_cap=1 << 12)
+    assert [m[1:] for m in mv] == [m[1:] for m in want_mv]
+    assert [np.float32(m[0]) for m in mv] == [np.float32(m[0]) for m in want_mv]
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals)
+    return got_t, st
+
+
+def test_three_opt_golden_G7(T, ctx, berlin52):  # docs/benchmarks.md:29
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    prob = T.Problem.euc2d(ctx, x, y)
+    t, st = check_three_opt(T, ctx, P, prob, O.nn_tour(P, 3))
+    assert f5(prob.tour_lengths(t)[0]) == "7742.64697" and (int(st.moves), int(st.passes)) == (10, 11)
+    check_three_opt(T, ctx, P, prob, np.arange(52))
+    check_three_opt(T, ctx, P, prob, O.nn_tour(P, 3), path=T.PATH_MATRIX)
+
+
+def test_three_opt_reference_unit_cases(T, ctx):  # three_opt.rs:263-276 and the n < 4 rule (:25-28)
+    p = T.Problem.euc2d(ctx, [0.0, 0.0, 0.0, 1.0, 1.0], [0.0, 0.5, 1.0, 1.0, 0.0])
+    t, st, _ = p.local_search(T.ALGO_THREE_OPT, np.arange(5))
+    assert t.tolist() == [0, 1, 2, 3, 4] and int(st.moves) == 0 and st.converged == 1
+    p3 = T.Problem.euc2d(ctx, [0.0, 1.0, 1.0], [0.0, 0.0, 1.0])
+    t, st, _ = p3.local_search(T.ALGO_THREE_OPT, [2, 0, 1])
+    assert t.tolist() == [0, 1, 2]
+    s = T.Problem.euc2d(ctx, [0.0, 1.0, 1.0, 0.0], [0.0, 0.0, 1.0, 1.0]).session(T.ALGO_THREE_OPT, [0, 1, 2, 3])
+    assert s.scan() is None
+    s.close()
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 33, 34, 35, 66, 131])
+def test_three_opt_small_and_block_edges(T, ctx, n):
+    x, y = O.gen_uniform(n, 700 + n)
+    check_three_opt(T, ctx, O.Problem(x, y), T.Problem.euc2d(ctx, x, y), O.shuffle_tour(n, n + 3), max_moves=40)
+
+
+def test_three_opt_ties_nint_and_explicit(T, ctx, golden_dir):
+    rng = np.random.default_rng(21)
+    x = rng.integers(0, 8, 70).astype(np.float32)
+    y = rng.integers(0, 8, 70).astype(np.float32)  # lattice: many equal savings
+    check_three_opt(T, ctx, O.Problem(x, y), T.Problem.euc2d(ctx, x, y), O.shuffle_tour(70, 2), max_moves=40)
+    gx, gy = O.gen_grid(80, 5)
+    Pi = O.Problem(tri=O.matrix_packed_nint(gx, gy), n=80)
+    check_three_opt(T, ctx, Pi, T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32), O.shuffle_tour(80, 9), max_moves=30)
+    n, tri = read_explicit(os.path.join(golden_dir, "gr17.tsp"))
+    check_three_opt(T, ctx, O.Problem(tri=tri, n=n), T.Problem.explicit(ctx, tri, n), np.arange(n))
+
+
+def test_three_opt_scan_only_600(T, ctx):
+    """One full scan of C(600,3) = 35.8 M triples against the threaded oracle."""
+    n = 600
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    t = O.shuffle_tour(n, 1)
+    s = T.Problem.euc2d(ctx, x, y).session(T.ALGO_THREE_OPT, t)
+    got = s.scan()
+    want, _ = O.three_opt_find_best(P, t, nthreads=8)
+    assert got is not None and got[1:] == want[1:] and np.float32(got[0]) == np.float32(want[0])
+    s.close()

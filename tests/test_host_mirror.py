@@ -126,6 +126,9 @@ def test_cli_goldens_berlin52(bins):
     # G6: `teeline solve or_opt` (docs/benchmarks.md:48)
     rc, out, _ = run([cli, "solve", "or_opt", "-i", inp])
     assert rc == 0 and parse_cli(out) == ("8097.47607", 0, [int(ids[p]) for p in O.or_opt(P, nn)[0]])
+    # G7: `teeline solve 3opt` = nn -> 3opt (docs/benchmarks.md:29)
+    rc, out, _ = run([cli, "solve", "3opt", "-i", inp])
+    assert rc == 0 and parse_cli(out) == ("7742.64697", 0, [int(ids[p]) for p in O.three_opt(P, nn)[0]])
     # stdin input + JSON output (main.rs:694-707)
     rc, out, _ = run([cli, "solve", "2opt", "--output-format", "json"], stdin=open(inp).read())
     obj = json.loads(out)

@@ -224,3 +224,40 @@ def test_generators_are_deterministic():
     assert (gx == np.floor(gx)).all() and gx.max() < 1e6
     t = O.shuffle_tour(100, 5)
     assert sorted(t.tolist()) == list(range(100)) and (t != np.arange(100)).any()
+
+
+# ---- 3-opt ----------------------------------------------------------
+
+def test_three_opt_golden_G7_berlin52(berlin52):
+    """G7: NN -> 3-opt on berlin52 = 7742.65 (docs/benchmarks.md:29); 10 moves, 11 scans."""
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    t, st, mv = O.three_opt(P, O.nn_tour(P, 3), log_cap=64)
+    assert "%.5f" % O.tour_length(P, t) == "7742.64697" and "%.2f" % O.tour_length(P, t) == "7742.65"
+    assert (st.moves, st.passes) == (10, 11) and st.evals == 11 * (52 * 51 * 50 // 6 - 50)
+    assert sorted(t.tolist()) == list(range(52)) and all(1 <= m[4] <= 7 for m in mv)
+
+
+def test_three_opt_reference_unit_vectors():
+    """apply_3opt vectors (three_opt.rs:284-331) and the seeded-optimal case (:263-276)."""
+    base = [0, 1, 2, 3, 4, 5]
+    want = {1: [0, 2, 1, 3, 4, 5], 2: [0, 1, 2, 4, 3, 5], 3: [0, 2, 1, 4, 3, 5], 4: [0, 3, 4, 1, 2, 5],
+            5: [0, 3, 4, 2, 1, 5], 6: [0, 4, 3, 1, 2, 5], 7: [0, 4, 3, 2, 1, 5]}
+    for case, w in want.items():
+        assert O.three_opt_apply(base, 0, 2, 4, case).tolist() == w
+    x, y = [0.0, 0.0, 0.0, 1.0, 1.0], [0.0, 0.5, 1.0, 1.0, 0.0]
+    P = O.Problem(x, y)
+    t, st, _ = O.three_opt(P, np.arange(5))
+    assert t.tolist() == [0, 1, 2, 3, 4] and st.moves == 0
+    assert O.three_opt_find_best(O.Problem([0.0, 1.0, 1.0, 0.0], [0.0, 0.0, 1.0, 1.0]), np.arange(4))[0] is None
+
+
+def test_three_opt_threads_agree_and_improves():
+    x, y = O.gen_uniform(90, 17)
+    P = O.Problem(x, y)
+    t = O.shuffle_tour(90, 4)
+    a, ev1 = O.three_opt_find_best(P, t, nthreads=1)
+    b, ev2 = O.three_opt_find_best(P, t, nthreads=5)
+    assert a == b and a is not None and ev1 == ev2 == 90 * 89 * 88 // 6 - 88
+    t2 = O.three_opt_apply(t, a[1], a[2], a[3], a[4])
+    assert np.float32(O.tour_length(P, t2)) < np.float32(O.tour_length(P, t))
