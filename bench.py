@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark: 2-opt moves evaluated per second at n = 10 000.
 
-Contract (see the task prompt, section 4): `python bench.py --gpus N --steps K --warmup W`
-prints ONE JSON line on rank 0.
+Contract (task prompt, section 4): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.
 
-Workload (BASELINE.json configs[2]): 10 000 uniform-random EUC_2D cities
-(splitmix64, seed 10000, [0,1000)^2 on a 2^-24 grid), nearest-neighbour start tour,
-best-improvement 2-opt ("Mode B").  A STEP is one full scan of the
+Workload (BASELINE.json configs[2], the config the metric is quoted on): 10 000 cities on the
+DIMACS-style 10^6 integer grid (splitmix64, seed 10000), TSPLIB nint distances, the int32
+distance matrix resident in HBM (n x ld x 4 B = 400 MB, larger than L2), nearest-neighbour
+start tour, best-improvement 2-opt ("Mode B").  A STEP is one full scan of the
 P(n) = (n-3)(n-2)/2 = 49 975 003 candidate moves plus the application of the best one.
 `value` = moves evaluated per second with everything resident in HBM.
-`e2e`   = the same metric through the C ABI with HOST buffers: each e2e step is one
-          tl_problem_create_euc2d + tl_local_search(max_moves = E) + tour read-back.
-With N > 1 every rank runs an independent replica from its own start tour
-(multi-start; no data-path collective) -> weak scaling.
+`e2e`   = the same metric through the C ABI with HOST buffers: one e2e step is the call a
+          `teeline solve nn,2opt` user makes -- tl_problem_create_euc2d (coordinates up),
+          tl_local_search to the 2-opt local optimum (matrix build + every scan+apply), tour
+          read-back -- so it is also BASELINE's second figure, wall time to the local optimum.
+`--path recompute --dist f32` benches the coordinate-recompute path instead; both alternatives
+are always reported under `other_paths`.
+With N > 1 every rank runs an independent instance (seed + rank; no data-path collective) ->
+weak scaling.
 
-`--impl reference` times the CPU oracle port of the same step (the reference itself is
-Rust and cannot be built in this image) with all host threads.
+`--impl reference` times the CPU oracle port of the same step on the same configuration (the
+reference itself is Rust and cannot be built in this image) with all host threads.
 """
 from __future__ import annotations
 
@@ -84,20 +89,69 @@ def pairs_per_scan(n: int) -> int:
     return (n - 3) * (n - 2) // 2
 
 
+def instance(n: int, seed: int, dist: str):
+    return gen_grid(n, seed) if dist == "nint" else gen_uniform(n, seed)
+
+
+def describe(workload: str, n: int, seed: int, path: str, dist: str) -> str:
+    coords = "10^6 integer grid, TSPLIB nint int32 distances" if dist == "nint" else \
+        "uniform [0,1000)^2 on a 2^-24 grid, f32 distances"
+    src = f"{'int32' if dist == 'nint' else 'f32'} distance matrix in HBM" if path == "matrix" else \
+        "distances recomputed from coordinates"
+    return (f"{workload}: n={n} EUC_2D ({coords}; splitmix64 seed {seed}), {src}, NN start tour, "
+            f"best-improvement 2-opt, one step = full scan of {pairs_per_scan(n)} moves + apply")
+
+
 # ---- clocks sampling ------------------------------------------------------------------------------
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every ~2 ms from a
+    thread (the timed region is tens of ms), nvidia-smi -lms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
         self.device, self.rows, self.proc = device, [], None
+        self.sm, self.reasons, self.mx, self.th, self.stop_flag = [], set(), None, None, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and vis.split(",")[device].isdigit() else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.stop_flag = False
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -108,10 +162,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def pause(self):
+        """Stop sampling between timed chunks (NVML mode only)."""
+        if self.nvml is not None and self.th is not None:
+            self.stop_flag = True
+            self.th.join()
+            self.th = None
+
     def stop(self):
+        if self.nvml is not None:
+            self.pause()
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml, 2 ms period, "
+                    "sampled only while the timed steps were running"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -132,16 +198,28 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # ---- CPU baseline (the oracle; never on the product path) ----------------------------------------------
 
-def cpu_scan_rate(n: int, seed: int, threads: int, budget_s: float):
-    """Times full Mode B scans of the oracle on the host cores; returns (moves/s, scans, seconds)."""
+def oracle_problem(n: int, seed: int, path: str, dist: str):
+    """The CPU twin of the benched configuration: packed int32/f32 triangle for the matrix-backed
+    paths (what DistanceMatrix holds, distance_matrix.rs:122-153), coordinates for recompute."""
     import oracle as O
-    x, y = O.gen_uniform(n, seed)
-    P = O.Problem(x, y)
+    x, y = instance(n, seed, dist)
+    if dist == "nint":
+        P = O.Problem(tri=O.matrix_packed_nint(x, y), n=n)
+    elif path == "matrix":
+        P = O.Problem(tri=O.matrix_packed_f32(x, y), n=n)
+    else:
+        P = O.Problem(x, y)
+    return O, P
+
+
+def cpu_scan_rate(n: int, seed: int, path: str, dist: str, threads: int, budget_s: float):
+    """Times full Mode B scans of the oracle on the host cores; returns (moves/s, scans, seconds)."""
+    O, P = oracle_problem(n, seed, path, dist)
     tour = O.nn_tour(P, 3)
     O.two_opt_best_scan(P, tour, nthreads=threads)  # warm
     t0 = time.perf_counter()
@@ -159,11 +237,9 @@ def run_reference(args, rank: int, world: int):
     """--impl reference: the CPU port of the same step (scan + apply), all host threads."""
     if rank != 0:
         return
-    import oracle as O
     n, seed = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    x, y = O.gen_uniform(n, seed)
-    P = O.Problem(x, y)
+    O, P = oracle_problem(n, seed, args.path, args.dist)
     tour = O.nn_tour(P, 3).copy()
     budget = 150.0
     done, t_all = 0, 0.0
@@ -185,9 +261,12 @@ def run_reference(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / done, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: n={n} uniform EUC_2D seed {seed}, NN start, Mode B scan+apply",
-                   "note": "CPU oracle port of the reference semantics (Rust reference not buildable here: no cargo)"},
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32" if args.dist == "nint" else "f32",
+        "data": "synthetic",
+        "config": {"workload": describe(args.workload, n, seed, args.path, args.dist),
+                   "path": args.path, "dist": args.dist,
+                   "note": "CPU oracle port of the reference semantics over the packed lower-triangle "
+                           "matrix (Rust reference not buildable here: no cargo)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -212,39 +291,51 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n, seed = WORKLOADS[args.workload]
+    n, seed0 = WORKLOADS[args.workload]
+    seed = seed0 + rank  # one independent instance per rank
     P = pairs_per_scan(n)
-    x, y = gen_uniform(n, seed)
+    kinds = {"nint": T.DIST_NINT_I32, "f32": T.DIST_F32_EXACT}
+    paths = {"recompute": T.PATH_RECOMPUTE, "matrix": T.PATH_MATRIX}
+    x, y = instance(n, seed, args.dist)
     stream = torch.cuda.current_stream().cuda_stream
     ctx = T.Context(local_rank, stream=stream)
-    prob = T.Problem.euc2d(ctx, x, y)
-    # start tour: rank 0 = nearest neighbour (the reference's `nn,2opt` pipeline); other ranks
-    # = independent multi-start tours
-    start = prob.nn_tour(3) if rank == 0 else shuffle_tour(n, rank)
-    path = {"recompute": T.PATH_RECOMPUTE, "matrix": T.PATH_MATRIX, "auto": T.PATH_AUTO}[args.path]
-    sess = prob.session(T.ALGO_TWO_OPT_BEST, start, path)
+    prob = T.Problem.euc2d(ctx, x, y, kinds[args.dist])
+    start = prob.nn_tour(3)  # the reference's `nn,2opt` pipeline
+    path = paths[args.path]
 
-    # --- device-resident timing: W warm-up steps, then exactly K steps
-    sess.enqueue(args.warmup)
-    barrier()
+    # --- device-resident timing: exactly K timed steps after W warm-up steps.  A session converges
+    #     after ~1500 moves, so K is cut into chunks; every chunk runs on a fresh session of the same
+    #     instance (warm-up again, untimed) and is bracketed by barrier + synchronize on both sides.
+    chunk_cap = max(1, min(args.chunk, args.steps))
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    sess.enqueue(args.steps)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launches - l0
+    ms, left, launches, sess, moves_applied = 0.0, args.steps, 0, None, 0
+    while left > 0:
+        k = min(chunk_cap, left)
+        if sess is not None:
+            sess.close()
+        sess = prob.session(T.ALGO_TWO_OPT_BEST, start, path)
+        sess.enqueue(args.warmup)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        sess.enqueue(k)
+        e1.record()
+        barrier()
+        if rank == 0:
+            sampler.pause()
+        ms += e0.elapsed_time(e1)
+        launches += ctx.launches - l0
+        real = int(sess.stats().moves)
+        if real < args.warmup + k:
+            raise SystemExit(f"bench invalid: the tour converged after {real} moves, fewer than "
+                             f"warmup+chunk={args.warmup + k}; lower --chunk")
+        moves_applied += k
+        left -= k
     clocks = sampler.stop() if rank == 0 else None
-    st = sess.stats()
-    real_steps = int(st.moves)
-    if real_steps < args.warmup + args.steps:
-        raise SystemExit(f"bench invalid: the tour converged after {real_steps} moves, fewer than "
-                         f"warmup+steps={args.warmup + args.steps}; lower --steps")
     if dist is not None:
         tms = torch.tensor([ms], device="cuda")
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -253,54 +344,58 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # --- dominant kernel: average launch duration of the scan kernel (CUDA events, same stream)
     scan_ms = sess.time_scans(max(10, min(args.steps, 200)))
-    stats_path = int(st.path_used)
+    stats_path = int(sess.stats().path_used)
+    sess.close()
 
-    # --- the matrix-backed paths on the same workload (BASELINE configs[2]: "int32 matrix-backed"):
-    #     f32 matrix of the same instance, and the TSPLIB nint int32 matrix of the integer-grid instance
+    # --- the alternatives on the same workload size, always reported
+    def probe(label, p_path, p_dist):
+        gx, gy = instance(n, seed, p_dist)
+        p2 = T.Problem.euc2d(ctx, gx, gy, kinds[p_dist])
+        s2 = p2.session(T.ALGO_TWO_OPT_BEST, p2.nn_tour(3), paths[p_path])
+        s2.enqueue(args.warmup)
+        torch.cuda.synchronize()
+        k = min(args.steps, 200)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        s2.enqueue(k)
+        a1.record()
+        torch.cuda.synchronize()
+        step_ms2 = a0.elapsed_time(a1) / k
+        scan_ms2 = s2.time_scans(k)
+        s2.close()
+        p2.close()
+        kern = "two_opt_scan_matrix_kernel" if p_path == "matrix" else "two_opt_scan_recompute_kernel"
+        return {"path": p_path, "dist": p_dist, "ms_per_step": step_ms2, "value": P / (step_ms2 * 1e-3),
+                "kernel_ms": scan_ms2, "kernel": kern, "scan_moves_per_s": P / (scan_ms2 * 1e-3)}
+
     other_paths = {}
     if rank == 0 and args.workload != "n100k":
-        for label, kind in (("matrix_f32", T.DIST_F32_EXACT), ("matrix_nint_i32", T.DIST_NINT_I32)):
-            if stats_path == T.PATH_MATRIX and kind == T.DIST_F32_EXACT:
-                continue
-            gx, gy = (x, y) if kind == T.DIST_F32_EXACT else gen_grid(n, seed)
-            p2 = T.Problem.euc2d(ctx, gx, gy, kind)
-            s2 = p2.session(T.ALGO_TWO_OPT_BEST, p2.nn_tour(3), T.PATH_MATRIX)
-            s2.enqueue(args.warmup)
-            torch.cuda.synchronize()
-            k = min(args.steps, 100)
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            s2.enqueue(k)
-            a1.record()
-            torch.cuda.synchronize()
-            step_ms2 = a0.elapsed_time(a1) / k
-            scan_ms2 = s2.time_scans(k)
-            other_paths[label] = {"ms_per_step": step_ms2, "value": P / (step_ms2 * 1e-3), "kernel_ms": scan_ms2,
-                                  "kernel": "two_opt_scan_matrix_kernel", "scan_moves_per_s": P / (scan_ms2 * 1e-3)}
-            s2.close()
-            p2.close()
+        for label, p_path, p_dist in (("matrix_nint_i32", "matrix", "nint"), ("matrix_f32", "matrix", "f32"),
+                                      ("recompute_f32", "recompute", "f32")):
+            if (p_path, p_dist) != (args.path, args.dist):
+                other_paths[label] = probe(label, p_path, p_dist)
 
-    # --- end to end through the C ABI with host buffers (pinned), copies inside the timed region
-    e2e_moves = args.e2e_moves
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    # --- end to end through the C ABI with host buffers (pinned), copies inside the timed region:
+    #     coordinates up, the whole local search to the 2-opt optimum, tour back
+    e2e_steps = max(1, args.e2e_steps)
     hx = torch.from_numpy(x).pin_memory().numpy()
     hy = torch.from_numpy(y).pin_memory().numpy()
     htour = torch.from_numpy(start.astype(np.uint32).view(np.int32)).pin_memory().numpy().view(np.uint32)
 
     def e2e_step():
-        p2 = T.Problem.euc2d(ctx, hx, hy)
-        t2, st2, _ = p2.local_search(T.ALGO_TWO_OPT_BEST, htour, path=path, max_moves=e2e_moves)
+        p2 = T.Problem.euc2d(ctx, hx, hy, kinds[args.dist])
+        t2, st2, _ = p2.local_search(T.ALGO_TWO_OPT_BEST, htour, path=path, max_moves=args.e2e_moves)
         p2.close()
-        return int(st2.evals), t2
+        return int(st2.evals), int(st2.moves), t2
 
-    for _ in range(2):
-        e2e_step()
+    e2e_step()
     barrier()
     t0 = time.perf_counter()
-    evals = 0
+    evals = e2e_applied = 0
     for _ in range(e2e_steps):
-        ev, _t = e2e_step()
+        ev, mv, _t = e2e_step()
         evals += ev
+        e2e_applied += mv
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if dist is not None:
@@ -323,7 +418,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     traffic = {}
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -338,32 +433,35 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "kernel": "two_opt_scan_matrix_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_move": 4,
                 "algorithmic_bytes_per_launch": 4 * P}
 
-    for label, o in other_paths.items():
-        o["roofline"] = hbm_roofline(o["kernel_ms"], label)
-    if stats_path == T.PATH_MATRIX:
-        roofline = hbm_roofline(scan_ms, "matrix_f32")
-    else:
+    def fp32_roofline(kernel_ms):
         ffma, mufu = ctx.microbench_fp32()
-        flops = 15.0 * P / (scan_ms * 1e-3)  # 13 FP32 ops + 2 sqrt per move
-        roofline = {"bound": "fp32_issue", "achieved": flops / 1e12, "peak": ffma / 1e12, "unit": "TFLOP/s",
-                    "frac": flops / ffma,
-                    "peak_source": "measured here: dependent-free FFMA stream, lane-instructions/s "
-                                   "(tl_microbench_fp32); MEASURED_PEAKS.json has no FP32 figure",
-                    "kernel": "two_opt_scan_recompute_kernel", "kernel_ms": scan_ms,
-                    "algorithmic_flop_per_move": 15, "mufu_peak_per_s": mufu,
-                    "traffic": traffic.get("recompute", {}).get("bytes_per_launch") if args.workload == "n10k" else None,
-                    "traffic_source": traffic.get("recompute", {}).get("source"),
-                    "note": "coordinate-recompute path: ~0 bytes/move, bound by FP32 issue, not HBM or tensor"}
+        flops = 15.0 * P / (kernel_ms * 1e-3)  # 13 FP32 ops + 2 sqrt per move
+        t = traffic.get("recompute", {}) if args.workload == "n10k" else {}
+        return {"bound": "fp32_issue", "achieved": flops / 1e12, "peak": ffma / 1e12, "unit": "TFLOP/s",
+                "frac": flops / ffma,
+                "peak_source": "measured here: dependent-free FFMA stream, lane-instructions/s "
+                               "(tl_microbench_fp32); MEASURED_PEAKS.json has no FP32 figure",
+                "kernel": "two_opt_scan_recompute_kernel", "kernel_ms": kernel_ms,
+                "algorithmic_flop_per_move": 15, "mufu_peak_per_s": mufu,
+                "traffic": t.get("bytes_per_launch"), "traffic_source": t.get("source"),
+                "note": "coordinate-recompute path: ~0 bytes/move, bound by FP32 issue, not HBM or tensor"}
+
+    for label, o in other_paths.items():
+        o["roofline"] = hbm_roofline(o["kernel_ms"], label) if o["path"] == "matrix" else fp32_roofline(o["kernel_ms"])
+    if stats_path == T.PATH_MATRIX:
+        roofline = hbm_roofline(scan_ms, "matrix_nint_i32" if args.dist == "nint" else "matrix_f32")
+    else:
+        roofline = fp32_roofline(scan_ms)
     roofline["kernel_share_of_step"] = scan_ms / (ms / args.steps)
 
     # --- CPU baseline: the oracle port on the host cores (bounded sample)
     threads = os.cpu_count() or 1
-    cpu_v, cpu_scans, cpu_dt = cpu_scan_rate(n, seed, threads, args.cpu_budget)
-    cpu_v1, cpu_scans1, cpu_dt1 = cpu_scan_rate(n, seed, 1, min(args.cpu_budget, 4.0))
+    cpu_v, cpu_scans, cpu_dt = cpu_scan_rate(n, seed, args.path, args.dist, threads, args.cpu_budget)
+    cpu_v1, cpu_scans1, cpu_dt1 = cpu_scan_rate(n, seed, args.path, args.dist, 1, min(args.cpu_budget, 4.0))
     cpu_baseline = {
         "value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
         "sample": f"{cpu_scans} full Mode B scans of the same n={n} tour in {cpu_dt:.1f} s, {threads} threads "
-                  f"(row-parallel oracle scan)",
+                  f"(row-parallel oracle scan over the same {'packed matrix' if args.path == 'matrix' or args.dist == 'nint' else 'coordinates'})",
         "single_thread_value": cpu_v1,
         "note": "C oracle with flat arrays; the Rust reference is single-threaded and pays 2 SipHash "
                 "lookups per distance, so this over-states the reference's speed",
@@ -372,22 +470,27 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: n={n} uniform EUC_2D (splitmix64 seed {seed}), NN start tour, "
-                               f"best-improvement 2-opt, one step = full scan of {P} moves + apply",
-                   "path": "matrix" if stats_path == T.PATH_MATRIX else "recompute",
-                   "l2": "inputs larger than L2 (400 MB matrix)" if stats_path == T.PATH_MATRIX else
+        "vs_baseline": None, "dtype": "int32" if args.dist == "nint" else "f32", "data": "synthetic",
+        "config": {"workload": describe(args.workload, n, seed0, args.path, args.dist),
+                   "path": "matrix" if stats_path == T.PATH_MATRIX else "recompute", "dist": args.dist,
+                   "l2": f"inputs larger than L2 ({4 * n * ((n + 31) // 32 * 32) / 1e6:.0f} MB matrix, "
+                         f"{4 * P / 1e6:.0f} MB read per scan, L2 126 MB); no flush" if stats_path == T.PATH_MATRIX else
                          "compute-bound kernel: 160 KB of tour-ordered points, L2 state irrelevant",
-                   "parallelism": f"replicas x{world} (independent multi-start tours)"},
+                   "timed_region": f"{args.steps} steps in chunks of <= {chunk_cap}; each chunk on a fresh session "
+                                   f"after {args.warmup} untimed warm-up steps, CUDA events, max over ranks",
+                   "parallelism": f"independent instances x{world} (seed + rank), no data-path collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "step": f"tl_problem_create_euc2d + tl_local_search(max_moves={e2e_moves}) + tour read-back, "
-                        f"{e2e_steps} calls, pinned host buffers", "seconds": dt},
+                "step": "tl_problem_create_euc2d + tl_local_search(" +
+                        ("to the 2-opt local optimum" if args.e2e_moves < 0 else f"max_moves={args.e2e_moves}") +
+                        f") + tour read-back, {e2e_steps} calls, pinned host buffers",
+                "seconds": dt, "wall_ms_per_call": 1e3 * dt / e2e_steps,
+                "moves_applied_per_call": e2e_applied / e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "other_paths": other_paths,
-        "moves_applied": real_steps,
+        "moves_applied": moves_applied,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -397,21 +500,29 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="n10k", choices=sorted(WORKLOADS))
-    ap.add_argument("--path", default="auto", choices=["auto", "recompute", "matrix"])
-    ap.add_argument("--e2e-moves", type=int, default=100)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--path", default="matrix", choices=["recompute", "matrix"])
+    ap.add_argument("--dist", default="nint", choices=["nint", "f32"])
+    ap.add_argument("--chunk", type=int, default=1000, help="timed steps per session (a tour converges)")
+    ap.add_argument("--e2e-moves", type=int, default=-1, help="-1: to the local optimum")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.path == "recompute" and args.dist == "nint":
+        args.dist = "f32"  # the recompute kernels evaluate the f32 metric
+    if args.workload == "n100k":
+        args.path, args.dist, args.chunk = "recompute", "f32", min(args.chunk, 50)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if args.steps > 50:
+            args.steps = 50  # bounded sample: ~30 ms per CPU step
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

@@ -37,8 +37,10 @@ else:
         env = dict(os.environ)
         if lib and lib.endswith(".so"):
             env["TL_LIB"] = lib
-        elif lib:
-            env[lib] = "1"
+        elif lib:  # "NAME" or "NAME=V;NAME2=V2"
+            for kv in lib.split(";"):
+                k, _, v = kv.partition("=")
+                env[k] = v or "1"
         r = subprocess.run([sys.executable, __file__, "child"] + (sys.argv[1:] or ["10000", "100000"]), env=env, capture_output=True, text=True)
         print(os.path.basename(lib) if lib else "default", r.stdout.strip() or r.stderr[-400:], flush=True)
     print("columns per case: scan_us, scan Tmove/s, step_us, step Tmove/s")

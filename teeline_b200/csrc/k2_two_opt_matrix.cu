@@ -66,6 +66,18 @@ __device__ __forceinline__ V ld_stream(const V *p)
     return Val<V>::from_bits(v);
 }
 
+// L2 residency (the matrix is larger than L2 but a scan re-reads the same elements every step):
+// loads of matrix rows whose SLOT is below pin_rows carry an L2 evict_last policy, every other
+// load evict_first, so that a fixed ~L2-sized part of the matrix survives from scan to scan and
+// only the rest streams from HBM.  The policy is chosen per row (warp-uniform).
+template <typename V>
+__device__ __forceinline__ V ld_hint(const V *p, uint64_t pol)
+{
+    int32_t v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return Val<V>::from_bits(v);
+}
+
 // Tail of a fused step (last CTA only), out of line so that it does not weigh on the scan loop's
 // register allocation: reduce the per-CTA records, reverse the segment, update the loop state.
 template <typename V>
@@ -102,12 +114,12 @@ __device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, ui
     }
 }
 
-template <typename V>
+template <typename V, bool PIN>
 __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     two_opt_scan_matrix_kernel(const V *__restrict__ M, uint32_t ld, Cs *__restrict__ cs, const ScanGeom g,
                                const int32_t *__restrict__ band_first, Best<V> *__restrict__ blockbest,
                                DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
-                               uint64_t log_cap, int fuse_apply)
+                               uint64_t log_cap, int fuse_apply, int pin_rows)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     griddep_launch_dependents(); // PDL, as in k2_two_opt.cu
@@ -116,6 +128,18 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     int2 *srow = reinterpret_cast<int2 *>(smem_raw) + warp * WARP_RECS;
     int2 *scol = srow + ROWS_CAP;
     Best<V> *red = reinterpret_cast<Best<V> *>(smem_raw + (size_t)WARPS * WARP_RECS * sizeof(int2));
+
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if constexpr (PIN) {
+        asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    }
+    auto ld_row = [&](const V *p, uint64_t pol) {
+        if constexpr (PIN)
+            return ld_hint(p, pol);
+        else
+            return ld_stream(p);
+    };
 
     V best = (V)0;
     uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
@@ -163,15 +187,19 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
             // cover HBM latency at 24 warps per SM (Little: ~40 KB per SM at 6.5 TB/s).
             V E[R], buf[D][R];
             {
-                const V *row0 = M + (size_t)srow[0].x * ld;
+                const int slot0 = srow[0].x;
+                const V *row0 = M + (size_t)slot0 * ld;
+                const uint64_t pol = slot0 < pin_rows ? pol_keep : pol_stream;
 #pragma unroll
-                for (int r = 0; r < R; ++r) E[r] = ld_stream(row0 + scol[lane + 32 * r].x);
+                for (int r = 0; r < R; ++r) E[r] = ld_row(row0 + scol[lane + 32 * r].x, pol);
             }
             auto issue = [&](auto Dc, int t) { // loads of row step t into buf[Dc]
                 constexpr int d = decltype(Dc)::value;
-                const V *rown = M + (size_t)srow[t + 1].x * ld;
+                const int slotn = srow[t + 1].x;
+                const V *rown = M + (size_t)slotn * ld;
+                const uint64_t pol = slotn < pin_rows ? pol_keep : pol_stream;
 #pragma unroll
-                for (int r = 0; r < R; ++r) buf[d][r] = ld_stream(rown + scol[t + 1 + lane + 32 * r].x);
+                for (int r = 0; r < R; ++r) buf[d][r] = ld_row(rown + scol[t + 1 + lane + 32 * r].x, pol);
             };
             static_for<D>([&](auto Dc) {
                 constexpr int d = decltype(Dc)::value;
@@ -299,35 +327,57 @@ size_t scan_matrix_smem_bytes()
 
 cudaError_t scan_matrix_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(two_opt_scan_matrix_kernel<float>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_matrix_smem_bytes());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(two_opt_scan_matrix_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)scan_matrix_smem_bytes());
+    const int smem = (int)scan_matrix_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(two_opt_scan_matrix_kernel<float, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(two_opt_scan_matrix_kernel<float, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(two_opt_scan_matrix_kernel<int32_t, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(two_opt_scan_matrix_kernel<int32_t, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e;
 }
 
 void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_first, void *blockbest,
                         DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap, bool fuse_apply,
-                        int grid, cudaStream_t st)
+                        int grid, const MatPin &pin, cudaStream_t st)
 {
     const size_t smem = scan_matrix_smem_bytes();
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    int nattr = 1;
+    if (pin.window_bytes > 0) { // driver-managed residency: persisting window over the first matrix rows
+        attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[1].val.accessPolicyWindow.base_ptr = const_cast<void *>(src.M);
+        attr[1].val.accessPolicyWindow.num_bytes = pin.window_bytes;
+        attr[1].val.accessPolicyWindow.hitRatio = pin.window_hit_ratio;
+        attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        nattr = 2;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(WARPS * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = nattr;
     const int fuse = fuse_apply ? 1 : 0;
-    if (src.is_int())
-        cudaLaunchKernelEx(&cfg, two_opt_scan_matrix_kernel<int32_t>, (const int32_t *)src.M, src.ld, src.cs, g,
-                           band_first, (BestI *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse);
-    else
-        cudaLaunchKernelEx(&cfg, two_opt_scan_matrix_kernel<float>, (const float *)src.M, src.ld, src.cs, g,
-                           band_first, (BestF *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse);
+    const int pin_rows = pin.hint_rows;
+#define TL_LAUNCH_MAT(V, PINNED, BEST)                                                                          \
+    cudaLaunchKernelEx(&cfg, two_opt_scan_matrix_kernel<V, PINNED>, (const V *)src.M, src.ld, src.cs, g,        \
+                       band_first, (BEST *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse, pin_rows)
+    if (src.is_int()) {
+        if (pin_rows > 0) TL_LAUNCH_MAT(int32_t, true, BestI); else TL_LAUNCH_MAT(int32_t, false, BestI);
+    } else {
+        if (pin_rows > 0) TL_LAUNCH_MAT(float, true, BestF); else TL_LAUNCH_MAT(float, false, BestF);
+    }
+#undef TL_LAUNCH_MAT
 }
 
 void launch_build_cs(const Src &src, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st)

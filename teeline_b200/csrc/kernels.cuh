@@ -157,9 +157,21 @@ constexpr int kMatMinBlocks = TL_MAT_MINB;
 constexpr int kMatD = TL_MAT_D;          // prefetch depth in row steps
 size_t scan_matrix_smem_bytes();
 cudaError_t scan_matrix_configure();
+#ifndef TL_MAT_PIN_MB
+#define TL_MAT_PIN_MB 0
+#endif
+constexpr double kMatPinMB = TL_MAT_PIN_MB; // default size of the L2-resident part (0 = off until measured)
+// L2 residency of a matrix larger than L2 (k2_two_opt_matrix.cu): either per-load eviction
+// hints on the rows with slot < hint_rows, or a driver access-policy window over the first
+// window_bytes of M (needs the persisting-L2 carve-out, session.cu); both 0 = plain streaming.
+struct MatPin {
+    int hint_rows = 0;
+    size_t window_bytes = 0;
+    float window_hit_ratio = 1.0f;
+};
 void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_first, void *blockbest,
                         DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap, bool fuse_apply,
-                        int grid, cudaStream_t st);
+                        int grid, const MatPin &pin, cudaStream_t st);
 // cs[q] = {slot = q, sp = M[q-1][q], city = tour[q]} (+ wrap copy at n when cyclic, -inf padding)
 void launch_build_cs(const Src &src, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st);
 // slot-ordered scratch for (re)building the matrix in tour order: from `tour` (session start)

@@ -13,7 +13,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 using namespace tl;
 
@@ -51,6 +53,7 @@ struct tl_session {
     int repermute_every = 0;     // matrix path: re-lay M in tour order every this many steps (0 = never)
     uint32_t steps_since_permute = 0;
     uint64_t repermutes = 0;
+    MatPin pin;                  // matrix path: L2 residency of part of a matrix larger than L2
 
     DevBuf<unsigned char> tmp;     // Or-opt: relocated range staging (npad records of 16 B)
     DevBuf<unsigned char> rowinfo; // Or-opt: per-row removal gains (npad x 16 B)
@@ -217,6 +220,48 @@ void build_matrix(tl_session *s, const uint32_t *d_tour)
     s->c->launches += 2;
 }
 
+// A Mode B scan reads every upper-triangle element once and the next scan reads (almost) the same
+// elements again.  When the matrix does not fit L2, keep a fixed part of it resident: the first
+// `rows` physical rows, whose scanned part is about `pin_mb` MB.
+//   TL_MAT_PIN_MB=<mb>      size of the resident part (0 disables; default kMatPinMB)
+//   TL_MAT_PIN_MODE=hint    per-load L2 eviction hints (default)
+//   TL_MAT_PIN_MODE=window  driver access-policy window + persisting-L2 carve-out
+void configure_matrix_pin(tl_session *s, size_t matrix_bytes)
+{
+    s->pin = MatPin{};
+    if (s->algo != TL_ALGO_TWO_OPT_BEST && s->algo != TL_ALGO_TWO_OPT_BEST_CYCLIC) return;
+    int l2 = 0;
+    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, s->c->device);
+    if (matrix_bytes / 2 <= (size_t)l2 * 3 / 4) return; // the scanned triangle already lives in L2
+    double pin_mb = kMatPinMB;
+    if (const char *ev = getenv("TL_MAT_PIN_MB")) pin_mb = atof(ev);
+    if (pin_mb <= 0) return;
+    // rows r of the scanned triangle hold (n - r) elements: smallest r0 with sum_{r<r0} 4 (n - r) >= pin bytes
+    const double n = (double)s->n, want = pin_mb * 1048576.0 / 4.0;
+    const double disc = n * n - 2.0 * want;
+    const int rows = disc <= 0 ? (int)s->n : (int)std::ceil(n - std::sqrt(disc));
+    const char *mode = getenv("TL_MAT_PIN_MODE");
+    if (mode && !strcmp(mode, "window")) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, s->c->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, s->c->device);
+        if (getenv("TL_DEBUG_PIN"))
+            fprintf(stderr, "[tl] L2 %d B, max persisting %d B, max window %d B, rows %d\n", l2, max_persist, max_window, rows);
+        if (max_persist <= 0 || max_window <= 0) return;
+        const size_t carve = std::min<size_t>((size_t)max_persist, (size_t)(pin_mb * 1048576.0));
+        const cudaError_t le = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        if (getenv("TL_DEBUG_PIN")) fprintf(stderr, "[tl] set persisting carve-out %zu B: %s\n", carve, cudaGetErrorString(le));
+        if (le != cudaSuccess) { cudaGetLastError(); return; }
+        const size_t span = std::min<size_t>((size_t)rows * s->ld * 4, (size_t)max_window);
+        s->pin.window_bytes = span;
+        // the window spans whole rows (both triangles); only about pin_mb of it is ever touched
+        s->pin.window_hit_ratio = 1.0f;
+        if (const char *hr = getenv("TL_MAT_PIN_HIT")) s->pin.window_hit_ratio = (float)atof(hr);
+    } else {
+        s->pin.hint_rows = rows;
+    }
+}
+
 void repermute(tl_session *s)
 {
     build_matrix(s, nullptr);
@@ -243,7 +288,7 @@ tl_status launch_scan(tl_session *s, bool fuse)
         s->c->launches += 2;
     } else if (s->matrix()) {
         launch_scan_matrix(s->src, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p, s->log_cap,
-                           fuse && s->shard_count == 1, s->grid, st);
+                           fuse && s->shard_count == 1, s->grid, s->pin, st);
         s->c->launches++;
     } else {
         launch_scan_recompute(s->pts.p, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p,
@@ -477,6 +522,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         // re-lay the matrix in tour order only when it cannot live in L2 (gathers are cheap there)
         s->repermute_every = bytes > ((size_t)96 << 20) ? 64 : 0;
         if (const char *ev = getenv("TL_REPERMUTE_EVERY")) s->repermute_every = atoi(ev);
+        configure_matrix_pin(s, bytes);
     } else {
         if (s->pts.alloc(s->npad) != cudaSuccess) { set_error("tl_session_create: device allocation failed"); return fail(TL_ERR_NOMEM); }
         s->src.kind = p->fast_sqrt ? SRC_EUC_FAST : SRC_EUC_SAFE;

@@ -525,6 +525,29 @@ def test_matrix_path_repermutation_keeps_results(T, ctx, monkeypatch):
     assert [m[1:] for m in mv] == [m[1:] for m in want_mv] and (got_t.astype(np.int64) == want_t).all()
 
 
+@pytest.mark.parametrize("mode", ["hint", "window"])
+@pytest.mark.parametrize("kind", ["f32", "nint"])
+def test_matrix_l2_residency_keeps_results(T, ctx, monkeypatch, mode, kind):
+    """Keeping part of a larger-than-L2 matrix resident in L2 (eviction hints or an access-policy
+    window) is a cache policy only: same moves as the oracle, step after step."""
+    n = 9000
+    monkeypatch.setenv("TL_MAT_PIN_MB", "48")
+    monkeypatch.setenv("TL_MAT_PIN_MODE", mode)
+    monkeypatch.setenv("TL_REPERMUTE_EVERY", "5")
+    if kind == "f32":
+        x, y = O.gen_uniform(n, 77)
+        P, dk = O.Problem(x, y), T.DIST_F32_EXACT
+    else:
+        x, y = O.gen_grid(n, 77)
+        P, dk = O.Problem(tri=O.matrix_packed_nint(x, y), n=n), T.DIST_NINT_I32
+    start = O.shuffle_tour(n, 5)
+    want_t, _, want_mv = O.two_opt_best(P, start, max_moves=12, nthreads=8, log_cap=64)
+    prob = T.Problem.euc2d(ctx, x, y, dk)
+    got_t, st, mv = prob.local_search(T.ALGO_TWO_OPT_BEST, start, path=T.PATH_MATRIX, max_moves=12, log_cap=64)
+    assert int(st.repermutes) >= 2
+    assert [m[1:] for m in mv] == [m[1:] for m in want_mv] and (got_t.astype(np.int64) == want_t).all()
+
+
 def test_matrix_scan_only_10k_f32_and_i32(T, ctx):
     n = 10000
     x, y = O.gen_uniform(n, n)
