@@ -30,6 +30,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace tl {
@@ -56,8 +57,7 @@ struct BatchCounters {
 
 // SCREEN: as in k2_two_opt.cu -- the walk evaluates deltas with the screening distance and
 // re-evaluates exactly (from the shared-memory records) whenever a row step comes within the
-// rigorous margin of the running best.  MAXT / MINB: launch bounds; small tours run 128 threads
-// with 7 resident CTAs per SM (1036 tours in flight on 148 SMs), large ones 256 threads.
+// rigorous margin of the running best.  MAXT / MINB: launch bounds of one configuration (kCfgs).
 template <bool FAST, bool SCREEN, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     two_opt_batch_kernel(const float2 *__restrict__ xy, uint32_t *__restrict__ tours, uint32_t n, uint32_t batch,
@@ -242,41 +242,54 @@ size_t two_opt_batch_counter_bytes() { return sizeof(BatchCounters); }
 
 namespace {
 
-constexpr int kSmallT = 128, kSmallMinB = 7; // 7 x 148 = 1036 tours in flight
-constexpr int kLargeT = kBatchMaxThreads, kLargeMinB = 3;
+// Launch configurations (threads per tour, resident CTAs per SM).  A tour is always ONE CTA; what
+// changes is how many threads work on it.  With >= ~1000 tours per GPU the smallest CTAs fill the
+// machine (7 x 148 = 1036 tours in flight); when the batch is sharded over several GPUs, or the
+// population is small, fewer tours are in flight and each one gets more threads, up to a whole SM,
+// so that the GPU stays full (BASELINE config 5 on 8 GPUs: 128 tours per GPU).
+struct BatchCfg {
+    int threads, minb;
+};
+constexpr BatchCfg kCfgs[] = {{128, 7}, {256, 4}, {256, 3}, {512, 2}, {1024, 1}};
+constexpr int kNumCfgs = (int)(sizeof(kCfgs) / sizeof(kCfgs[0]));
+constexpr size_t kSmemPerSM = 200 * 1024; // shared memory the resident CTAs of one SM may use together
 
-// small configuration: 7 tours fit one SM
-bool use_small(uint32_t n) { return two_opt_batch_smem_bytes(n) * kSmallMinB <= 200 * 1024; }
+bool cfg_fits(int c, uint32_t n) { return two_opt_batch_smem_bytes(n) * kCfgs[c].minb <= kSmemPerSM; }
 
-// rows per work item: ~16 items per warp and scan, at least 8 rows
+// rows per work item: 16 (small CTAs) .. 2 (1024 threads) items per warp and scan (measured:
+// profiles/r01n_batch_scaling.txt), at least 8 rows:
+// an item costs a fixed prologue, so big CTAs on a short scan take longer items
 int chunk_rows(uint32_t n, int cyclic, int threads)
 {
     const int jmax = cyclic ? (int)n - 1 : (int)n - 2;
     const int nbands = ((int)n - 3 + BW - 1) / BW;
     long long rows = 0;
     for (int b = 0; b < nbands; ++b) rows += jmax - (2 + b * BW) + 1;
-    const long long want = 16LL * (threads / 32);
+    long long per_warp = threads <= 128 ? 16 : threads <= 256 ? 8 : threads <= 512 ? 4 : 2;
+    if (const char *ev = getenv("TL_BATCH_IPW")) per_warp = std::max(1, atoi(ev));
+    const long long want = per_warp * (threads / 32);
     return (int)std::max<long long>(8, (rows + want - 1) / want);
-}
-
-template <typename K>
-cudaError_t set_smem(K kern)
-{
-    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBatchMaxSmem);
 }
 
 using BatchKernel = void (*)(const float2 *, uint32_t *, uint32_t, uint32_t, int, long long, float, int, BatchCounters *);
 
-BatchKernel pick_kernel(bool small, bool fast, bool screen)
+template <int T, int MINB>
+BatchKernel pick_variant(bool fast, bool screen)
 {
-    if (small) {
-        if (fast && screen) return two_opt_batch_kernel<true, true, kSmallT, kSmallMinB>;
-        if (fast) return two_opt_batch_kernel<true, false, kSmallT, kSmallMinB>;
-        return two_opt_batch_kernel<false, false, kSmallT, kSmallMinB>;
+    if (fast && screen) return two_opt_batch_kernel<true, true, T, MINB>;
+    if (fast) return two_opt_batch_kernel<true, false, T, MINB>;
+    return two_opt_batch_kernel<false, false, T, MINB>;
+}
+
+BatchKernel pick_kernel(int cfg, bool fast, bool screen)
+{
+    switch (cfg) {
+    case 0: return pick_variant<kCfgs[0].threads, kCfgs[0].minb>(fast, screen);
+    case 1: return pick_variant<kCfgs[1].threads, kCfgs[1].minb>(fast, screen);
+    case 2: return pick_variant<kCfgs[2].threads, kCfgs[2].minb>(fast, screen);
+    case 3: return pick_variant<kCfgs[3].threads, kCfgs[3].minb>(fast, screen);
+    default: return pick_variant<kCfgs[4].threads, kCfgs[4].minb>(fast, screen);
     }
-    if (fast && screen) return two_opt_batch_kernel<true, true, kLargeT, kLargeMinB>;
-    if (fast) return two_opt_batch_kernel<true, false, kLargeT, kLargeMinB>;
-    return two_opt_batch_kernel<false, false, kLargeT, kLargeMinB>;
 }
 
 } // namespace
@@ -284,30 +297,47 @@ BatchKernel pick_kernel(bool small, bool fast, bool screen)
 cudaError_t two_opt_batch_configure()
 {
     cudaError_t e = cudaSuccess;
-    for (int small = 0; small < 2 && e == cudaSuccess; ++small)
-        for (int v = 0; v < 3 && e == cudaSuccess; ++v) e = set_smem(pick_kernel(small, v > 0, v == 2));
+    for (int c = 0; c < kNumCfgs && e == cudaSuccess; ++c)
+        for (int v = 0; v < 3 && e == cudaSuccess; ++v)
+            e = cudaFuncSetAttribute(pick_kernel(c, v > 0, v == 2), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kBatchMaxSmem);
     return e;
 }
 
-int two_opt_batch_threads(uint32_t n) { return use_small(n) ? kSmallT : kLargeT; }
+// The first configuration (fewest threads per tour) whose CTA slots the batch fills to >= 80 %;
+// a batch too small for any of them takes the largest CTAs that fit.  TL_BATCH_CFG overrides (tests).
+int two_opt_batch_config(uint32_t n, uint64_t batch, int sm_count)
+{
+    if (const char *ev = getenv("TL_BATCH_CFG")) {
+        const int c = atoi(ev);
+        if (c >= 0 && c < kNumCfgs && cfg_fits(c, n)) return c;
+    }
+    int last = -1;
+    for (int c = 0; c < kNumCfgs; ++c) {
+        if (!cfg_fits(c, n)) continue;
+        last = c;
+        if (batch * 5 >= (uint64_t)sm_count * kCfgs[c].minb * 4) return c;
+    }
+    return last < 0 ? kNumCfgs - 1 : last;
+}
 
-int two_opt_batch_grid(uint32_t n, uint64_t batch, int sm_count, bool fast, bool screen)
+int two_opt_batch_grid(int cfg, uint32_t n, uint64_t batch, int sm_count, bool fast, bool screen)
 {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(use_small(n), fast, screen),
-                                                  two_opt_batch_threads(n), two_opt_batch_smem_bytes(n));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel(cfg, fast, screen), kCfgs[cfg].threads,
+                                                  two_opt_batch_smem_bytes(n));
     if (per_sm < 1) per_sm = 1;
     const uint64_t cap = (uint64_t)sm_count * per_sm;
     return (int)(batch < cap ? batch : cap);
 }
 
-void launch_two_opt_batch(const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
+void launch_two_opt_batch(int cfg, const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
                           long long max_moves, float screen_margin, void *counters, int grid, bool fast,
                           cudaStream_t st)
 {
     const bool screen = fast && screen_margin >= 0.0f;
-    const int threads = two_opt_batch_threads(n);
-    pick_kernel(use_small(n), fast, screen)<<<grid, threads, two_opt_batch_smem_bytes(n), st>>>(
+    const int threads = kCfgs[cfg].threads;
+    pick_kernel(cfg, fast, screen)<<<grid, threads, two_opt_batch_smem_bytes(n), st>>>(
         xy, tours, n, (uint32_t)batch, cyclic, max_moves, screen_margin, chunk_rows(n, cyclic, threads),
         reinterpret_cast<BatchCounters *>(counters));
 }

@@ -182,15 +182,16 @@ void launch_reset_slots(const Src &src, uint32_t n, uint32_t npad, int cyclic, c
 
 // K2-batch: one CTA per tour, tour records in shared memory
 constexpr int kBatchR = 5;              // diagonals per thread group (odd => conflict-free LDS.128)
-constexpr int kBatchMaxThreads = 256;
 constexpr int kBatchMaxSmem = 200 * 1024;
 size_t two_opt_batch_smem_bytes(uint32_t n);
 size_t two_opt_batch_counter_bytes();
 cudaError_t two_opt_batch_configure();
-int two_opt_batch_grid(uint32_t n, uint64_t batch, int sm_count, bool fast, bool screen);
+// launch configuration (threads per tour x resident CTAs per SM) for a batch of this size
+int two_opt_batch_config(uint32_t n, uint64_t batch, int sm_count);
+int two_opt_batch_grid(int cfg, uint32_t n, uint64_t batch, int sm_count, bool fast, bool screen);
 // counters: {u64 moves, u64 scans, u32 next_tour, u32 unconverged}, zeroed by the caller;
 // screen_margin < 0 disables screening (common.cuh: kScreenMarginScale)
-void launch_two_opt_batch(const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
+void launch_two_opt_batch(int cfg, const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
                           long long max_moves, float screen_margin, void *counters, int grid, bool fast,
                           cudaStream_t st);
 

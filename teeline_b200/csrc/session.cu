@@ -803,8 +803,9 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
         const float m = p->dmax * kScreenMarginScale;
         const float margin =
             (p->fast_sqrt && std::isfinite(m) && p->dmax >= kScreenMinDmax && !getenv("TL_NO_SCREEN")) ? m : -1.0f;
-        const int grid = two_opt_batch_grid(n, batch, c->sm_count, p->fast_sqrt, margin >= 0.0f);
-        launch_two_opt_batch(p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p, grid, p->fast_sqrt, st);
+        const int cfg = two_opt_batch_config(n, batch, c->sm_count);
+        const int grid = two_opt_batch_grid(cfg, n, batch, c->sm_count, p->fast_sqrt, margin >= 0.0f);
+        launch_two_opt_batch(cfg, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p, grid, p->fast_sqrt, st);
         c->launches++;
         e = cudaGetLastError();
     }

@@ -591,6 +591,18 @@ def test_batch_small_n_matches_oracle(T, ctx, n):
         check_batch(T, ctx, x, y, tours, cyclic=cyclic)
 
 
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+def test_batch_every_launch_configuration(T, ctx, monkeypatch, cfg):
+    """128 ... 1024 threads per tour (picked by batch size so that a sharded population still fills
+    the GPU): the same tours, moves and lengths whatever the CTA size."""
+    monkeypatch.setenv("TL_BATCH_CFG", str(cfg))
+    n = 700
+    x, y = O.gen_uniform(n, 4242)
+    tours = np.stack([O.nn_tour(O.Problem(x, y), 3)] + [O.shuffle_tour(n, s) for s in range(1, 6)])
+    check_batch(T, ctx, x, y, tours, max_moves=40)
+    check_batch(T, ctx, x, y, tours[:2], cyclic=True, max_moves=25)
+
+
 def test_batch_berlin52_population(T, ctx, berlin52):
     _, x, y = berlin52
     P = O.Problem(x, y)
