@@ -22,7 +22,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         path = T.PATH_RECOMPUTE if kind == "recompute" else T.PATH_MATRIX
         s = p.session(T.ALGO_TWO_OPT_BEST, p.nn_tour(3), path)
         pairs = (n - 3) * (n - 2) // 2
-        steps = 100 if n <= 30000 else 5
+        steps = int(os.environ.get('PROBE_STEPS', 100)) if n <= 30000 else 5
         s.enqueue(5); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); s.enqueue(steps); e1.record(); torch.cuda.synchronize()

@@ -35,6 +35,30 @@ constexpr int COLS_CAP = TI + BW + 1; // positions i0+K0 .. i0+K0+cnt+BW
 constexpr int WARP_RECS = ROWS_CAP + COLS_CAP;
 constexpr int D = kMatD;              // row steps of matrix loads kept in flight per thread
 
+#ifdef TL_TIMELINE
+// Step timeline (tuning builds only, -DTL_TIMELINE): globaltimer stamps of one fused step, folded
+// into running sums by the last CTA.  tl_tmark: 0 = earliest CTA past griddep_wait, 1 = earliest
+// scan end, 2 = latest scan end, 3 = end of the previous step.  tl_tacc: sums (ns) of
+// [gap prev end -> first start, first scan end, last scan end, tail entry, reduced, reversed, done] + count.
+__device__ unsigned long long tl_tmark_par[2][4] = {{~0ull, ~0ull, 0ull, 0ull}, {~0ull, ~0ull, 0ull, 0ull}}; // by step parity
+__device__ unsigned long long tl_prev_done;
+#define tl_tmark tl_tmark_par[tl_par]
+__device__ unsigned long long tl_tacc[8];
+__device__ unsigned long long tl_tcta[3][1024]; // per CTA of the latest step: past-wait time, scan-end time, SM id
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_MARK_MIN(k) do { if (threadIdx.x == 0) { const unsigned long long t_ = gtime(); atomicMin(&tl_tmark[k], t_); \
+        if (blockIdx.x < 1024) { tl_tcta[k][blockIdx.x] = t_; if (k == 0) { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); tl_tcta[2][blockIdx.x] = sm_; } } } } while (0)
+#define TL_MARK_MAX(k) do { if (threadIdx.x == 0) atomicMax(&tl_tmark[k], gtime()); } while (0)
+#else
+#define TL_MARK_MIN(k) do { } while (0)
+#define TL_MARK_MAX(k) do { } while (0)
+#endif
+
 template <int N, typename F>
 __device__ __forceinline__ void static_for(F &&f)
 {
@@ -44,12 +68,14 @@ __device__ __forceinline__ void static_for(F &&f)
     }
 }
 
-__device__ __forceinline__ int find_band_m(const int32_t *__restrict__ band_first, int nbands, int item)
+constexpr int kBandCap = 1024; // band table entries kept in shared memory (n up to ~260k)
+
+__device__ __forceinline__ int find_band_m(const int32_t *band_first, int nbands, int item)
 {
     int lo = 0, hi = nbands - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(&band_first[mid]) <= item)
+        if (band_first[mid] <= item)
             lo = mid;
         else
             hi = mid - 1;
@@ -57,24 +83,21 @@ __device__ __forceinline__ int find_band_m(const int32_t *__restrict__ band_firs
     return lo;
 }
 
-// streaming load: every matrix element is used once per scan, keep it out of L1
-template <typename V>
-__device__ __forceinline__ V ld_stream(const V *p)
+// Matrix element at byte address rowbase + 4 * col: ONE IMAD.WIDE.U32 per load (the row base is
+// formed once per row step).  Streaming: every element is used once per scan, keep it out of L1.
+// With PIN (L2 residency experiment, the matrix is larger than L2 but a scan re-reads the same
+// elements every step): rows whose SLOT is below pin_rows carry an L2 evict_last policy, every
+// other load evict_first; the policy is chosen per row (warp-uniform).
+template <typename V, bool PIN>
+__device__ __forceinline__ V ld_elem(uint64_t rowbase, uint32_t col, uint64_t pol)
 {
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(col), "l"(rowbase));
     int32_t v;
-    asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
-    return Val<V>::from_bits(v);
-}
-
-// L2 residency (the matrix is larger than L2 but a scan re-reads the same elements every step):
-// loads of matrix rows whose SLOT is below pin_rows carry an L2 evict_last policy, every other
-// load evict_first, so that a fixed ~L2-sized part of the matrix survives from scan to scan and
-// only the rest streams from HBM.  The policy is chosen per row (warp-uniform).
-template <typename V>
-__device__ __forceinline__ V ld_hint(const V *p, uint64_t pol)
-{
-    int32_t v;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    if constexpr (PIN)
+        asm("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    else
+        asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(a));
     return Val<V>::from_bits(v);
 }
 
@@ -87,14 +110,28 @@ __device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, ui
                                                      tl_move *__restrict__ log, uint64_t log_cap)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __threadfence();
+#ifdef TL_TIMELINE
+    const int tl_par = 0;
+    const unsigned long long t_entry = gtime();
+#endif
+    // (ordering: thread 0's acq_rel ticket + the caller's __syncthreads; the records are read from L2)
     StateHeader hdr{};
     if (threadIdx.x == 0) hdr = load_state_header(state); // in flight with the candidate loads
     Best<V> v{(V)0, 0xffffffffu, 0xffffffffu, 0u};
-    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
-        const int4 raw = __ldcg(reinterpret_cast<const int4 *>(blockbest) + c);
-        const Best<V> o{Val<V>::from_bits(raw.x), (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
-        if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    // all of this thread's candidate loads are issued before the first compare (one round trip)
+    for (int c0 = threadIdx.x; c0 < (int)gridDim.x; c0 += 4 * blockDim.x) {
+        int4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * (int)blockDim.x;
+            raw[u] = c < (int)gridDim.x ? __ldcg(reinterpret_cast<const int4 *>(blockbest) + c)
+                                        : make_int4(0, -1, -1, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const Best<V> o{Val<V>::from_bits(raw[u].x), (uint32_t)raw[u].y, (uint32_t)raw[u].z, (uint32_t)raw[u].w};
+            if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+        }
     }
     warp_argmin_2opt(v.delta, v.i, v.j);
     __syncthreads();
@@ -107,26 +144,52 @@ __device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, ui
         if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
     }
     const bool found = v.i != 0xffffffffu;
+#ifdef TL_TIMELINE
+    const unsigned long long t_reduced = gtime();
+#endif
     if (found) reverse_segment_inplace(MatPol<V>{cs, M, ld}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
+#ifdef TL_TIMELINE
+    __syncthreads();
+    const unsigned long long t_reversed = gtime();
+#endif
     if (threadIdx.x == 0) {
         *ticket = 0u;
         finish_best_step(state, hdr, found, (float)v.delta, v.i, v.j, log, log_cap);
+#ifdef TL_TIMELINE
+        const unsigned long long t_done = gtime();
+        const unsigned long long t0 = tl_tmark[0];
+        if (tl_prev_done) tl_tacc[0] += t0 - tl_prev_done;
+        tl_tacc[1] += tl_tmark[1] - t0;
+        tl_tacc[2] += tl_tmark[2] - t0;
+        tl_tacc[3] += t_entry - t0;
+        tl_tacc[4] += t_reduced - t0;
+        tl_tacc[5] += t_reversed - t0;
+        tl_tacc[6] += t_done - t0;
+        tl_tacc[7] += 1;
+        tl_tmark[0] = ~0ull; tl_tmark[1] = ~0ull; tl_tmark[2] = 0ull; tl_prev_done = t_done;
+#endif
     }
 }
 
 template <typename V, bool PIN>
 __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     two_opt_scan_matrix_kernel(const V *__restrict__ M, uint32_t ld, Cs *__restrict__ cs, const ScanGeom g,
-                               const int32_t *__restrict__ band_first, Best<V> *__restrict__ blockbest,
+                               const int32_t *__restrict__ band_first_g, Best<V> *__restrict__ blockbest,
                                DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
                                uint64_t log_cap, int fuse_apply, int pin_rows)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     griddep_launch_dependents(); // PDL, as in k2_two_opt.cu
+#ifdef TL_TIMELINE
+    const int tl_par = 0;
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-warp staging of (slot, entering-edge bits) pairs, 8 bytes each => conflict-free LDS.64
-    int2 *srow = reinterpret_cast<int2 *>(smem_raw) + warp * WARP_RECS;
-    int2 *scol = srow + ROWS_CAP;
+    // per-warp staging, four plain 32-bit arrays (conflict-free LDS.32): matrix slot and
+    // entering-edge bits of the tile's row positions and of its column positions
+    int32_t *srow_slot = reinterpret_cast<int32_t *>(smem_raw) + warp * (2 * WARP_RECS);
+    int32_t *srow_sp = srow_slot + ROWS_CAP;
+    int32_t *scol_slot = srow_sp + ROWS_CAP;
+    int32_t *scol_sp = scol_slot + COLS_CAP;
     Best<V> *red = reinterpret_cast<Best<V> *>(smem_raw + (size_t)WARPS * WARP_RECS * sizeof(int2));
 
     uint64_t pol_keep = 0, pol_stream = 0;
@@ -134,36 +197,64 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
         asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
         asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
     }
-    auto ld_row = [&](const V *p, uint64_t pol) {
-        if constexpr (PIN)
-            return ld_hint(p, pol);
-        else
-            return ld_stream(p);
-    };
+    const uint32_t ld4 = ld * 4u; // row pitch in bytes
+
+    // band table (geometry only): shared-memory copy, so that looking up a work item costs no
+    // global round trips
+    __shared__ int32_t s_band[kBandCap];
+    const int32_t *band_first = band_first_g;
+    if (g.nbands + 1 <= kBandCap) {
+        for (int t = threadIdx.x; t <= g.nbands; t += blockDim.x) s_band[t] = __ldg(&band_first_g[t]);
+        __syncthreads();
+        band_first = s_band;
+    }
 
     V best = (V)0;
     uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
-    const int total_warps = gridDim.x * WARPS;
-    const int item0 = g.item_begin + blockIdx.x * WARPS + warp;
-    int t_next = 0, tf_next = 0; // table slot of this warp's first work item (geometry only)
-    if (item0 < g.item_end) {
-        t_next = find_band_m(band_first, g.nbands, item0);
-        tf_next = __ldg(&band_first[t_next]);
+    // this warp's static run of work items (geometry only, so it may be looked up before the wait)
+    int u_lo = g.item_begin + (blockIdx.x * WARPS + warp) * g.run;
+    int u_hi = min(u_lo + g.run, g.dyn_begin);
+    int t_next = 0, tf_next = 0, tl_next = 0; // band of item u_lo, first item of that band and of the next one
+    if (u_lo < u_hi) {
+        t_next = find_band_m(band_first, g.nbands, u_lo);
+        tf_next = band_first[t_next];
+        tl_next = band_first[t_next + 1];
     }
     griddep_wait(); // the previous step's move is applied and visible from here on
     if (*reinterpret_cast<const volatile int *>(&state->done)) return; // grid-uniform
+    TL_MARK_MIN(0);
+    // the items [dyn_begin, item_end) go to whichever warp asks first; the next ticket is always
+    // requested before the current item is scanned, so its latency is hidden
+    const bool has_dyn = g.dyn_begin < g.item_end;
+    unsigned int tk = 0;
+    if (has_dyn && lane == 0) tk = atomicAdd(ticket + 1, 1u);
+    bool first = true;
 
-    for (int item = item0; item < g.item_end; item += total_warps) {
-        if (item != item0) {
-            t_next = find_band_m(band_first, g.nbands, item);
-            tf_next = __ldg(&band_first[t_next]);
+    for (;;) {
+        if (u_lo >= u_hi) { // run exhausted: take the next dynamic item
+            if (!has_dyn) break;
+            const int item = g.dyn_begin + (int)__shfl_sync(0xffffffffu, tk, 0);
+            if (item >= g.item_end) break;
+            if (lane == 0) tk = atomicAdd(ticket + 1, 1u);
+            u_lo = item;
+            u_hi = item + 1;
+            first = false;
         }
+        if (!first) {
+            t_next = find_band_m(band_first, g.nbands, u_lo);
+            tf_next = band_first[t_next];
+            tl_next = band_first[t_next + 1];
+        }
+        first = false;
+        // as many of the run's items as lie in this band are scanned as one piece
+        const int q = min(u_hi, tl_next) - u_lo;
         const int b = t_next;
-        const int cidx = item - tf_next; // row chunk within the band
+        const int cidx = u_lo - tf_next; // first row chunk within the band
+        u_lo += q;
         const int K0 = 2 + b * BW;
         const int H = g.jmax - K0 + 1;
         const int r_begin = cidx * g.chunk;
-        const int r_end = min(r_begin + g.chunk, H);
+        const int r_end = min(r_begin + q * g.chunk, H);
         const int ntiles = (r_end - r_begin + TI - 1) / TI;
         const int tile_rows = ntiles > 0 ? (r_end - r_begin + ntiles - 1) / ntiles : 0;
 
@@ -172,54 +263,56 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
             __syncwarp();
             for (int t = lane; t < cnt + 1; t += 32) {
                 const Cs c = cs[i0 + t];
-                srow[t] = make_int2(c.slot, c.sp_bits);
+                srow_slot[t] = c.slot;
+                srow_sp[t] = c.sp_bits;
             }
             for (int t = lane; t < cnt + BW + 1; t += 32) {
                 const Cs c = cs[i0 + K0 + t];
-                scol[t] = make_int2(c.slot, c.sp_bits);
+                scol_slot[t] = c.slot;
+                scol_sp[t] = c.sp_bits;
             }
             __syncwarp();
 
-            // E[r] = d(p_i, p_j) carried down diagonal k_r = K0 + lane + 32 r; the record of
-            // position j+1 at row i0+tau sits at scol[tau + 1 + lane + 32 r].
-            // buf[d] holds the matrix elements of row step (tau % D == d), loaded D steps ahead:
-            // D * R independent 4-byte loads per thread stay in flight, which is what it takes to
-            // cover HBM latency at 24 warps per SM (Little: ~40 KB per SM at 6.5 TB/s).
-            V E[R], buf[D][R];
-            {
-                const int slot0 = srow[0].x;
-                const V *row0 = M + (size_t)slot0 * ld;
-                const uint64_t pol = slot0 < pin_rows ? pol_keep : pol_stream;
+            // Lane l owns the diagonals k_r = K0 + l + 32 r.  Row step tau handles the pairs
+            // (i0 + tau, i0 + tau + k_r): it needs E = d(p_i, p_j), which is the element the
+            // previous row step loaded as ITS d(p_i+1, p_j+1), and en = d(p_i+1, p_j+1) from
+            // matrix row slot(i+1) at the columns slot(j+1) = scol_slot[tau + 1 + l + 32 r].
+            // ring[] is a ring of NB = D + 1 row buffers addressed with compile-time indices
+            // (the loop is unrolled NB times), so nothing is ever copied: at step tau the
+            // buffer tau-1 is E, tau is en, tau+1 .. tau+D-1 are in flight, and once the step
+            // is computed the loads of step tau+D are issued into the (dead) buffer of E.
+            // D * R independent 4-byte loads per thread stay in flight, which is what it takes
+            // to cover HBM latency at 24 warps per SM (Little: ~40 KB per SM at 6.5 TB/s).
+            constexpr int NB = D + 1;
+            V ring[NB][R];
+            auto issue = [&](auto Bc, int t) { // loads of row step t into ring[Bc]
+                constexpr int bq = decltype(Bc)::value;
+                const uint32_t slotn = (uint32_t)srow_slot[t + 1];
+                uint64_t rowbase;
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(rowbase) : "r"(slotn), "r"(ld4), "l"(M));
+                uint64_t pol = 0;
+                if constexpr (PIN) pol = (int)slotn < pin_rows ? pol_keep : pol_stream;
+                const int32_t *cslot = scol_slot + (t + 1 + lane);
 #pragma unroll
-                for (int r = 0; r < R; ++r) E[r] = ld_row(row0 + scol[lane + 32 * r].x, pol);
-            }
-            auto issue = [&](auto Dc, int t) { // loads of row step t into buf[Dc]
-                constexpr int d = decltype(Dc)::value;
-                const int slotn = srow[t + 1].x;
-                const V *rown = M + (size_t)slotn * ld;
-                const uint64_t pol = slotn < pin_rows ? pol_keep : pol_stream;
-#pragma unroll
-                for (int r = 0; r < R; ++r) buf[d][r] = ld_row(rown + scol[t + 1 + lane + 32 * r].x, pol);
+                for (int r = 0; r < R; ++r) ring[bq][r] = ld_elem<V, PIN>(rowbase, (uint32_t)cslot[32 * r], pol);
             };
+            issue(std::integral_constant<int, NB - 1>{}, -1); // E of row step 0
             static_for<D>([&](auto Dc) {
                 constexpr int d = decltype(Dc)::value;
                 if (d < cnt) issue(Dc, d);
             });
-            auto step = [&](auto Dc, int tau) {
-                constexpr int d = decltype(Dc)::value;
-                V en[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) en[r] = buf[d][r];
-                if (tau + D < cnt) issue(Dc, tau + D); // refill this slot before consuming the row
-                const V si = Val<V>::from_bits(srow[tau + 1].y); // s_i
+            auto step = [&](auto Sc, int tau) {
+                constexpr int s = decltype(Sc)::value;
+                constexpr int e = (s + NB - 1) % NB; // buffer of E; refilled with step tau + D
+                const V si = Val<V>::from_bits(srow_sp[tau + 1]); // s_i
+                const int32_t *csp = scol_sp + (tau + 1 + lane);
                 V dl[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const V sj = Val<V>::from_bits(scol[tau + 1 + lane + 32 * r].y);
+                    const V sj = Val<V>::from_bits(csp[32 * r]);
                     const V cur = Val<V>::add(si, sj);
-                    const V nw = Val<V>::add(E[r], en[r]);
+                    const V nw = Val<V>::add(ring[e][r], ring[s][r]);
                     dl[r] = Val<V>::sub(nw, cur);
-                    E[r] = en[r];
                 }
                 V m = dl[0];
 #pragma unroll
@@ -238,12 +331,13 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
                         }
                     }
                 }
+                if (tau + D < cnt) issue(std::integral_constant<int, e>{}, tau + D);
             };
             int t = 0;
 #pragma unroll 1
-            for (; t + D <= cnt; t += D) static_for<D>([&](auto Dc) { step(Dc, t + decltype(Dc)::value); });
-            static_for<D>([&](auto Dc) {
-                if (t + decltype(Dc)::value < cnt) step(Dc, t + decltype(Dc)::value);
+            for (; t + NB <= cnt; t += NB) static_for<NB>([&](auto Sc) { step(Sc, t + decltype(Sc)::value); });
+            static_for<NB>([&](auto Sc) {
+                if (t + decltype(Sc)::value < cnt) step(Sc, t + decltype(Sc)::value);
             });
         }
     }
@@ -256,17 +350,20 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
         warp_argmin_2opt(v.delta, v.i, v.j);
         if (lane == 0) blockbest[blockIdx.x] = v;
     }
-    if (!fuse_apply) return;
-
-    // fused step tail: the last CTA reduces the per-CTA records and applies the move in place
+    // the last CTA to finish re-arms the dynamic work queue and, in a fused step, reduces the
+    // per-CTA records and applies the move in place
     __shared__ unsigned int s_last;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    }
+    TL_MARK_MIN(1);
+    TL_MARK_MAX(2);
+    if (threadIdx.x == 0) s_last = (ticket_take_acq_rel(ticket) == gridDim.x - 1) ? 1u : 0u; // thread 0 wrote blockbest
     __syncthreads();
     if (!s_last) return;
+    if (threadIdx.x == 0) ticket[1] = 0u;
+    if (!fuse_apply) {
+        if (threadIdx.x == 0) *ticket = 0u;
+        return;
+    }
     fused_apply_tail_matrix<V>(M, ld, cs, blockbest, red, state, ticket, log, log_cap);
 }
 
@@ -319,6 +416,24 @@ __global__ void __launch_bounds__(256) reset_slots_kernel(Cs *__restrict__ cs, u
 }
 
 } // namespace
+
+#ifdef TL_TIMELINE
+extern "C" int tl_debug_timeline(double *out8, int reset)
+{
+    unsigned long long h[8];
+    if (cudaMemcpyFromSymbol(h, tl_tacc, sizeof h) != cudaSuccess) return 1;
+    if (reset == 2) return cudaMemcpyFromSymbol(out8, tl_tcta, sizeof(unsigned long long) * 3 * 1024) != cudaSuccess; // raw u64[3][1024]
+    for (int k = 0; k < 8; ++k) out8[k] = (double)h[k];
+    if (reset) {
+        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const unsigned long long m[8] = {~0ull, ~0ull, 0ull, 0ull, ~0ull, ~0ull, 0ull, 0ull};
+        cudaMemcpyToSymbol(tl_tacc, z, sizeof z);
+        cudaMemcpyToSymbol(tl_tmark_par, m, sizeof m);
+        cudaMemcpyToSymbol(tl_prev_done, z, sizeof(unsigned long long));
+    }
+    return 0;
+}
+#endif
 
 size_t scan_matrix_smem_bytes()
 {

@@ -27,6 +27,11 @@ struct ScanGeom {
     int32_t item_end;
     int32_t cyclic;
     float screen_margin; // recompute path: Dmax * kScreenMarginScale, < 0 disables screening
+    // matrix path: warp w first scans the `run` consecutive items starting at item_begin + w * run
+    // (clipped to dyn_begin); the items [dyn_begin, item_end) are handed out one at a time through
+    // an atomic ticket to whichever warp finishes first (evens out the tail of the scan)
+    int32_t run;
+    int32_t dyn_begin;
 };
 
 // device-resident loop state, updated by the apply kernels
@@ -152,7 +157,7 @@ constexpr int kMatWarps = 8;
 #endif
 constexpr int kMatMinBlocks = TL_MAT_MINB;
 #ifndef TL_MAT_D
-#define TL_MAT_D 2
+#define TL_MAT_D 4
 #endif
 constexpr int kMatD = TL_MAT_D;          // prefetch depth in row steps
 size_t scan_matrix_smem_bytes();

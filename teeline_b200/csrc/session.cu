@@ -127,11 +127,18 @@ void build_geometry(tl_session *s, std::vector<int32_t> &band_first_h)
     const int64_t per = ((int64_t)s->nitems + s->shard_count - 1) / s->shard_count;
     g.item_begin = (int32_t)std::min<int64_t>(s->nitems, per * s->shard_index);
     g.item_end = (int32_t)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
+    // matrix path: one static item per warp.  (Tried: cutting a warp's share into ~7 items and
+    // handing the last 15-40 % out through an atomic ticket to even out the 28-36 us spread of the
+    // CTAs' finishing times -- every short item restarts the load pipeline with two dependent
+    // round trips, and the scan got 5 us SLOWER; profiles/r01t_probe_dynamic_tail.txt.)
+    g.run = 1; // set below once the grid is known
+    g.dyn_begin = g.item_end;
     // same grid on every rank so the all-gather is symmetric
     const int64_t blocks = (per + warps - 1) / warps;
     s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * minb));
     // test hook: a small grid makes every warp walk several work items
     if (const char *cap = getenv("TL_MAX_GRID")) s->grid = std::max(1, std::min(s->grid, atoi(cap)));
+    g.run = (int32_t)std::max<int64_t>(1, (per + (int64_t)s->grid * warps - 1) / ((int64_t)s->grid * warps));
 }
 
 // Or-opt work decomposition: column blocks of 32*kOrR insertion edges x row chunks.
@@ -472,7 +479,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         return rc;
     };
     DevBuf<uint32_t> d_tour;
-    if (d_tour.alloc(p->n) != cudaSuccess || s->state.alloc(1) != cudaSuccess || s->ticket.alloc(1) != cudaSuccess ||
+    if (d_tour.alloc(p->n) != cudaSuccess || s->state.alloc(1) != cudaSuccess || s->ticket.alloc(2) != cudaSuccess ||
         s->log.alloc(s->log_cap) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
         cudaEventCreate(&s->ev1) != cudaSuccess) {
         set_error("tl_session_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -493,7 +500,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         tour = ident.data();
     }
     cudaError_t e = cudaMemcpyAsync(d_tour.p, tour, (size_t)p->n * 4, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(s->ticket.p, 0, 4, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->ticket.p, 0, 8, c->stream);
     if (e != cudaSuccess) { set_error("tl_session_create: %s", cudaGetErrorString(e)); return fail(TL_ERR_CUDA); }
 
     if (want_matrix) {
@@ -520,7 +527,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         launch_build_cs(s->src, d_tour.p, p->n, s->npad, s->cyclic, c->stream);
         c->launches++;
         // re-lay the matrix in tour order only when it cannot live in L2 (gathers are cheap there)
-        s->repermute_every = bytes > ((size_t)96 << 20) ? 64 : 0;
+        s->repermute_every = bytes > ((size_t)96 << 20) ? 256 : 0;
         if (const char *ev = getenv("TL_REPERMUTE_EVERY")) s->repermute_every = atoi(ev);
         configure_matrix_pin(s, bytes);
     } else {

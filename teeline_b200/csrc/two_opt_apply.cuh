@@ -78,9 +78,10 @@ __device__ __forceinline__ StateHeader load_state_header(const DevState *state)
     h.h1 = __ldcg(reinterpret_cast<const longlong2 *>(state) + 1);
     return h;
 }
-__device__ __forceinline__ void finish_best_step(DevState *state, const StateHeader &h, bool found, float delta,
-                                                 uint32_t mi, uint32_t mj, tl_move *__restrict__ log,
-                                                 uint64_t log_cap)
+// Returns the value of state->done after the step.
+__device__ __forceinline__ int finish_best_step(DevState *state, const StateHeader &h, bool found, float delta,
+                                                uint32_t mi, uint32_t mj, tl_move *__restrict__ log,
+                                                uint64_t log_cap)
 {
     const unsigned long long m = h.h0.x;
     const long long max_moves = h.h1.x;
@@ -88,11 +89,25 @@ __device__ __forceinline__ void finish_best_step(DevState *state, const StateHea
     if (found) {
         if (log && m < log_cap) log[m] = tl_move{delta, mi, mj, 0, 0, 0};
         state->moves = m + 1;
-        if (max_moves >= 0 && (long long)(m + 1) >= max_moves) state->done = 1;
-    } else {
-        state->done = 1;
-        state->converged = 1;
+        if (max_moves >= 0 && (long long)(m + 1) >= max_moves) {
+            state->done = 1;
+            return 1;
+        }
+        return 0;
     }
+    state->done = 1;
+    state->converged = 1;
+    return 1;
+}
+
+// Last-CTA detection with ONE acq_rel atomic instead of fence.sc + relaxed atomic + fence.sc:
+// release publishes this thread's candidate record, acquire (plus the caller's __syncthreads)
+// orders the last CTA's reads of everybody else's records after it.
+__device__ __forceinline__ unsigned int ticket_take_acq_rel(unsigned int *ticket)
+{
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ticket) : "memory");
+    return old;
 }
 
 // Stand-alone apply step for Mode B (sharded sessions and the matrix path): every block
