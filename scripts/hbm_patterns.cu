@@ -44,6 +44,20 @@ __global__ void __launch_bounds__(256) contig_kernel(const int4 *__restrict__ p,
     if (acc == 0x12345678) *sink = acc;
 }
 
+// write-only ceiling for K1 (distance-matrix build): grid-stride 16-byte stores
+__global__ void __launch_bounds__(256) fill_kernel(int4 *__restrict__ p, size_t n16, int v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n16; i += stride) p[i] = make_int4(v, v + 1, v + 2, v + 3);
+}
+// same, but every CTA owns one contiguous piece (the K1 packed kernel's decomposition)
+__global__ void __launch_bounds__(256) fill_piece_kernel(int4 *__restrict__ p, size_t n16, size_t per_cta16, int v)
+{
+    const size_t b = (size_t)blockIdx.x * per_cta16, e = b + per_cta16 < n16 ? b + per_cta16 : n16;
+    for (size_t i = b + threadIdx.x; i < e; i += 256) p[i] = make_int4(v, v + 1, v + 2, v + 3);
+}
+
 template <int D, int MINB>
 __global__ void __launch_bounds__(256, MINB) band_kernel(const int *__restrict__ M, uint32_t ld, const Item *__restrict__ items, int nitems, int *sink)
 {
@@ -139,6 +153,23 @@ int main(int argc, char **argv)
     CK(cudaMemset(M, 1, (size_t)(n + 1) * ld * 4));
     CK(cudaMalloc(&sink, 4));
     const int jmax = n - 2;
+    if (argc > 2) { // write-only patterns
+        for (double mb : {200.0, 400.0}) {
+            const size_t n16 = (size_t)(mb * 1e6 / 16);
+            const double bytes = (double)n16 * 16;
+            auto rep = [&](const char *name, float ms) { printf("  write %.0f MB %-26s %8.2f us  %7.1f GB/s\n", mb, name, ms * 1e3, bytes / (ms * 1e-3) / 1e9); fflush(stdout); };
+            rep("cudaMemsetAsync", time_it([&] { cudaMemsetAsync(M, 1, n16 * 16); }, 20));
+            for (int g : {148 * 8, 148 * 16, 148 * 64}) {
+                char nm[64];
+                snprintf(nm, sizeof nm, "fill grid-stride grid=%d", g);
+                rep(nm, time_it([&] { fill_kernel<<<g, 256>>>(reinterpret_cast<int4 *>(M), n16, 3); }, 20));
+                snprintf(nm, sizeof nm, "fill pieces grid=%d", g);
+                const size_t per = (n16 + g - 1) / g;
+                rep(nm, time_it([&] { fill_piece_kernel<<<g, 256>>>(reinterpret_cast<int4 *>(M), n16, per, 3); }, 20));
+            }
+        }
+        return 0;
+    }
     for (int grid_ctas : {442, 592, 888}) {
         std::vector<Item> items;
         long long steps = 0;

@@ -262,6 +262,22 @@ static tl_status matrix_packed_impl(tl_problem *p, void *out, bool want_int)
     launch_k1_packed(p->d_xy, p->n, p->fast_sqrt, want_int, d.p, c->sm_count, c->stream);
     c->launches++;
     TL_CUDA_TRY(cudaGetLastError());
+    if (getenv("TL_K1_TIMING")) { // tuning aid: warm kernel time (CUDA events, 20 back-to-back launches) on stderr
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+        for (int r = 0; r < 20; ++r) launch_k1_packed(p->d_xy, p->n, p->fast_sqrt, want_int, d.p, c->sm_count, c->stream);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[tl] k1_packed n=%u %s: %.2f us per launch, %.1f GB/s written\n", p->n,
+                want_int ? "nint" : (p->fast_sqrt ? "f32-fast" : "f32-safe"), ms / 20 * 1e3, cnt * 4.0 / (ms / 20 * 1e-3) / 1e9);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        c->launches += 20;
+    }
     TL_CUDA_TRY(cudaMemcpyAsync(out, d.p, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return TL_OK;

@@ -5,13 +5,22 @@
 // idx = hi*(hi-1)/2 + lo (distance_matrix.rs:177-191).  Also builds the padded
 // square, tour-ordered matrix the matrix-backed scans read.
 //
-// Roofline: HBM write, 4 B per pair.  Each thread produces 4 consecutive packed
-// entries and stores them with one 128-bit STG; coordinate reads are L1/L2 hits
-// (lo runs over consecutive cities, hi is warp-uniform most of the time).  The
-// packed index is inverted with fp64 once per thread, then advanced incrementally.
+// Roofline: HBM write, 4 B per pair.  A warp produces 128 consecutive packed entries per step
+// with fully coalesced coordinate loads (L1/L2 hits) and stores.  The packed index is inverted
+// with fp64 once per thread, then advanced incrementally.
 #include "kernels.cuh"
 
 namespace tl {
+
+// one matrix entry as raw bits: NINT = 0 f32 (FAST: guarded fast sqrt), 1 TSPLIB nint in double
+template <bool FAST, int NINT>
+__device__ __forceinline__ uint32_t k1_dist(const float2 a, const float2 b)
+{
+    if constexpr (NINT == 1)
+        return (uint32_t)dist_nint(a.x, a.y, b.x, b.y);
+    else
+        return __float_as_uint(dist_f32<FAST>(a.x, a.y, b.x, b.y));
+}
 
 __device__ __forceinline__ void packed_index_to_pair(uint64_t t, uint32_t &hi, uint32_t &lo)
 {
@@ -24,47 +33,50 @@ __device__ __forceinline__ void packed_index_to_pair(uint64_t t, uint32_t &hi, u
 }
 
 // Every CTA owns one contiguous piece of the packed array (`per_cta` entries, a multiple of 1024).
-// A thread produces 4 consecutive entries per step (one 128-bit store) and moves 1024 entries
-// ahead; its (hi, lo) pair is found once with the closed form and then advanced incrementally
-// (rows are longer than 1024 almost everywhere, so the wrap loop runs 0-1 times).
-template <bool FAST, bool NINT>
+// A warp produces 128 consecutive entries per step and moves 1024 entries ahead: lane l owns the
+// entries T + 32 e + l, e < 4, so every coordinate load (32 lanes x 8 B = 256 contiguous bytes) and
+// every store (128 contiguous bytes) is fully coalesced -- the kernel is bound by L1 wavefronts,
+// and 4 consecutive entries per lane cost 8 wavefronts per 8-byte load instead of 2.  The (hi, lo)
+// pair of T is found once with the closed form and then advanced incrementally (rows are longer
+// than 1024 almost everywhere, so the wrap loop runs 0-1 times).
+template <bool FAST, int NINT>
 __global__ void __launch_bounds__(256) k1_packed_kernel(const float2 *__restrict__ xy, uint32_t n,
                                                         uint64_t total, uint64_t per_cta,
                                                         void *__restrict__ out)
 {
     const uint64_t begin = (uint64_t)blockIdx.x * per_cta;
     const uint64_t end = min(begin + per_cta, total);
-    uint64_t t0 = begin + (uint64_t)threadIdx.x * 4;
-    if (t0 >= end) return;
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t T = begin + (uint64_t)(threadIdx.x >> 5) * 128;
+    if (T >= end) return;
     uint32_t hi, lo;
-    packed_index_to_pair(t0, hi, lo);
-    for (; t0 < end; t0 += 1024) {
-        float2 ph = __ldg(&xy[hi]);
-        uint32_t v[4];
-        uint32_t h = hi, l = lo;
+    packed_index_to_pair(T, hi, lo); // warp-uniform
+    for (; T < end; T += 1024) {
+        uint32_t *o = reinterpret_cast<uint32_t *>(out) + T;
+        if (lo + 128 <= hi && T + 128 <= total) {
+            // common case: the warp's 128 entries lie in one row
+            const float2 ph = __ldg(&xy[hi]);
+            float2 pl[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (t0 + e < total) {
-                const float2 pl = __ldg(&xy[l]);
+            for (int e = 0; e < 4; ++e) pl[e] = __ldg(&xy[lo + 32 * e + lane]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
                 // the reference evaluates cities[hi].distance(cities[lo])
-                if (NINT)
-                    v[e] = (uint32_t)dist_nint(ph.x, ph.y, pl.x, pl.y);
-                else
-                    v[e] = __float_as_uint(dist_f32<FAST>(ph.x, ph.y, pl.x, pl.y));
-                if (++l == h) {
-                    ++h;
-                    l = 0;
-                    if (h < n) ph = __ldg(&xy[h]);
-                }
-            } else {
-                v[e] = 0;
+                o[32 * e + lane] = k1_dist<FAST, NINT>(ph, pl[e]);
             }
-        }
-        uint32_t *o = reinterpret_cast<uint32_t *>(out) + t0;
-        if (t0 + 4 <= total) {
-            *reinterpret_cast<uint4 *>(o) = make_uint4(v[0], v[1], v[2], v[3]);
         } else {
-            for (int e = 0; e < 4 && t0 + e < total; ++e) o[e] = v[e];
+#pragma unroll 1
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t k = 32 * e + lane;
+                if (T + k >= total) break;
+                uint32_t h = hi, l = lo + k;
+                while (l >= h) {
+                    l -= h;
+                    ++h;
+                }
+                const float2 ph = __ldg(&xy[h]), pl = __ldg(&xy[l]);
+                o[k] = k1_dist<FAST, NINT>(ph, pl);
+            }
         }
         // 1024 entries ahead: row hi holds hi entries
         lo += 1024;
@@ -79,7 +91,7 @@ __global__ void __launch_bounds__(256) k1_packed_kernel(const float2 *__restrict
 // columns [n, ld) are zero.  sxy holds slot-ordered coordinates.  One thread per
 // 4 columns, 128-bit stores; a block covers a 64-row x 256-column tile so the row
 // coordinates are reused from registers.
-template <bool FAST, bool NINT>
+template <bool FAST, int NINT>
 __global__ void __launch_bounds__(256) k1_square_kernel(const float2 *__restrict__ sxy, uint32_t n,
                                                         uint32_t ld, void *__restrict__ out)
 {
@@ -96,15 +108,10 @@ __global__ void __launch_bounds__(256) k1_square_kernel(const float2 *__restrict
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const uint32_t cc = col0 + e;
-            if (cc >= n || cc == r) {
-                v[e] = 0;
-            } else {
-                // evaluate as hi.distance(lo) like the reference (bitwise symmetric anyway)
-                const bool rhi = r > cc;
-                const float2 a = rhi ? p : c[e], b = rhi ? c[e] : p;
-                v[e] = NINT ? (uint32_t)dist_nint(a.x, a.y, b.x, b.y)
-                            : __float_as_uint(dist_f32<FAST>(a.x, a.y, b.x, b.y));
-            }
+            // d(a, b) == d(b, a) bit for bit ((a-b)^2 == (b-a)^2 in IEEE arithmetic), so the
+            // reference's hi.distance(lo) operand order needs no select here
+            const uint32_t d = k1_dist<FAST, NINT>(p, c[e]);
+            v[e] = (cc >= n || cc == r) ? 0u : d;
         }
         *reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(out) + (size_t)r * ld + col0) =
             make_uint4(v[0], v[1], v[2], v[3]);
@@ -154,11 +161,11 @@ void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, bool nint, void *
     blocks = (total + per_cta - 1) / per_cta;
     if (blocks == 0) blocks = 1;
     if (nint)
-        k1_packed_kernel<false, true><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
+        k1_packed_kernel<false, 1><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
     else if (fast)
-        k1_packed_kernel<true, false><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
+        k1_packed_kernel<true, 0><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
     else
-        k1_packed_kernel<false, false><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
+        k1_packed_kernel<false, 0><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
 }
 
 void launch_k1_square(const float2 *sxy, uint32_t n, uint32_t ld, bool fast, bool nint, void *out,
@@ -166,11 +173,11 @@ void launch_k1_square(const float2 *sxy, uint32_t n, uint32_t ld, bool fast, boo
 {
     dim3 grid((ld / 4 + 63) / 64, (n + 63) / 64);
     if (nint)
-        k1_square_kernel<false, true><<<grid, 256, 0, st>>>(sxy, n, ld, out);
+        k1_square_kernel<false, 1><<<grid, 256, 0, st>>>(sxy, n, ld, out);
     else if (fast)
-        k1_square_kernel<true, false><<<grid, 256, 0, st>>>(sxy, n, ld, out);
+        k1_square_kernel<true, 0><<<grid, 256, 0, st>>>(sxy, n, ld, out);
     else
-        k1_square_kernel<false, false><<<grid, 256, 0, st>>>(sxy, n, ld, out);
+        k1_square_kernel<false, 0><<<grid, 256, 0, st>>>(sxy, n, ld, out);
 }
 
 void launch_k1_square_from_packed(const uint32_t *tri, const int32_t *slot_city, uint32_t n,

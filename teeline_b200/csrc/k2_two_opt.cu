@@ -71,7 +71,7 @@ __device__ __noinline__ void fused_apply_tail(Pt *__restrict__ pts, const BestF 
                                               uint64_t log_cap)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __threadfence();
+    // (ordering: thread 0's acq_rel ticket + the caller's __syncthreads; the records are read from L2)
     StateHeader hdr{};
     if (threadIdx.x == 0) hdr = load_state_header(state); // in flight with the candidate loads
     BestF v{0.0f, 0xffffffffu, 0xffffffffu, 0u};
@@ -264,10 +264,7 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
     // reverses the segment in place and updates the loop state, saving a kernel launch per step.
     __shared__ unsigned int s_last;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    }
+    if (threadIdx.x == 0) s_last = (ticket_take_acq_rel(ticket) == gridDim.x - 1) ? 1u : 0u; // thread 0 wrote blockbest
     __syncthreads();
     if (!s_last) return;
     fused_apply_tail<FAST>(pts, blockbest, red, state, ticket, log, log_cap);

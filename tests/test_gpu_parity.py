@@ -73,6 +73,32 @@ def test_k1_nint_matches_oracle(T, ctx, berlin52):
     assert (p.matrix_packed() == O.matrix_packed_nint(gx, gy)).all()
 
 
+@pytest.mark.parametrize("case", ["wide_ints", "offset_ints", "half_integers", "long_thin"])
+def test_k1_nint_coordinate_ranges(T, ctx, case):
+    """TSPLIB nint over coordinate sets that stress the rounding: distances up to 1.5e6, large
+    offsets, half-integers, d2 = 0, 1, 4, 9, ... neighbours."""
+    rng = np.random.default_rng(7)
+    n = 1200
+    if case == "wide_ints":              # ranges 2^20 wide, distances up to 1.48e6
+        x = rng.integers(0, 1048577, n).astype(np.float32)
+        y = rng.integers(0, 1048577, n).astype(np.float32)
+        x[:2], y[:2] = [0, 1048576], [0, 1048576]
+    elif case == "offset_ints":          # integer coordinates near 2^22
+        x = (3145728 + rng.integers(0, 1000000, n)).astype(np.float32)
+        y = (-4194304 + rng.integers(0, 1000000, n)).astype(np.float32)
+    elif case == "half_integers":
+        x = (rng.integers(0, 2000, n) + 0.5).astype(np.float32)
+        y = rng.integers(0, 2000, n).astype(np.float32)
+    else:
+        x = rng.integers(0, 4000000, n).astype(np.float32)
+        y = rng.integers(0, 1000, n).astype(np.float32)
+    # neighbours at small distances too
+    x[10:20], y[10:20] = x[0] + np.arange(10, dtype=np.float32), y[0]
+    x[20], y[20] = x[0], y[0]
+    p = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32)
+    assert (p.matrix_packed() == O.matrix_packed_nint(x, y)).all()
+
+
 def test_k1_safe_sqrt_path_for_wild_coordinates(T, ctx):
     """Coordinates outside the fast-sqrt guarantee (tiny / huge) take the IEEE-safe kernels."""
     rng = np.random.default_rng(5)
