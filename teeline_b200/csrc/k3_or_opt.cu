@@ -118,10 +118,20 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+#ifdef TL_TIMELINE
+// tuning builds only: per-warp start / end globaltimer stamps and item counts of the latest scan
+__device__ unsigned long long tl_or_t[3][4096];
+__device__ __forceinline__ unsigned long long or_gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 template <class Pol>
 __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
-    or_opt_scan_kernel(Pol P, const Quad<typename Pol::V> *__restrict__ info, uint32_t n, int chunk,
-                       int items_per_cb, int item_begin, int item_end,
+    or_opt_scan_kernel(Pol P, const Quad<typename Pol::V> *__restrict__ info, uint32_t n, const OrOrder order,
                        Best<typename Pol::V> *__restrict__ blockbest, const DevState *__restrict__ state,
                        unsigned int *__restrict__ work_ticket)
 {
@@ -143,18 +153,26 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
     uint32_t phase = 0;
 
     BestV best{Val<V>::or_threshold(), kNone, kNone, 0u}; // or_opt.rs:86: best_delta = -1e-3
+#ifdef TL_TIMELINE
+    const unsigned long long tl_t0 = or_gtime();
+    unsigned long long tl_items = 0;
+#endif
 
     // Work items (column block x row chunk) are pulled from a global ticket: the tiles next to the
     // diagonal run the masked step and cost about twice the others, so a static one-item-per-warp
     // split would make the whole scan wait for them.
     for (;;) {
-        int item = 0;
-        if (lane == 0) item = item_begin + (int)atomicAdd(work_ticket, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= item_end) break;
-        const int cb = item / items_per_cb;
-        const int r_begin = (item - cb * items_per_cb) * chunk;
-        const int r_end = min(r_begin + chunk, (int)n);
+        int tk = 0;
+        if (lane == 0) tk = (int)atomicAdd(work_ticket, 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= order.total) break;
+#ifdef TL_TIMELINE
+        ++tl_items;
+#endif
+        int cb, ci;
+        order.item_of_ticket(tk, cb, ci); // diagonal (masked, expensive) tiles first: kernels.cuh
+        const int r_begin = ci * order.chunk;
+        const int r_end = min(r_begin + order.chunk, (int)n);
         const int J0 = cb * CW;           // first column of the warp
         const int j0 = J0 + lane * R;     // first column of this lane
 
@@ -258,6 +276,14 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
         }
     }
 
+#ifdef TL_TIMELINE
+    if (lane == 0 && blockIdx.x * WARPS + warp < 4096) {
+        const int w = blockIdx.x * WARPS + warp;
+        tl_or_t[0][w] = tl_t0;
+        tl_or_t[1][w] = or_gtime();
+        tl_or_t[2][w] = tl_items;
+    }
+#endif
     warp_argmin_or(best);
     if (lane == 0) red[warp] = best;
     __syncthreads();
@@ -422,14 +448,12 @@ void launch_or_rowinfo(const Src &src, uint32_t n, uint32_t npad, void *info, co
                              work_ticket)));
 }
 
-void launch_or_scan(const Src &src, const void *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
-                    int item_end, void *blockbest, const DevState *state, unsigned int *work_ticket, int grid,
-                    cudaStream_t st)
+void launch_or_scan(const Src &src, const void *info, uint32_t n, const OrOrder &order, void *blockbest,
+                    const DevState *state, unsigned int *work_ticket, int grid, cudaStream_t st)
 {
     const size_t smem = or_scan_smem_bytes();
     TL_DISPATCH_POL(src, (or_opt_scan_kernel<<<grid, WARPS * 32, smem, st>>>(
-                             P, reinterpret_cast<const Quad<typename decltype(P)::V> *>(info), n, chunk,
-                             items_per_cb, item_begin, item_end,
+                             P, reinterpret_cast<const Quad<typename decltype(P)::V> *>(info), n, order,
                              reinterpret_cast<Best<typename decltype(P)::V> *>(blockbest), state, work_ticket)));
 }
 
@@ -444,5 +468,12 @@ void launch_or_apply(const Src &src, void *tmp, uint32_t n, const void *cand, in
         or_apply_scatter_kernel<<<grid, 256, 0, st>>>(P, t, n, c, ncand, state, ticket, log, log_cap);
     });
 }
+
+#ifdef TL_TIMELINE
+extern "C" int tl_debug_or_timeline(unsigned long long *out)
+{
+    return cudaMemcpyFromSymbol(out, tl_or_t, sizeof(tl_or_t)) != cudaSuccess;
+}
+#endif
 
 } // namespace tl

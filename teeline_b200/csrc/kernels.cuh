@@ -124,9 +124,50 @@ size_t or_scan_smem_bytes();
 cudaError_t or_scan_configure();
 void launch_or_rowinfo(const Src &src, uint32_t n, uint32_t npad, void *info, const DevState *state,
                        unsigned int *work_ticket, cudaStream_t st);
-void launch_or_scan(const Src &src, const void *info, uint32_t n, int chunk, int items_per_cb, int item_begin,
-                    int item_end, void *blockbest, const DevState *state, unsigned int *work_ticket, int grid,
-                    cudaStream_t st);
+// Order in which the Or-opt scan hands out its work items (column block cb x row chunk c, index
+// cb * items_per_cb + c).  The tiles that touch the diagonal run the masked step and cost ~4x the
+// others; taken late they ARE the tail of the scan (per-warp timeline: warps end between 114 and
+// 223 us, mean 145), so the queue serves them first: in every column block the `near` chunks
+// [near_first(cb), near_first(cb) + near) count as "near".  A rank that owns the items [begin, end)
+// of the plain order takes ticket t < near_count as the (near_begin + t)-th near item of the whole
+// instance and any later ticket as the (far_begin + t - near_count)-th other item -- a bijection
+// onto [begin, end), so which items a rank scans does not change, only their order.  (One more
+// masked tile is not "near": rows 0.. against the LAST column block, where j = n-1 is the position
+// before i = 0.  An unsharded scan walks the other items from the last column block down so that
+// this tile comes right after the near ones instead of at the very end.)
+struct OrOrder {
+    int chunk, items_per_cb, near; // rows per item; items per column block; near chunks per block
+    int total;                     // items of this rank
+    int near_begin, near_count, far_begin;
+    int far_reversed_ncb; // > 0: unsharded scan over this many column blocks, far items taken last block first
+    __host__ __device__ int near_first(int cb) const
+    {
+        const int j0 = cb * 32 * kOrR;
+        const int a = j0 < 3 ? 0 : (j0 - 3) / chunk;
+        return a < items_per_cb - near ? a : items_per_cb - near;
+    }
+    __host__ __device__ int near_before(int item) const // near items among the plain-order items [0, item)
+    {
+        const int cb = item / items_per_cb, c = item - cb * items_per_cb - near_first(cb);
+        return cb * near + (c < 0 ? 0 : (c > near ? near : c));
+    }
+    __host__ __device__ void item_of_ticket(int t, int &cb, int &c) const
+    {
+        if (t < near_count) {
+            const int q = near_begin + t;
+            cb = q / near;
+            c = near_first(cb) + (q - cb * near);
+        } else {
+            const int far = items_per_cb - near, q = far_begin + (t - near_count);
+            cb = q / far;
+            const int cc = q - cb * far;
+            if (far_reversed_ncb > 0) cb = far_reversed_ncb - 1 - cb;
+            c = cc < near_first(cb) ? cc : cc + near;
+        }
+    }
+};
+void launch_or_scan(const Src &src, const void *info, uint32_t n, const OrOrder &order, void *blockbest,
+                    const DevState *state, unsigned int *work_ticket, int grid, cudaStream_t st);
 void launch_or_apply(const Src &src, void *tmp, uint32_t n, const void *cand, int ncand, DevState *state,
                      unsigned int *ticket, tl_move *log, uint64_t log_cap, int grid, cudaStream_t st);
 

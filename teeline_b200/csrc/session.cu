@@ -59,6 +59,7 @@ struct tl_session {
     DevBuf<unsigned char> rowinfo; // Or-opt: per-row removal gains (npad x 16 B)
     DevBuf<unsigned int> or_ticket; // Or-opt: work queue of the scan kernel
     int or_chunk = 0, or_items_per_cb = 0, or_item_begin = 0, or_item_end = 0;
+    OrOrder or_order{};
 
     ScanGeom geom{};
     DevBuf<int32_t> band_first;
@@ -148,7 +149,10 @@ void build_or_geometry(tl_session *s)
     const int cw = 32 * kOrR;
     const int ncb = (n + cw - 1) / cw;
     // ~4 items per resident warp (times the shard count): the scan kernel hands them out dynamically
-    const int64_t target = (int64_t)s->c->sm_count * kOrMinBlocks * kOrWarps * s->shard_count * 4;
+    // (6, 8 and 12 are no faster: every item re-stages its columns and restarts the distance pipeline)
+    int per_warp = 4;
+    if (const char *ev = getenv("TL_OR_ITEMS_PER_WARP")) per_warp = std::max(1, atoi(ev));
+    const int64_t target = (int64_t)s->c->sm_count * kOrMinBlocks * kOrWarps * s->shard_count * per_warp;
     const int per_cb = (int)std::max<int64_t>(1, target / ncb);
     s->or_chunk = std::max(16, (n + per_cb - 1) / per_cb);
     s->or_items_per_cb = (n + s->or_chunk - 1) / s->or_chunk;
@@ -158,6 +162,17 @@ void build_or_geometry(tl_session *s)
     s->or_item_end = (int)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
     const int64_t blocks = (per + kOrWarps - 1) / kOrWarps;
     s->grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)s->c->sm_count * kOrMinBlocks));
+    // diagonal tiles first (kernels.cuh: OrOrder)
+    OrOrder &o = s->or_order;
+    o.chunk = s->or_chunk;
+    o.items_per_cb = s->or_items_per_cb;
+    o.near = std::min(o.items_per_cb, (cw + 3 + o.chunk - 1) / o.chunk + 2);
+    if (getenv("TL_OR_PLAIN_ORDER")) o.near = o.items_per_cb; // every chunk "near": the plain cb-major order
+    o.total = s->or_item_end - s->or_item_begin;
+    o.near_begin = o.near_before(s->or_item_begin);
+    o.near_count = (s->or_item_end >= s->nitems ? ncb * o.near : o.near_before(s->or_item_end)) - o.near_begin;
+    o.far_begin = s->or_item_begin - o.near_begin;
+    o.far_reversed_ncb = s->shard_count == 1 ? ncb : 0;
 }
 
 // 3-opt work decomposition: an item is row i x 32 consecutive j; row_first[i] = items before row i.
@@ -290,8 +305,7 @@ tl_status launch_scan(tl_session *s, bool fuse)
         s->c->launches++;
     } else if (s->algo == TL_ALGO_OR_OPT) {
         launch_or_rowinfo(s->src, s->n, s->npad, s->rowinfo.p, s->state.p, s->or_ticket.p, st);
-        launch_or_scan(s->src, s->rowinfo.p, s->n, s->or_chunk, s->or_items_per_cb, s->or_item_begin,
-                       s->or_item_end, mine, s->state.p, s->or_ticket.p, s->grid, st);
+        launch_or_scan(s->src, s->rowinfo.p, s->n, s->or_order, mine, s->state.p, s->or_ticket.p, s->grid, st);
         s->c->launches += 2;
     } else if (s->matrix()) {
         launch_scan_matrix(s->src, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p, s->log_cap,
