@@ -383,9 +383,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     htour = torch.from_numpy(start.astype(np.uint32).view(np.int32)).pin_memory().numpy().view(np.uint32)
 
     def e2e_step():
+        ta = time.perf_counter()
         p2 = T.Problem.euc2d(ctx, hx, hy, kinds[args.dist])
+        tb = time.perf_counter()
         t2, st2, _ = p2.local_search(T.ALGO_TWO_OPT_BEST, htour, path=path, max_moves=args.e2e_moves)
+        tc = time.perf_counter()
         p2.close()
+        if os.environ.get("TL_DEBUG_TIMING"):
+            print(f"[bench] e2e call: create {1e3 * (tb - ta):.2f} ms, local_search {1e3 * (tc - tb):.2f} ms, "
+                  f"close {1e3 * (time.perf_counter() - tc):.2f} ms", file=sys.stderr)
         return int(st2.evals), int(st2.moves), t2
 
     e2e_step()

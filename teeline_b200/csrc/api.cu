@@ -126,6 +126,7 @@ void tl_ctx_destroy(tl_ctx *ctx)
     DeviceGuard g(ctx);
     if (ctx->nccl_comm) nccl_comm_destroy(ctx->nccl_comm);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (void *chunk : ctx->pin_chunks) cudaFreeHost(chunk);
     delete ctx;
 }
 

@@ -3,6 +3,9 @@
 
 #include <cuda_runtime.h>
 
+#include <mutex>
+#include <vector>
+
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -21,6 +24,29 @@ struct tl_ctx {
     // NCCL (resolved at run time with dlopen, see nccl_shim.cu)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // pinned host slots (256 B each) for asynchronous state snapshots: cudaMallocHost / cudaFreeHost
+    // cost milliseconds and synchronise the device, so sessions borrow a slot instead of owning one
+    std::mutex pin_mu;
+    std::vector<void *> pin_free;   // slots ready to be borrowed
+    std::vector<void *> pin_chunks; // cudaMallocHost allocations, freed with the context
+    void *borrow_pinned()
+    {
+        std::lock_guard<std::mutex> lk(pin_mu);
+        if (pin_free.empty()) {
+            void *chunk = nullptr;
+            if (cudaMallocHost(&chunk, 16 * 256) != cudaSuccess) return nullptr;
+            pin_chunks.push_back(chunk);
+            for (int k = 0; k < 16; ++k) pin_free.push_back(static_cast<char *>(chunk) + 256 * k);
+        }
+        void *p = pin_free.back();
+        pin_free.pop_back();
+        return p;
+    }
+    void return_pinned(void *p)
+    {
+        std::lock_guard<std::mutex> lk(pin_mu);
+        pin_free.push_back(p);
+    }
 };
 
 enum ProblemKind { PK_EUC_F32 = 0, PK_EUC_NINT = 1, PK_EXPLICIT = 2 };

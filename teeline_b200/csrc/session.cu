@@ -12,6 +12,7 @@
 #include "host.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -77,6 +78,10 @@ struct tl_session {
     uint64_t pairs_per_scan = 0;
     uint64_t launches0 = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // tl_session_run: two pinned snapshots of the device state, read back asynchronously so that the
+    // next batch of steps is already queued while the host looks at the previous one
+    DevState *h_snap = nullptr;
+    cudaEvent_t ev_snap[2] = {nullptr, nullptr};
     bool timing_open = false;
     double device_ms = 0.0;
 
@@ -583,6 +588,9 @@ void tl_session_destroy(tl_session *s)
     cudaStreamSynchronize(s->c->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : s->ev_snap)
+        if (e) cudaEventDestroy(e);
+    if (s->h_snap) s->c->return_pinned(s->h_snap);
     delete s;
 }
 
@@ -682,16 +690,39 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
     s->h.done = (max_moves >= 0 && (long long)s->h.moves >= max_moves) ? 1 : 0;
     rc = push_state(s);
     if (rc != TL_OK) return rc;
-    while (!s->h.done) {
-        // one host round trip per batch; steps enqueued past convergence are no-op launches
+    if (s->h.done) return close_timing(s);
+    if (!s->h_snap) {
+        static_assert(2 * sizeof(DevState) <= 256, "two state snapshots fit one pinned slot");
+        s->h_snap = static_cast<DevState *>(s->c->borrow_pinned());
+        if (!s->h_snap) { set_error("tl_session_run: pinned host allocation failed"); return TL_ERR_NOMEM; }
+        for (cudaEvent_t &e : s->ev_snap) TL_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // Batches of steps are double buffered: batch k+1 is queued before the host waits for the state
+    // snapshot taken after batch k, so the device never idles on a host round trip.  Steps queued
+    // past convergence (or past max_moves, which the device checks itself) are no-op launches.
+    auto issue = [&](int slot) -> tl_status {
         uint32_t batch = s->algo == TL_ALGO_TWO_OPT_REF ? 64 : 32;
         if (max_moves >= 0 && s->algo != TL_ALGO_TWO_OPT_REF) // every step applies exactly one move
             batch = (uint32_t)std::min<int64_t>(256, std::max<int64_t>(1, max_moves - (int64_t)s->h.moves));
-        rc = enqueue_steps(s, batch);
+        tl_status r = enqueue_steps(s, batch);
+        if (r != TL_OK) return r;
+        TL_CUDA_TRY(cudaMemcpyAsync(s->h_snap + slot, s->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, s->c->stream));
+        TL_CUDA_TRY(cudaEventRecord(s->ev_snap[slot], s->c->stream));
+        return TL_OK;
+    };
+    int slot = 0;
+    rc = issue(0);
+    if (rc != TL_OK) return rc;
+    for (;;) {
+        rc = issue(1 - slot);
         if (rc != TL_OK) return rc;
-        rc = pull_state(s);
-        if (rc != TL_OK) return rc;
+        TL_CUDA_TRY(cudaEventSynchronize(s->ev_snap[slot]));
+        s->h = s->h_snap[slot];
+        slot = 1 - slot;
+        if (s->h.done) break;
     }
+    TL_CUDA_TRY(cudaEventSynchronize(s->ev_snap[slot])); // the batch that was queued ahead
+    s->h = s->h_snap[slot];
     return close_timing(s);
 }
 
@@ -750,8 +781,12 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
 {
     if (!p || !tour_inout) { set_error("tl_local_search: null argument"); return TL_ERR_INVALID; }
     tl_session *s = nullptr;
+    const bool trace = getenv("TL_DEBUG_TIMING") != nullptr; // host wall time of each phase on stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0.0;
     tl_status rc = tl_session_create(p, algo, path, tour_inout, &s);
     if (rc != TL_OK) return rc;
+    const double t1 = trace ? now() : 0.0;
     if (log && log_cap > s->log_cap) {
         DeviceGuard g(s->c);
         if (s->log.alloc(log_cap) != cudaSuccess) {
@@ -762,13 +797,18 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
         s->log_cap = log_cap;
     }
     rc = tl_session_run(s, max_moves);
+    const double t2 = trace ? now() : 0.0;
     if (rc == TL_OK) rc = tl_session_tour(s, tour_inout);
     if (rc == TL_OK && stats) rc = tl_session_stats(s, stats);
     if (rc == TL_OK && log) {
         size_t got = 0;
         rc = tl_session_log(s, log, log_cap, &got);
     }
+    const double t3 = trace ? now() : 0.0;
     tl_session_destroy(s);
+    if (trace)
+        fprintf(stderr, "[tl] local_search: create %.2f ms, run %.2f ms, tour+stats+log %.2f ms, destroy %.2f ms\n",
+                t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
 }
 
