@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     two_opt_scan_matrix_kernel(const V *__restrict__ M, uint32_t ld, Cs *__restrict__ cs, const ScanGeom g,
                                const int32_t *__restrict__ band_first_g, Best<V> *__restrict__ blockbest,
                                DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
-                               uint64_t log_cap, int fuse_apply, int pin_rows)
+                               uint64_t log_cap, int fuse_apply, int pin_rows, int pf_rows)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     griddep_launch_dependents(); // PDL, as in k2_two_opt.cu
@@ -219,6 +219,30 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
         t_next = find_band_m(band_first, g.nbands, u_lo);
         tf_next = band_first[t_next];
         tl_next = band_first[t_next + 1];
+        // L2 prefetch of the first rows of this warp's item, issued BEFORE the grid dependency
+        // resolves.  Programmatic dependent launch makes this CTA resident while the previous step
+        // is still running down (its CTAs finish between 30 and 38 us) and while its last CTA
+        // reduces the candidates and reverses the segment -- 6 us per step during which HBM would
+        // otherwise idle.  The matrix itself never changes; the tour records read here may be
+        // one move stale (the apply may be rewriting them), which can only make a prefetch useless,
+        // never wrong: nothing read here is used after the wait.  One lane per row, one bulk
+        // prefetch of the row's ~1 KB (contiguous whenever the columns still sit in one run).
+        if (pf_rows > 0) {
+            const int K0p = 2 + t_next * BW;
+            const int r0 = (u_lo - tf_next) * g.chunk;
+            const int r1 = min(r0 + (min(u_hi, tl_next) - u_lo) * g.chunk, g.jmax - K0p + 1);
+            const int rows = min(pf_rows, r1 - r0 + 1); // + the row of E
+            if (lane < rows) {
+                const int rs = __ldcg(&cs[r0 + lane].slot);
+                const int s0 = __ldcg(&cs[r0 + K0p + lane].slot), s1 = __ldcg(&cs[r0 + K0p + lane + BW - 1].slot);
+                const size_t first = (size_t)(uint32_t)rs * ld + (uint32_t)min(s0, s1);
+                const size_t last = (size_t)g.n * ld; // one past the matrix
+                if (rs >= 0 && rs < g.n && first + BW + 4 <= last) {
+                    const uint64_t a = (reinterpret_cast<uint64_t>(M) + first * sizeof(V)) & ~(uint64_t)15;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)(BW * sizeof(V) + 16)) : "memory");
+                }
+            }
+        }
     }
     griddep_wait(); // the previous step's move is applied and visible from here on
     if (*reinterpret_cast<const volatile int *>(&state->done)) return; // grid-uniform
@@ -484,9 +508,14 @@ void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_f
     cfg.numAttrs = nattr;
     const int fuse = fuse_apply ? 1 : 0;
     const int pin_rows = pin.hint_rows;
+    static const int pf_default = [] {
+        const char *ev = getenv("TL_MAT_PREFETCH_ROWS");
+        return ev ? max(0, min(32, atoi(ev))) : kMatPrefetchRows;
+    }();
+    const int pf_rows = pf_default;
 #define TL_LAUNCH_MAT(V, PINNED, BEST)                                                                          \
     cudaLaunchKernelEx(&cfg, two_opt_scan_matrix_kernel<V, PINNED>, (const V *)src.M, src.ld, src.cs, g,        \
-                       band_first, (BEST *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse, pin_rows)
+                       band_first, (BEST *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse, pin_rows, pf_rows)
     if (src.is_int()) {
         if (pin_rows > 0) TL_LAUNCH_MAT(int32_t, true, BestI); else TL_LAUNCH_MAT(int32_t, false, BestI);
     } else {

@@ -201,6 +201,7 @@ constexpr int kMatMinBlocks = TL_MAT_MINB;
 #define TL_MAT_D 4
 #endif
 constexpr int kMatD = TL_MAT_D;          // prefetch depth in row steps
+constexpr int kMatPrefetchRows = 16;      // rows per warp prefetched into L2 before the grid dependency resolves
 size_t scan_matrix_smem_bytes();
 cudaError_t scan_matrix_configure();
 #ifndef TL_MAT_PIN_MB
