@@ -356,6 +356,8 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
                     }
                 }
                 if (tau + D < cnt) issue(std::integral_constant<int, e>{}, tau + D);
+                // (Tried: an in-loop L2 bulk prefetch 8-32 row steps ahead of the ring, to speed up
+                // the last warps of a scan -- 10k step 40.7 -> 45.7 us, 20k 150 -> 178 us; removed.)
             };
             int t = 0;
 #pragma unroll 1
