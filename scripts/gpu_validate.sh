@@ -13,3 +13,9 @@ NCU="ncu --clock-control none"
 timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file $out/launches_nint.csv python scripts/prof_target.py matrix 10000 20 best nint > $out/launches_nint.log 2>&1
 timeout 900 $NCU --set full --import-source on -k regex:two_opt_scan -s 3 -c 1 -f -o $out/prof_nint python scripts/prof_target.py matrix 10000 8 best nint > $out/prof_nint.log 2>&1
 ls -la $out
+# per-kernel table (time / DRAM bytes / instructions of every kernel around the headline scan)
+timeout 900 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --csv --log-file $out/kernels_launches.csv python scripts/kernels_target.py > $out/kernels.log 2>&1
+python scripts/kernels_table.py $out/kernels_launches.csv $out/kernels_table.md > /dev/null
+# full capture of the Or-opt scan
+timeout 900 $NCU --set full --import-source on -k regex:or_opt_scan -s 1 -c 1 -f -o $out/prof_oropt python scripts/prof_target.py recompute 10000 3 oropt > $out/prof_oropt.log 2>&1
+ls -la $out
