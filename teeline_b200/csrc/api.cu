@@ -353,6 +353,25 @@ tl_status tl_tour_lengths(tl_problem *p, const uint32_t *tours, size_t batch, in
                             c->sm_count, c->stream);
     c->launches++;
     TL_CUDA_TRY(cudaGetLastError());
+    if (getenv("TL_K4_TIMING")) { // tuning aid: warm kernel time (CUDA events, 10 back-to-back launches) on stderr
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+        for (int r = 0; r < 10; ++r)
+            launch_tour_lengths_f32(p->d_xy, p->d_tri, p->n, d_t.p, batch, p->fast_sqrt, mode == TL_LEN_FAST, d_o.p,
+                                    c->sm_count, c->stream);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[tl] tour_lengths %s n=%u batch=%zu: %.2f us per launch, %.1f GB/s of tour indices, %.2f G edges/s\n",
+                mode == TL_LEN_FAST ? "fast" : "exact", p->n, batch, ms / 10 * 1e3,
+                batch * p->n * 4.0 / (ms / 10 * 1e-3) / 1e9, batch * (double)p->n / (ms / 10 * 1e-3) / 1e9);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        c->launches += 10;
+    }
     TL_CUDA_TRY(cudaMemcpyAsync(out_f32, d_o.p, batch * 4, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return TL_OK;

@@ -21,16 +21,19 @@ namespace tl {
 
 namespace {
 
-template <bool FAST>
+// SXY: `xy` is the CTA's shared-memory copy of the coordinates.  The two gathers per edge are
+// what bounds this kernel: 32 random 8-byte reads through L1 cost ~25 wavefronts per instruction
+// (one per distinct 128-byte line), from shared memory 3-4 (bank conflicts only).
+template <bool FAST, bool SXY>
 __device__ __forceinline__ float edge_f32(const float2 *__restrict__ xy, const float *__restrict__ tri,
                                           uint32_t a, uint32_t b)
 {
     if (a == b) return 0.0f; // distance_by_pos: pos1 == pos2 -> 0.0
-    if (tri) {
+    if (!SXY && tri) {
         const uint64_t hi = max(a, b), lo = min(a, b);
         return __ldg(&tri[hi * (hi - 1) / 2 + lo]);
     }
-    const float2 p = __ldg(&xy[a]), q = __ldg(&xy[b]);
+    const float2 p = SXY ? xy[a] : __ldg(&xy[a]), q = SXY ? xy[b] : __ldg(&xy[b]);
     return dist_f32<FAST>(p.x, p.y, q.x, q.y);
 }
 
@@ -42,13 +45,19 @@ __device__ __forceinline__ float edge_f32(const float2 *__restrict__ xy, const f
 //      lanes busy -- 2 warp instructions per 32 edges instead of 64 for a warp-per-tour shuffle
 //      chain.  The serial f32 chain (the reference's sum order) is kept; 32 chains run side by
 //      side and the edge computation of the other 7 warps overlaps other CTAs' folds.
-template <bool FAST, bool FASTMODE>
+template <bool FAST, bool FASTMODE, bool SXY>
 __global__ void __launch_bounds__(256)
-    tour_lengths_f32_kernel(const float2 *__restrict__ xy, const float *__restrict__ tri, uint32_t n,
+    tour_lengths_f32_kernel(const float2 *__restrict__ gxy, const float *__restrict__ tri, uint32_t n,
                             const uint32_t *__restrict__ tours, uint64_t batch, float *__restrict__ out)
 {
     __shared__ float slen[8][32][33]; // [chunk slot][tour][edge], padded: conflict-free both ways
     __shared__ unsigned int s_bad;    // bit e: tour e of the group has an out-of-range entry
+    extern __shared__ __align__(16) float2 s_xy[]; // SXY: all n coordinates
+    const float2 *xy = gxy;
+    if constexpr (SXY) {
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) s_xy[t] = __ldg(&gxy[t]);
+        xy = s_xy; // the first __syncthreads of the group loop orders the copy before its readers
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t groups = (batch + 31) / 32;
     const uint32_t nchunks = n < 2 ? 0 : (n - 1 + 31) / 32;
@@ -66,7 +75,7 @@ __global__ void __launch_bounds__(256)
         if (have && n >= 2) { // closing edge first (distance_matrix.rs:240)
             const uint32_t first = __ldg(&tours[mine * n]), last = __ldg(&tours[mine * n + n - 1]);
             bad = first >= n || last >= n;
-            const float e0 = bad ? 0.0f : edge_f32<FAST>(xy, tri, last, first);
+            const float e0 = bad ? 0.0f : edge_f32<FAST, false>(gxy, tri, last, first);
             acc = e0;
             dacc = (double)e0;
         }
@@ -96,7 +105,7 @@ __global__ void __launch_bounds__(256)
                         const bool in = (uint32_t)lane < cnt;
                         const bool oob = in && (a[u] >= n || c[u] >= n);
                         if (oob) badbits |= 1u << (e0 + u < ntours ? e0 + u : ntours - 1);
-                        len[u] = (in && !oob) ? edge_f32<FAST>(xy, tri, a[u], c[u]) : 0.0f;
+                        len[u] = (in && !oob) ? edge_f32<FAST, SXY>(xy, tri, a[u], c[u]) : 0.0f;
                     }
 #pragma unroll
                     for (int u = 0; u < U; ++u)
@@ -165,17 +174,26 @@ void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, con
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return;
     const unsigned g = (unsigned)blocks;
+    // coordinates in shared memory when they fit beside the edge buffer and there are enough tours
+    // per CTA to pay for the copy
+    const size_t xy_bytes = (size_t)n * sizeof(float2);
+    const bool sxy = !tri && xy_bytes <= 190 * 1024 && batch >= 4 * blocks;
+#define TL_LAUNCH_K4(FS, FM)                                                                                     \
+    do {                                                                                                         \
+        if (sxy) {                                                                                               \
+            cudaFuncSetAttribute(tour_lengths_f32_kernel<FS, FM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 190 * 1024);                                                                    \
+            tour_lengths_f32_kernel<FS, FM, true><<<g, 256, xy_bytes, st>>>(xy, tri, n, tours, batch, out);       \
+        } else {                                                                                                 \
+            tour_lengths_f32_kernel<FS, FM, false><<<g, 256, 0, st>>>(xy, tri, n, tours, batch, out);            \
+        }                                                                                                        \
+    } while (0)
     if (fast_sqrt) {
-        if (fast_mode)
-            tour_lengths_f32_kernel<true, true><<<g, 256, 0, st>>>(xy, tri, n, tours, batch, out);
-        else
-            tour_lengths_f32_kernel<true, false><<<g, 256, 0, st>>>(xy, tri, n, tours, batch, out);
+        if (fast_mode) TL_LAUNCH_K4(true, true); else TL_LAUNCH_K4(true, false);
     } else {
-        if (fast_mode)
-            tour_lengths_f32_kernel<false, true><<<g, 256, 0, st>>>(xy, tri, n, tours, batch, out);
-        else
-            tour_lengths_f32_kernel<false, false><<<g, 256, 0, st>>>(xy, tri, n, tours, batch, out);
+        if (fast_mode) TL_LAUNCH_K4(false, true); else TL_LAUNCH_K4(false, false);
     }
+#undef TL_LAUNCH_K4
 }
 
 void launch_tour_lengths_nint(const float2 *xy, uint32_t n, const uint32_t *tours, uint64_t batch,
