@@ -86,6 +86,19 @@ t0 = time.perf_counter()
 (lo, hi), mine, all_len, best, best_tour = multi.sharded_population(tours, lambda t: p.two_opt_batch(t)[::2], dist)
 torch.cuda.synchronize()
 dt = tmax(time.perf_counter() - t0)
+# weak scaling of the same case: every rank solves its OWN 1024-tour population (different shuffles),
+# no data-path collective; the time is the slowest rank's wall clock
+wtours = np.stack([bench.shuffle_tour(n, 100000 * (rank + 1) + s) for s in range(B)])
+dist.barrier()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+_, wst, _ = p.two_opt_batch(wtours)
+torch.cuda.synchronize()
+wdt = tmax(time.perf_counter() - t0)
+wev = torch.tensor([float(wst.evals)], device="cuda", dtype=torch.float64)
+dist.all_reduce(wev)
+out["config5_weak_1024_per_gpu"] = {"tours_total": B * world, "slowest_rank_wall_s": wdt, "evals_total": float(wev.item()),
+                                    "evals_per_s_aggregate": float(wev.item()) / wdt}
 single = None
 if rank == 0:
     t0 = time.perf_counter()

@@ -245,13 +245,16 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
         }
     }
     griddep_wait(); // the previous step's move is applied and visible from here on
-    if (*reinterpret_cast<const volatile int *>(&state->done)) return; // grid-uniform
+    // "done" (grid-uniform: later launches of a finished search are no-ops) is only LOADED here; the
+    // branch sits behind the first tile's staging loads so that the two round trips overlap.
+    // Nothing but this warp's shared-memory staging is written before it.
+    const int done_flag = *reinterpret_cast<const volatile int *>(&state->done);
     TL_MARK_MIN(0);
     // the items [dyn_begin, item_end) go to whichever warp asks first; the next ticket is always
     // requested before the current item is scanned, so its latency is hidden
     const bool has_dyn = g.dyn_begin < g.item_end;
     unsigned int tk = 0;
-    if (has_dyn && lane == 0) tk = atomicAdd(ticket + 1, 1u);
+    if (has_dyn && !done_flag && lane == 0) tk = atomicAdd(ticket + 1, 1u);
     bool first = true;
 
     for (;;) {
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
                 scol_slot[t] = c.slot;
                 scol_sp[t] = c.sp_bits;
             }
+            if (done_flag) return;
             __syncwarp();
 
             // Lane l owns the diagonals k_r = K0 + l + 32 r.  Row step tau handles the pairs
@@ -371,6 +375,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
         }
     }
 
+    if (done_flag) return; // warps without a work item
     warp_argmin_2opt(best, bi, bj);
     if (lane == 0) red[warp] = Best<V>{best, bi, bj, 0u};
     __syncthreads();
