@@ -21,8 +21,13 @@ for algo_name, algo, cand in (("two_opt_best", T.ALGO_TWO_OPT_BEST, P2), ("or_op
         s = p.session(algo, p.nn_tour(3), path)
         s.enqueue(3)
         ctx.sync()
+        import time
+        t0 = time.perf_counter()
+        s.enqueue(50)
+        ctx.sync()
+        step_ms = (time.perf_counter() - t0) * 1e3 / 50  # scan + apply (+ rowinfo for Or-opt), host-timed over 50 steps
         ms = s.time_scans(20)
-        print(json.dumps({"algo": algo_name, "path": path_name, "n": n, "scan_ms": round(ms, 4), "candidates": cand,
-                          "G_candidates_per_s": round(cand / ms / 1e6, 1)}), flush=True)
+        print(json.dumps({"algo": algo_name, "path": path_name, "n": n, "scan_ms": round(ms, 4), "step_ms": round(step_ms, 4),
+                          "candidates": cand, "G_candidates_per_s": round(cand / ms / 1e6, 1)}), flush=True)
         s.close()
         p.close()
