@@ -53,10 +53,7 @@ __global__ void __launch_bounds__(256)
         __syncthreads();
         const uint32_t cnt = min((uint32_t)kTile, n - c0);
         if (q < n) {
-            for (uint32_t t = 0; t < cnt; ++t) {
-                const uint32_t c = c0 + t;
-                const float2 pc = tile[t];
-                const float d = metric<METRIC>(pq.x, pq.y, pc.x, pc.y);
+            auto offer = [&](uint32_t c, float d) {
                 if (c != q && d < dk[K - 1]) {
                     // elements <= d stay; the first slot with a larger key takes d; the rest shift
 #pragma unroll
@@ -72,6 +69,23 @@ __global__ void __launch_bounds__(256)
                         }
                     }
                 }
+            };
+            // a query is one thread walking n candidates: four distances are computed before the
+            // four (ordered, rarely taken) insertions so that their sqrt chains overlap
+            uint32_t t = 0;
+            for (; t + 4 <= cnt; t += 4) {
+                float d[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 pc = tile[t + u];
+                    d[u] = metric<METRIC>(pq.x, pq.y, pc.x, pc.y);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) offer(c0 + t + u, d[u]);
+            }
+            for (; t < cnt; ++t) {
+                const float2 pc = tile[t];
+                offer(c0 + t, metric<METRIC>(pq.x, pq.y, pc.x, pc.y));
             }
         }
     }
@@ -236,15 +250,18 @@ __global__ void __launch_bounds__(1024)
 template <int METRIC>
 void launch_knn_k(const float2 *xy, uint32_t n, uint32_t k, uint32_t *out, cudaStream_t st)
 {
-    const int grid = (int)((n + 255) / 256);
+    // one thread per query: a query's time is n candidates long whatever the grid, so small
+    // instances get small CTAs -- more SMs busy, fewer warps sharing a scheduler
+    const int threads = n >= 148u * 256u ? 256 : (n >= 148u * 128u ? 128 : 64);
+    const int grid = (int)((n + threads - 1) / threads);
     if (k <= 4)
-        knn_kernel<METRIC, 4><<<grid, 256, 0, st>>>(xy, n, k, out);
+        knn_kernel<METRIC, 4><<<grid, threads, 0, st>>>(xy, n, k, out);
     else if (k <= 8)
-        knn_kernel<METRIC, 8><<<grid, 256, 0, st>>>(xy, n, k, out);
+        knn_kernel<METRIC, 8><<<grid, threads, 0, st>>>(xy, n, k, out);
     else if (k <= 16)
-        knn_kernel<METRIC, 16><<<grid, 256, 0, st>>>(xy, n, k, out);
+        knn_kernel<METRIC, 16><<<grid, threads, 0, st>>>(xy, n, k, out);
     else
-        knn_kernel<METRIC, 32><<<grid, 256, 0, st>>>(xy, n, k, out);
+        knn_kernel<METRIC, 32><<<grid, threads, 0, st>>>(xy, n, k, out);
 }
 
 } // namespace
