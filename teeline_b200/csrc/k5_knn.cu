@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(1024)
                 cur = pick;
                 ++step;
             }
+            __syncwarp(); // every lane has read s_cur / s_step (the walk may have made no step)
             if (lane == 0) {
                 s_cur = cur;
                 s_step = step;
