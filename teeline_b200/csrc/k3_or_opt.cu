@@ -222,7 +222,11 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
 #pragma unroll
                 for (int c = 0; c <= R; ++c) A[P2][c] = P.dist_rc(rp, cc[c]);
                 const int i = i0 + tau;
-                const int prev = i == 0 ? (int)n - 1 : i - 1;
+                // forbidden insertion edges of row i, segment length s (or_opt.rs:124): j == prev or
+                // i <= j < i + s.  For i >= 1 that is j - i in [-1, s-1], i.e. (unsigned)(j - i + 1) <= s:
+                // one compare per candidate on a per-row base; row 0 has prev = n - 1 instead of -1.
+                const int mbase = j0 - i + 1;                         // (j - i + 1) for r = 0
+                const int jwrap = i == 0 ? (int)n - 1 - j0 : -1;      // r of column n-1 in row 0, else none
                 // candidate (r, k): k = 0 fwd1, 1 fwd2, 2 rev2, 3 fwd3, 4 rev3
                 auto cand = [&](int r, int k) -> V {
                     const V nrg = k == 0 ? ri.x : (k <= 2 ? ri.y : ri.z);
@@ -230,9 +234,8 @@ __global__ void __launch_bounds__(WARPS * 32, kOrMinBlocks)
                     const V second = (k == 1) ? A[P1][r + 1] : (k == 3 ? A[P2][r + 1] : A[P0][r + 1]);
                     V d = Val<V>::sub(Val<V>::add(Val<V>::add(nrg, first), second), exy[r]);
                     if (MASKED) {
-                        const int j = j0 + r;
-                        const int s = k == 0 ? 1 : (k <= 2 ? 2 : 3);
-                        if (j == prev || (j >= i && j < i + s)) d = Val<V>::pos_inf();
+                        const unsigned s = k == 0 ? 1u : (k <= 2 ? 2u : 3u);
+                        if ((unsigned)(mbase + r) <= s || r == jwrap) d = Val<V>::pos_inf();
                     }
                     return d;
                 };
