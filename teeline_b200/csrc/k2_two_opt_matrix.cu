@@ -68,6 +68,20 @@ __device__ __forceinline__ void static_for(F &&f)
     }
 }
 
+// warp argmin that also carries the record's aux word (the winning pair's d(p_i, p_j), see below)
+template <typename V>
+__device__ __forceinline__ void warp_argmin_2opt_aux(V &d, uint32_t &i, uint32_t &j, uint32_t &aux)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const V od = __shfl_xor_sync(0xffffffffu, d, off);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, i, off);
+        const uint32_t oj = __shfl_xor_sync(0xffffffffu, j, off);
+        const uint32_t oa = __shfl_xor_sync(0xffffffffu, aux, off);
+        if (better_2opt(od, oi, oj, d, i, j)) { d = od; i = oi; j = oj; aux = oa; }
+    }
+}
+
 constexpr int kBandCap = 1024; // band table entries kept in shared memory (n up to ~260k)
 
 __device__ __forceinline__ int find_band_m(const int32_t *band_first, int nbands, int item)
@@ -133,7 +147,7 @@ __device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, ui
             if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
         }
     }
-    warp_argmin_2opt(v.delta, v.i, v.j);
+    warp_argmin_2opt_aux(v.delta, v.i, v.j, v.aux);
     __syncthreads();
     if (lane == 0) red[warp] = v;
     __syncthreads();
@@ -147,7 +161,10 @@ __device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, ui
 #ifdef TL_TIMELINE
     const unsigned long long t_reduced = gtime();
 #endif
-    if (found) reverse_segment_inplace(MatPol<V>{cs, M, ld}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
+    // integer metric: the record carries d(p_i, p_j), so the reversal needs no matrix loads
+    if (found)
+        reverse_segment_inplace(MatPol<V>{cs, M, ld}, v.i, v.j, nullptr, threadIdx.x, blockDim.x,
+                                std::is_same<V, int32_t>::value, Val<V>::from_bits((int32_t)v.aux), v.delta);
 #ifdef TL_TIMELINE
     __syncthreads();
     const unsigned long long t_reversed = gtime();
@@ -210,7 +227,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     }
 
     V best = (V)0;
-    uint32_t bi = 0xffffffffu, bj = 0xffffffffu;
+    uint32_t bi = 0xffffffffu, bj = 0xffffffffu, baux = 0u;
     // this warp's static run of work items (geometry only, so it may be looked up before the wait)
     int u_lo = g.item_begin + (blockIdx.x * WARPS + warp) * g.run;
     int u_hi = min(u_lo + g.run, g.dyn_begin);
@@ -356,6 +373,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
                             best = dl[r];
                             bi = i;
                             bj = j;
+                            baux = (uint32_t)Val<V>::bits(ring[e][r]); // d(p_i, p_j): the apply needs it
                         }
                     }
                 }
@@ -376,12 +394,12 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     }
 
     if (done_flag) return; // warps without a work item
-    warp_argmin_2opt(best, bi, bj);
-    if (lane == 0) red[warp] = Best<V>{best, bi, bj, 0u};
+    warp_argmin_2opt_aux(best, bi, bj, baux);
+    if (lane == 0) red[warp] = Best<V>{best, bi, bj, baux};
     __syncthreads();
     if (warp == 0) {
         Best<V> v = (lane < WARPS) ? red[lane] : Best<V>{(V)0, 0xffffffffu, 0xffffffffu, 0u};
-        warp_argmin_2opt(v.delta, v.i, v.j);
+        warp_argmin_2opt_aux(v.delta, v.i, v.j, v.aux);
         if (lane == 0) blockbest[blockIdx.x] = v;
     }
     // the last CTA to finish re-arms the dynamic work queue and, in a fused step, reduces the

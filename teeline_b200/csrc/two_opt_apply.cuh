@@ -13,9 +13,14 @@ namespace tl {
 // two new edges are produced by thread 0.  Every field of every record is read and written by
 // exactly one thread, so the update is race free without a second buffer.  If delta_out is
 // non-null, thread 0 also stores (d(p_i,p_j) + d(p_i+1,p_j+1)) - (d(p_i,p_i+1) + d(p_j,p_j+1)).
+// known_e1: the caller already knows e1 = d(p_i, p_j) and the move's delta (integer metric only:
+// the matrix scan's winning thread held e1, and e2 = delta + (s_i + s_j) - e1 exactly), which
+// saves the two dependent matrix loads -- an HBM round trip on the fused step's critical path.
 template <class Pol>
 __device__ __forceinline__ void reverse_segment_inplace(const Pol &P, uint32_t mi, uint32_t mj, float *delta_out,
-                                                        uint32_t tid, uint32_t nthreads)
+                                                        uint32_t tid, uint32_t nthreads, bool known_e1 = false,
+                                                        typename Pol::V e1_in = typename Pol::V(),
+                                                        typename Pol::V delta_in = typename Pol::V())
 {
     using V = typename Pol::V;
     using Rec = typename Pol::Rec;
@@ -47,8 +52,14 @@ __device__ __forceinline__ void reverse_segment_inplace(const Pol &P, uint32_t m
             if (t >= nxy) continue;
             const uint32_t a = mi + 1 + t, b = mj - t;
             if (t == 0) {
-                const V e1 = P.dist(P0, B[u]); // new edge (p_i, p_j)
-                const V e2 = P.dist(A[u], P1); // new edge (p_i+1, p_j+1)
+                V e1, e2;
+                if (known_e1) {
+                    e1 = e1_in;
+                    e2 = Val<V>::sub(Val<V>::add(delta_in, Val<V>::add(Pol::sp(A[u]), Pol::sp(P1))), e1_in);
+                } else {
+                    e1 = P.dist(P0, B[u]); // new edge (p_i, p_j)
+                    e2 = P.dist(A[u], P1); // new edge (p_i+1, p_j+1)
+                }
                 if (delta_out)
                     *delta_out = (float)Val<V>::sub(Val<V>::add(e1, e2), Val<V>::add(Pol::sp(A[u]), Pol::sp(P1)));
                 P.store_sp(a, e1);
