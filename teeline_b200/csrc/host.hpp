@@ -24,7 +24,7 @@ struct tl_ctx {
     // NCCL (resolved at run time with dlopen, see nccl_shim.cu)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
-    // pinned host slots (256 B each) for asynchronous state snapshots: cudaMallocHost / cudaFreeHost
+    // pinned host slots (512 B each) for asynchronous state snapshots: cudaMallocHost / cudaFreeHost
     // cost milliseconds and synchronise the device, so sessions borrow a slot instead of owning one
     std::mutex pin_mu;
     std::vector<void *> pin_free;   // slots ready to be borrowed
@@ -34,9 +34,9 @@ struct tl_ctx {
         std::lock_guard<std::mutex> lk(pin_mu);
         if (pin_free.empty()) {
             void *chunk = nullptr;
-            if (cudaMallocHost(&chunk, 16 * 256) != cudaSuccess) return nullptr;
+            if (cudaMallocHost(&chunk, 16 * 512) != cudaSuccess) return nullptr;
             pin_chunks.push_back(chunk);
-            for (int k = 0; k < 16; ++k) pin_free.push_back(static_cast<char *>(chunk) + 256 * k);
+            for (int k = 0; k < 16; ++k) pin_free.push_back(static_cast<char *>(chunk) + 512 * k);
         }
         void *p = pin_free.back();
         pin_free.pop_back();

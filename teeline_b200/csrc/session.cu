@@ -78,10 +78,10 @@ struct tl_session {
     uint64_t pairs_per_scan = 0;
     uint64_t launches0 = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // tl_session_run: two pinned snapshots of the device state, read back asynchronously so that the
-    // next batch of steps is already queued while the host looks at the previous one
+    // tl_session_run: pinned snapshots of the device state, read back asynchronously so that the
+    // next batches of steps are already queued while the host looks at an earlier one
     DevState *h_snap = nullptr;
-    cudaEvent_t ev_snap[2] = {nullptr, nullptr};
+    cudaEvent_t ev_snap[3] = {nullptr, nullptr, nullptr};
     bool timing_open = false;
     double device_ms = 0.0;
 
@@ -691,38 +691,53 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
     rc = push_state(s);
     if (rc != TL_OK) return rc;
     if (s->h.done) return close_timing(s);
+    constexpr int kSlots = 3; // batches in flight: two are always queued behind the one the host waits for
     if (!s->h_snap) {
-        static_assert(2 * sizeof(DevState) <= 256, "two state snapshots fit one pinned slot");
+        static_assert(kSlots * sizeof(DevState) <= 512, "the state snapshots fit one pinned slot");
         s->h_snap = static_cast<DevState *>(s->c->borrow_pinned());
         if (!s->h_snap) { set_error("tl_session_run: pinned host allocation failed"); return TL_ERR_NOMEM; }
         for (cudaEvent_t &e : s->ev_snap) TL_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    // Batches of steps are double buffered: batch k+1 is queued before the host waits for the state
-    // snapshot taken after batch k, so the device never idles on a host round trip.  Steps queued
+    // Batches of steps are queued ahead of the host: batches k+1 and k+2 are already enqueued when
+    // the host waits for the state snapshot taken after batch k, so the device does not idle on a
+    // host round trip (or on a host thread that is late by a millisecond or two).  Steps queued
     // past convergence (or past max_moves, which the device checks itself) are no-op launches.
+    // with a move budget every step applies exactly one move (or finds none and stops), so the host
+    // knows how many steps are still worth queueing without looking at the device
+    const bool budgeted = max_moves >= 0 && s->algo != TL_ALGO_TWO_OPT_REF;
+    int64_t budget = budgeted ? max_moves - (int64_t)s->h.moves : 0;
     auto issue = [&](int slot) -> tl_status {
         uint32_t batch = s->algo == TL_ALGO_TWO_OPT_REF ? 64 : 32;
-        if (max_moves >= 0 && s->algo != TL_ALGO_TWO_OPT_REF) // every step applies exactly one move
-            batch = (uint32_t)std::min<int64_t>(256, std::max<int64_t>(1, max_moves - (int64_t)s->h.moves));
+        if (budgeted) {
+            batch = (uint32_t)std::min<int64_t>(256, budget);
+            budget -= batch;
+        }
         tl_status r = enqueue_steps(s, batch);
         if (r != TL_OK) return r;
         TL_CUDA_TRY(cudaMemcpyAsync(s->h_snap + slot, s->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, s->c->stream));
         TL_CUDA_TRY(cudaEventRecord(s->ev_snap[slot], s->c->stream));
         return TL_OK;
     };
-    int slot = 0;
-    rc = issue(0);
-    if (rc != TL_OK) return rc;
+    int head = 0, queued = 0; // `queued` snapshots are outstanding, the oldest one in slot `head`
     for (;;) {
-        rc = issue(1 - slot);
-        if (rc != TL_OK) return rc;
-        TL_CUDA_TRY(cudaEventSynchronize(s->ev_snap[slot]));
-        s->h = s->h_snap[slot];
-        slot = 1 - slot;
+        while (queued < kSlots && (!budgeted || budget > 0)) {
+            rc = issue((head + queued) % kSlots);
+            if (rc != TL_OK) return rc;
+            ++queued;
+        }
+        if (queued == 0) break; // budget spent and every snapshot seen
+        TL_CUDA_TRY(cudaEventSynchronize(s->ev_snap[head]));
+        s->h = s->h_snap[head];
+        head = (head + 1) % kSlots;
+        --queued;
         if (s->h.done) break;
     }
-    TL_CUDA_TRY(cudaEventSynchronize(s->ev_snap[slot])); // the batch that was queued ahead
-    s->h = s->h_snap[slot];
+    while (queued > 0) { // the batches that were queued ahead
+        TL_CUDA_TRY(cudaEventSynchronize(s->ev_snap[head]));
+        s->h = s->h_snap[head];
+        head = (head + 1) % kSlots;
+        --queued;
+    }
     return close_timing(s);
 }
 
