@@ -153,9 +153,10 @@ void build_or_geometry(tl_session *s)
     const int n = (int)s->n;
     const int cw = 32 * kOrR;
     const int ncb = (n + cw - 1) / cw;
-    // ~4 items per resident warp (times the shard count): the scan kernel hands them out dynamically
-    // (6, 8 and 12 are no faster: every item re-stages its columns and restarts the distance pipeline)
-    int per_warp = 4;
+    // ~3 items per resident warp (times the shard count): the scan kernel hands them out dynamically
+    // (2 leaves a long tail; 4, 6, 8 and 12 are slower: every item re-stages its columns and restarts
+    // the distance pipeline -- profiles/r01zx_or_items.txt)
+    int per_warp = 3;
     if (const char *ev = getenv("TL_OR_ITEMS_PER_WARP")) per_warp = std::max(1, atoi(ev));
     const int64_t target = (int64_t)s->c->sm_count * kOrMinBlocks * kOrWarps * s->shard_count * per_warp;
     const int per_cb = (int)std::max<int64_t>(1, target / ncb);
