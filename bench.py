@@ -102,6 +102,30 @@ def describe(workload: str, n: int, seed: int, path: str, dist: str) -> str:
             f"best-improvement 2-opt, one step = full scan of {pairs_per_scan(n)} moves + apply")
 
 
+def bench_config(args, world: int) -> dict:
+    """`config` of the JSON line: a function of the command line only, so that both arms (ours and
+    --impl reference) print the SAME dictionary for the same invocation."""
+    n, seed = WORKLOADS[args.workload]
+    ld = (n + 31) // 32 * 32
+    return {
+        "workload": describe(args.workload, n, seed, args.path, args.dist),
+        "path": args.path, "dist": args.dist,
+        "l2": (f"inputs larger than L2 ({4 * n * ld / 1e6:.0f} MB matrix, {4 * pairs_per_scan(n) / 1e6:.0f} MB read per "
+               "scan, L2 126 MB); no flush") if args.path == "matrix" else
+              "compute-bound path: 16 B per city of tour-ordered points, L2 state irrelevant",
+        "timed_region": f"chunks of {args.steps} steps, each after {args.warmup} untimed warm-up steps, repeated until "
+                        f">= {MIN_TIMED_MS:.0f} ms are timed; ms_per_step is the median chunk / {args.steps}",
+        "parallelism": f"independent instances x{world} (seed + rank), no data-path collective; the partitioned "
+                       "cases (configs 4 and 5) are under `partitioned`",
+    }
+
+
+MIN_TIMED_MS = 50.0   # a 20-step chunk is < 1 ms: repeat it until this much device time has been timed
+# an NN tour converges after ~1500 (10k) / ~170 (1k) moves: start a fresh session before that
+SESSION_CAPS = {"n10k": 1400, "n1k": 150, "n100k": 4000}
+SCAN_REPS = 200  # scan-kernel launches averaged for the roofline, whatever --steps is
+
+
 # ---- clocks sampling ------------------------------------------------------------------------------
 
 class ClockSampler:
@@ -263,10 +287,10 @@ def run_reference(args, rank: int, world: int):
         "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32" if args.dist == "nint" else "f32",
         "data": "synthetic",
-        "config": {"workload": describe(args.workload, n, seed, args.path, args.dist),
-                   "path": args.path, "dist": args.dist,
-                   "note": "CPU oracle port of the reference semantics over the packed lower-triangle "
-                           "matrix (Rust reference not buildable here: no cargo)"},
+        "config": bench_config(args, world),
+        "note": "CPU oracle port of the reference semantics over the packed lower-triangle matrix, "
+                "row-parallel over all host threads (the Rust reference is single-threaded and cannot "
+                "be built here: no cargo)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -303,47 +327,77 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     start = prob.nn_tour(3)  # the reference's `nn,2opt` pipeline
     path = paths[args.path]
 
-    # --- device-resident timing: exactly K timed steps after W warm-up steps.  A session converges
-    #     after ~1500 moves, so K is cut into chunks; every chunk runs on a fresh session of the same
-    #     instance (warm-up again, untimed) and is bracketed by barrier + synchronize on both sides.
-    chunk_cap = max(1, min(args.chunk, args.steps))
+    # --- device-resident timing.  One CHUNK = exactly K timed steps after W untimed warm-up steps,
+    #     bracketed by barrier + synchronize on both sides and timed with CUDA events on the library's
+    #     stream.  A 20-step chunk lasts < 1 ms -- too short for NVML to sample and dominated by clock
+    #     ramp-up -- so the chunk is repeated (same session while the tour has moves left, else a fresh
+    #     one) until >= MIN_TIMED_MS of device time has been timed; the reported step time is the
+    #     MEDIAN chunk (max over ranks per chunk) / K.
+    cap = SESSION_CAPS[args.workload]
     sampler = ClockSampler(local_rank)
-    ms, left, launches, sess, moves_applied = 0.0, args.steps, 0, None, 0
-    while left > 0:
-        k = min(chunk_cap, left)
-        if sess is not None:
-            sess.close()
-        sess = prob.session(T.ALGO_TWO_OPT_BEST, start, path)
-        sess.enqueue(args.warmup)
-        barrier()
-        if rank == 0:
-            sampler.start()
-        l0 = ctx.launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        sess.enqueue(k)
-        e1.record()
-        barrier()
-        if rank == 0:
-            sampler.pause()
-        ms += e0.elapsed_time(e1)
-        launches += ctx.launches - l0
-        real = int(sess.stats().moves)
-        if real < args.warmup + k:
-            raise SystemExit(f"bench invalid: the tour converged after {real} moves, fewer than "
-                             f"warmup+chunk={args.warmup + k}; lower --chunk")
-        moves_applied += k
-        left -= k
+    state = {"sess": None, "used": 0}
+
+    def session_for(steps_needed):
+        if state["sess"] is None or state["used"] + steps_needed > cap:
+            if state["sess"] is not None:
+                state["sess"].close()
+            state["sess"], state["used"] = prob.session(T.ALGO_TWO_OPT_BEST, start, path), 0
+        state["used"] += steps_needed
+        return state["sess"]
+
+    def timed_chunk():
+        """K timed steps (in pieces when K exceeds what one tour can supply); returns (ms, launches)."""
+        ms_c, launches_c, left = 0.0, 0, args.steps
+        while left > 0:
+            k = min(left, max(1, cap - args.warmup))
+            sess = session_for(args.warmup + k)
+            sess.enqueue(args.warmup)
+            barrier()
+            if rank == 0:
+                sampler.start()
+            l0 = ctx.launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sess.enqueue(k)
+            e1.record()
+            barrier()
+            if rank == 0:
+                sampler.pause()
+            ms_c += e0.elapsed_time(e1)
+            launches_c += ctx.launches - l0
+            left -= k
+        return ms_c, launches_c
+
+    def rank_max(values):
+        if dist is None:
+            return list(values)
+        t = torch.tensor(list(values), device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    first_ms, launches = timed_chunk()
+    first_ms = rank_max([first_ms])[0]
+    n_chunks = int(min(400, max(3, np.ceil(MIN_TIMED_MS / max(first_ms, 1e-3)))))
+    chunk_ms = [first_ms]
+    mine = []
+    for _ in range(n_chunks - 1):
+        ms_c, l_c = timed_chunk()
+        mine.append(ms_c)
+        launches += l_c
+    chunk_ms += rank_max(mine)
+    sess = state["sess"]
+    real = int(sess.stats().moves)
+    if real < state["used"]:
+        raise SystemExit(f"bench invalid: the tour converged after {real} moves, fewer than the {state['used']} "
+                         f"steps enqueued on it; lower SESSION_CAPS[{args.workload!r}]")
     clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        tms = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    ms_chunk = float(np.median(chunk_ms))
+    ms = ms_chunk  # device time of K steps
     value = world * args.steps * P / (ms * 1e-3)
+    moves_applied = args.steps * len(chunk_ms)
 
     # --- dominant kernel: average launch duration of the scan kernel (CUDA events, same stream)
-    scan_ms = sess.time_scans(max(10, min(args.steps, 200)))
+    scan_ms = sess.time_scans(SCAN_REPS)
     stats_path = int(sess.stats().path_used)
     sess.close()
 
@@ -354,14 +408,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         s2 = p2.session(T.ALGO_TWO_OPT_BEST, p2.nn_tour(3), paths[p_path])
         s2.enqueue(args.warmup)
         torch.cuda.synchronize()
-        k = min(args.steps, 200)
+        k = 200
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         s2.enqueue(k)
         a1.record()
         torch.cuda.synchronize()
         step_ms2 = a0.elapsed_time(a1) / k
-        scan_ms2 = s2.time_scans(k)
+        scan_ms2 = s2.time_scans(SCAN_REPS)
         s2.close()
         p2.close()
         kern = "two_opt_scan_matrix_kernel" if p_path == "matrix" else "two_opt_scan_recompute_kernel"
@@ -380,28 +434,35 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     e2e_steps = max(1, args.e2e_steps)
     hx = torch.from_numpy(x).pin_memory().numpy()
     hy = torch.from_numpy(y).pin_memory().numpy()
-    htour = torch.from_numpy(start.astype(np.uint32).view(np.int32)).pin_memory().numpy().view(np.uint32)
 
     def e2e_step():
+        """What `teeline solve 2opt` does with a problem file already parsed (2opt auto-expands to the
+        nn,2opt pipeline, src/tsp/mod.rs:129-139): coordinates up, NN start tour (device, read back as the
+        stage's Solution), 2-opt to the local optimum from that seed, tour back."""
         ta = time.perf_counter()
         p2 = T.Problem.euc2d(ctx, hx, hy, kinds[args.dist])
         tb = time.perf_counter()
-        t2, st2, _ = p2.local_search(T.ALGO_TWO_OPT_BEST, htour, path=path, max_moves=args.e2e_moves)
+        seed_tour = p2.nn_tour(3)
+        tn = time.perf_counter()
+        t2, st2, _ = p2.local_search(T.ALGO_TWO_OPT_BEST, seed_tour, path=path, max_moves=args.e2e_moves)
         tc = time.perf_counter()
         p2.close()
         if os.environ.get("TL_DEBUG_TIMING"):
-            print(f"[bench] e2e call: create {1e3 * (tb - ta):.2f} ms, local_search {1e3 * (tc - tb):.2f} ms, "
-                  f"close {1e3 * (time.perf_counter() - tc):.2f} ms", file=sys.stderr)
-        return int(st2.evals), int(st2.moves), t2
+            print(f"[bench] e2e call: create {1e3 * (tb - ta):.2f} ms, nn_tour {1e3 * (tn - tb):.2f} ms, "
+                  f"local_search {1e3 * (tc - tn):.2f} ms, close {1e3 * (time.perf_counter() - tc):.2f} ms",
+                  file=sys.stderr)
+        return int(st2.evals), int(st2.moves), t2, tn - tb
 
     e2e_step()
     barrier()
     t0 = time.perf_counter()
     evals = e2e_applied = 0
+    nn_s = 0.0
     for _ in range(e2e_steps):
-        ev, mv, _t = e2e_step()
+        ev, mv, _t, nn_dt = e2e_step()
         evals += ev
         e2e_applied += mv
+        nn_s += nn_dt
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if dist is not None:
@@ -409,8 +470,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
         dt = float(tdt.item())
     e2e_value = world * evals / dt
-    h2d = 2 * 4 * n + 4 * n  # x, y, start tour
-    d2h = 4 * n + 64         # tour + stats
+    h2d = 2 * 4 * n + 4 * n  # x, y; the NN tour goes back up as the 2-opt stage's seed
+    d2h = 4 * n + 4 * n + 64  # NN tour, final tour, stats
 
     if rank != 0:
         if dist is not None:
@@ -459,6 +520,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     else:
         roofline = fp32_roofline(scan_ms)
     roofline["kernel_share_of_step"] = scan_ms / (ms / args.steps)
+    roofline["kernel_reps_timed"] = SCAN_REPS
 
     # --- CPU baseline: the oracle port on the host cores (bounded sample)
     threads = os.cpu_count() or 1
@@ -476,21 +538,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "timed_chunks": len(chunk_ms), "timed_ms_total": float(sum(chunk_ms)),
+        "chunk_ms": {"median": ms_chunk, "min": float(min(chunk_ms)), "max": float(max(chunk_ms)),
+                     "first": float(chunk_ms[0])},
         "vs_baseline": None, "dtype": "int32" if args.dist == "nint" else "f32", "data": "synthetic",
-        "config": {"workload": describe(args.workload, n, seed0, args.path, args.dist),
-                   "path": "matrix" if stats_path == T.PATH_MATRIX else "recompute", "dist": args.dist,
-                   "l2": f"inputs larger than L2 ({4 * n * ((n + 31) // 32 * 32) / 1e6:.0f} MB matrix, "
-                         f"{4 * P / 1e6:.0f} MB read per scan, L2 126 MB); no flush" if stats_path == T.PATH_MATRIX else
-                         "compute-bound kernel: 160 KB of tour-ordered points, L2 state irrelevant",
-                   "timed_region": f"{args.steps} steps in chunks of <= {chunk_cap}; each chunk on a fresh session "
-                                   f"after {args.warmup} untimed warm-up steps, CUDA events, max over ranks",
-                   "parallelism": f"independent instances x{world} (seed + rank), no data-path collective"},
+        "config": bench_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "step": "tl_problem_create_euc2d + tl_local_search(" +
+                "step": "tl_problem_create_euc2d + tl_nn_tour + tl_local_search(" +
                         ("to the 2-opt local optimum" if args.e2e_moves < 0 else f"max_moves={args.e2e_moves}") +
                         f") + tour read-back, {e2e_steps} calls, pinned host buffers",
                 "seconds": dt, "wall_ms_per_call": 1e3 * dt / e2e_steps,
-                "moves_applied_per_call": e2e_applied / e2e_steps},
+                "moves_applied_per_call": e2e_applied / e2e_steps,
+                "nn_tour_ms_per_call": 1e3 * nn_s / e2e_steps,
+                "metric_note": "moves evaluated by the 2-opt stage / wall time of the WHOLE call (NN start tour "
+                               "construction and all copies included)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -512,7 +573,6 @@ def main():
     ap.add_argument("--workload", default="n10k", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="matrix", choices=["recompute", "matrix"])
     ap.add_argument("--dist", default="nint", choices=["nint", "f32"])
-    ap.add_argument("--chunk", type=int, default=1000, help="timed steps per session (a tour converges)")
     ap.add_argument("--e2e-moves", type=int, default=-1, help="-1: to the local optimum")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-budget", type=float, default=10.0)
@@ -522,7 +582,7 @@ def main():
     if args.path == "recompute" and args.dist == "nint":
         args.dist = "f32"  # the recompute kernels evaluate the f32 metric
     if args.workload == "n100k":
-        args.path, args.dist, args.chunk = "recompute", "f32", min(args.chunk, 50)
+        args.path, args.dist = "recompute", "f32"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

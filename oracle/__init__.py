@@ -198,10 +198,13 @@ def two_opt_best(p: Problem, tour, cyclic: bool = False, max_moves: int = -1, nt
     return t, st, _moves(log, st, log_cap)
 
 
-def or_opt_find_best(p: Problem, tour):
+def or_opt_find_best(p: Problem, tour, nthreads: int = 1):
     t = _tour(tour)
     mv = Move()
-    found = lib().tlo_or_opt_find_best(p.ref, _p(t), C.byref(mv))
+    if nthreads > 1:
+        found = lib().tlo_or_opt_find_best_mt(p.ref, _p(t), C.c_int(nthreads), C.byref(mv), None)
+    else:
+        found = lib().tlo_or_opt_find_best(p.ref, _p(t), C.byref(mv))
     return mv.astuple() if found else None
 
 

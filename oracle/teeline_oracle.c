@@ -254,6 +254,80 @@ int tlo_or_opt_find_best(const tlo_problem *p, const int32_t *tour, tlo_move *mv
     return IS_INT(p) ? or_opt_find_best_i(p, tour, mv, NULL) : or_opt_find_best_f(p, tour, mv, NULL);
 }
 
+/* Threaded find_best_move (test/bench convenience; same result): jobs are (seg_len, block of
+ * segment starts) in scan order; each starts from the -1e-3 threshold and keeps its own
+ * first-found minimum; merging in job order with strict '<' reproduces the sequential
+ * first-found-wins rule (or_opt.rs:141-160). */
+typedef struct {
+    const tlo_problem *p;
+    const int32_t *tour;
+    int32_t seg, i0, i1;
+    int found;
+    int64_t evals;
+    tlo_move mv;
+} or_job;
+
+typedef struct {
+    or_job *jobs;
+    int njobs;
+    int next; /* guarded by mu */
+    pthread_mutex_t mu;
+} or_queue;
+
+static void *or_worker(void *arg)
+{
+    or_queue *q = (or_queue *)arg;
+    for (;;) {
+        pthread_mutex_lock(&q->mu);
+        const int k = q->next++;
+        pthread_mutex_unlock(&q->mu);
+        if (k >= q->njobs) return NULL;
+        or_job *jb = &q->jobs[k];
+        jb->found = IS_INT(jb->p)
+                        ? or_opt_scan_job_i(jb->p, jb->tour, jb->seg, jb->i0, jb->i1, &jb->mv, &jb->evals)
+                        : or_opt_scan_job_f(jb->p, jb->tour, jb->seg, jb->i0, jb->i1, &jb->mv, &jb->evals);
+    }
+}
+
+int tlo_or_opt_find_best_mt(const tlo_problem *p, const int32_t *tour, int nthreads, tlo_move *mv,
+                            int64_t *evals)
+{
+    const int32_t n = p->n;
+    if (evals) *evals = 0;
+    if (n < 4) return 0;
+    if (nthreads > 256) nthreads = 256;
+    if (nthreads <= 1 || n < 64 * nthreads) {
+        return IS_INT(p) ? or_opt_find_best_i(p, tour, mv, evals) : or_opt_find_best_f(p, tour, mv, evals);
+    }
+    const int per_seg = 4 * nthreads; /* small jobs + a shared queue even out the load */
+    const int njobs = 3 * per_seg;
+    or_job *jobs = (or_job *)calloc((size_t)njobs, sizeof(or_job));
+    for (int s = 0; s < 3; ++s)
+        for (int b = 0; b < per_seg; ++b) {
+            or_job *jb = &jobs[s * per_seg + b];
+            jb->p = p; jb->tour = tour; jb->seg = s + 1;
+            jb->i0 = (int32_t)((int64_t)n * b / per_seg);
+            jb->i1 = (int32_t)((int64_t)n * (b + 1) / per_seg);
+        }
+    or_queue q;
+    q.jobs = jobs; q.njobs = njobs; q.next = 0;
+    pthread_mutex_init(&q.mu, NULL);
+    pthread_t th[256];
+    for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, or_worker, &q);
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    pthread_mutex_destroy(&q.mu);
+    int found = 0;
+    for (int k = 0; k < njobs; ++k) {
+        if (evals) *evals += jobs[k].evals;
+        if (jobs[k].found && (!found || jobs[k].mv.delta < mv->delta)) {
+            *mv = jobs[k].mv;
+            found = 1;
+        }
+    }
+    free(jobs);
+    return found;
+}
+
 /* apply_relocation, src/tsp/or_opt.rs:172-184 (drain + splice on a Vec) */
 void tlo_or_opt_apply(int32_t *tour, int32_t n, int32_t i, int32_t seg_len, int32_t j,
                       int32_t reversed)

@@ -100,6 +100,10 @@ void tlo_two_opt_best(const tlo_problem *p, int32_t *tour, int cyclic, int64_t m
 
 /* ---- Or-opt (or_opt.rs:80-184) --------------------------------------------- */
 int tlo_or_opt_find_best(const tlo_problem *p, const int32_t *tour, tlo_move *mv);
+/* Same scan split over pthreads (identical result: per-job first-found minima merged in scan
+ * order with strict '<'); *evals (nullable) = candidates evaluated. */
+int tlo_or_opt_find_best_mt(const tlo_problem *p, const int32_t *tour, int nthreads, tlo_move *mv,
+                            int64_t *evals);
 void tlo_or_opt_apply(int32_t *tour, int32_t n, int32_t i, int32_t seg_len, int32_t j,
                       int32_t reversed);
 void tlo_or_opt(const tlo_problem *p, int32_t *tour, int64_t max_moves, tlo_stats *st,

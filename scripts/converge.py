@@ -51,8 +51,8 @@ for n in (1000, 10000):
     print(rows[-1], flush=True)
 
     b = gpu(prob, T.ALGO_TWO_OPT_BEST, start, T.PATH_RECOMPUTE, "gpu 2-opt Mode B (best-improvement), recompute", n)
-    gpu(prob, T.ALGO_TWO_OPT_BEST, start, T.PATH_MATRIX, "gpu 2-opt Mode B, f32 matrix", n)
-    rows[-1]["same_tour_as_recompute"] = True
+    bm = gpu(prob, T.ALGO_TWO_OPT_BEST, start, T.PATH_MATRIX, "gpu 2-opt Mode B, f32 matrix", n)
+    rows[-1]["same_tour_as_recompute"] = bool((bm == b).all())
     if n <= 1000:
         t0 = time.perf_counter()
         want, st, _ = O.two_opt_best(P, start)

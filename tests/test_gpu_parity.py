@@ -791,3 +791,141 @@ def test_three_opt_scan_only_600(T, ctx):
     want, _ = O.three_opt_find_best(P, t, nthreads=8)
     assert got is not None and got[1:] == want[1:] and np.float32(got[0]) == np.float32(want[0])
     s.close()
+
+
+# ---- BASELINE-size parity (configs 3, 4, 5 at their full sizes) ------------------------------------------
+#
+# The oracle cannot run these searches to the end in test time (config 3 Mode B is ~10^11 evaluations),
+# so the checks are: single scans compared outright, and for whole searches the logged move sequence is
+# replayed on the host and every k-th logged move is RE-DERIVED by an oracle scan of the tour state
+# before it; the final tour must be an oracle-verified local optimum.
+
+NCPU = os.cpu_count() or 8
+
+
+def replay_two_opt(start, moves, upto):
+    """Tour state after the first `upto` logged 2-opt moves (swap_2opt, two_opt.rs:69-79)."""
+    t = np.asarray(start, dtype=np.int32).copy()
+    for (_, i, j, _, _) in moves[:upto]:
+        t[i + 1:j + 1] = t[i + 1:j + 1][::-1].copy()
+    return t
+
+
+def test_config3_full_10k_nint_matrix_solve_against_oracle(T, ctx):
+    """BASELINE configs[2], the headline workload: n = 10 000 on the 10^6 grid, TSPLIB nint int32 matrix
+    in HBM, NN start, Mode B to the local optimum (1508 moves, >= 5 re-lays of the matrix).  Every 50th
+    logged move is re-derived by an oracle scan; the final tour is an oracle-verified local optimum;
+    the integer tour length drops by exactly the sum of the logged deltas."""
+    n = 10000
+    gx, gy = O.gen_grid(n, n)
+    Pi = O.Problem(tri=O.matrix_packed_nint(gx, gy), n=n)
+    start = O.nn_tour(Pi, 3)
+    prob = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32)
+    assert (prob.nn_tour(3).astype(np.int64) == start).all()
+    got_t, st, mv = prob.local_search(T.ALGO_TWO_OPT_BEST, start, path=T.PATH_MATRIX, log_cap=1 << 12)
+    assert st.path_used == T.PATH_MATRIX and st.converged == 1
+    assert int(st.moves) == 1508 == len(mv) and int(st.passes) == 1509
+    assert int(st.evals) == 1509 * ((n - 3) * (n - 2) // 2)
+    assert int(st.repermutes) >= 5
+    # the replayed log is the returned tour
+    assert (replay_two_opt(start, mv, len(mv)) == got_t.astype(np.int64)).all()
+    assert sorted(got_t.tolist()) == list(range(n))
+    # sampled re-derivation: state before move k -> the oracle's best move must be move k
+    for k in list(range(0, len(mv), 50)) + [len(mv) - 1]:
+        want = O.two_opt_best_scan(Pi, replay_two_opt(start, mv, k), nthreads=NCPU)
+        assert want is not None and (want[1], want[2]) == (mv[k][1], mv[k][2]) and want[0] == mv[k][0], k
+    # local optimum: one more oracle scan finds nothing
+    assert O.two_opt_best_scan(Pi, got_t, nthreads=NCPU) is None
+    # exact integer bookkeeping
+    assert int(O.tour_length(Pi, got_t)) == int(O.tour_length(Pi, start)) + int(sum(m[0] for m in mv))
+    assert int(prob.tour_lengths(got_t)[0]) == int(O.tour_length(Pi, got_t))
+
+
+def test_config3_or_opt_on_the_10k_nint_matrix(T, ctx):
+    """Second half of configs[2]: Or-opt on the int32 matrix at n = 10 000 -- scan-level equality from
+    two different tours and the first 20 applied moves, each re-derived by the (threaded) oracle scan."""
+    n = 10000
+    gx, gy = O.gen_grid(n, n)
+    Pi = O.Problem(tri=O.matrix_packed_nint(gx, gy), n=n)
+    prob = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32)
+    shuffled = O.shuffle_tour(n, 3)
+    s = prob.session(T.ALGO_OR_OPT, shuffled, T.PATH_AUTO)
+    got, want = s.scan(), O.or_opt_find_best(Pi, shuffled, nthreads=NCPU)
+    assert int(s.stats().path_used) == T.PATH_MATRIX
+    assert got is not None and got[1:] == want[1:] and got[0] == want[0]
+    s.close()
+    start = O.nn_tour(Pi, 3)
+    got_t, st, mv = prob.local_search(T.ALGO_OR_OPT, start, path=T.PATH_AUTO, max_moves=20, log_cap=64)
+    assert int(st.moves) == 20 == len(mv)
+    t = start.copy()
+    for k, m in enumerate(mv):
+        want = O.or_opt_find_best(Pi, t, nthreads=NCPU)
+        assert want is not None and want[1:] == m[1:] and want[0] == m[0], k
+        t = O.or_opt_apply(t, m[1], m[3], m[2], m[4])
+    assert (t == got_t.astype(np.int64)).all()
+
+
+def test_config3_matrix_tour_equals_recompute_tour_f32(T, ctx):
+    """The f32 matrix path and the coordinate-recompute path are bit-identical metrics: the complete
+    10k searches must produce the same move log and the same tour (what scripts/converge.py reports)."""
+    n = 10000
+    x, y = O.gen_uniform(n, n)
+    prob = T.Problem.euc2d(ctx, x, y)
+    start = prob.nn_tour(3)
+    ta, sa, ma = prob.local_search(T.ALGO_TWO_OPT_BEST, start, path=T.PATH_RECOMPUTE, log_cap=1 << 12)
+    tb, sb, mb = prob.local_search(T.ALGO_TWO_OPT_BEST, start, path=T.PATH_MATRIX, log_cap=1 << 12)
+    assert (ta == tb).all() and ma == mb and int(sa.moves) == int(sb.moves) > 1000
+    P = O.Problem(x, y)
+    for k in (0, len(ma) // 2, len(ma) - 1):
+        want = O.two_opt_best_scan(P, replay_two_opt(start, ma, k), nthreads=NCPU)
+        assert (want[1], want[2]) == (ma[k][1], ma[k][2]) and np.float32(want[0]) == np.float32(ma[k][0])
+    assert O.two_opt_best_scan(P, ta, nthreads=NCPU) is None
+
+
+@pytest.mark.parametrize("start_kind", ["nn", "shuffled"])
+def test_config4_100k_scan_and_move_log_against_oracle(T, ctx, start_kind):
+    """BASELINE configs[3]: n = 100 000, coordinate recompute.  P(100k) = 4 999 750 003 > 2^32, so pair
+    counters and work-item arithmetic are exercised beyond 32 bits.  One full scan against the threaded
+    oracle scan, then a 20-move search whose every 5th logged move is re-derived by the oracle."""
+    n = 100000
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    prob = T.Problem.euc2d(ctx, x, y)
+    start = prob.nn_tour(3).astype(np.int32) if start_kind == "nn" else O.shuffle_tour(n, 4)
+    s = prob.session(T.ALGO_TWO_OPT_BEST, start, T.PATH_RECOMPUTE)
+    got = s.scan()
+    want = O.two_opt_best_scan(P, start, nthreads=NCPU)
+    assert got is not None and (got[1], got[2]) == (want[1], want[2]) and np.float32(got[0]) == np.float32(want[0])
+    s.run(20)
+    st, mv, final = s.stats(), s.log(64), s.tour()
+    s.close()
+    assert int(st.moves) == 20 == len(mv) and int(st.evals) == int(st.passes) * ((n - 3) * (n - 2) // 2)
+    assert (mv[0][1], mv[0][2]) == (want[1], want[2])
+    for k in (5, 10, 15, 19):
+        w = O.two_opt_best_scan(P, replay_two_opt(start, mv, k), nthreads=NCPU)
+        assert (w[1], w[2]) == (mv[k][1], mv[k][2]) and np.float32(w[0]) == np.float32(mv[k][0]), k
+    assert (replay_two_opt(start, mv, 20) == final.astype(np.int64)).all()
+
+
+def test_config5_full_population_to_local_optimum(T, ctx):
+    """BASELINE configs[4]: 1024 start tours (tour 0 = NN, 1..1023 = splitmix64 shuffles) on the 1k
+    instance, every tour to its 2-opt local optimum in one launch.  Sampled tours equal the oracle's
+    complete searches; every result is a permutation, a local optimum length-wise (no tour longer than
+    its start) and carries its exact-order length."""
+    n, B = 1000, 1024
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    p = T.Problem.euc2d(ctx, x, y)
+    tours = np.stack([O.nn_tour(P, 3)] + [O.shuffle_tour(n, s) for s in range(1, B)])
+    before = p.tour_lengths(tours)
+    got, st, lengths = p.two_opt_batch(tours, T.ALGO_TWO_OPT_BEST)
+    assert st.converged == 1 and int(st.launches) == 2
+    assert (np.sort(got, axis=1) == np.arange(n, dtype=np.uint32)[None, :]).all()
+    assert (lengths <= before).all() and (bits(lengths) == bits(p.tour_lengths(got))).all()
+    moves = 0
+    for b in (0, 1, 511, 1023):
+        want_t, want_st, _ = O.two_opt_best(P, tours[b], nthreads=NCPU)
+        assert (got[b].astype(np.int64) == want_t).all(), b
+        moves += want_st.moves
+    assert f5(lengths[0]) == "25282.04297"  # tour 0 is the survey probe's NN -> Mode B result
+    assert int(st.moves) > moves and int(st.passes) == int(st.moves) + B
