@@ -85,6 +85,25 @@ def shuffle_tour(n: int, seed: int) -> np.ndarray:
     return t
 
 
+def shuffle_tours(n: int, seeds) -> np.ndarray:
+    """shuffle_tour for many seeds at once (vectorised over the tours; same permutations)."""
+    seeds = np.asarray(list(seeds), dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n, dtype=np.uint64)
+        z = seeds[:, None] + idx[None, :] * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        r = z ^ (z >> np.uint64(31))
+    t = np.tile(np.arange(n, dtype=np.uint32), (len(seeds), 1))
+    rows = np.arange(len(seeds))
+    for k, i in enumerate(range(n - 1, 0, -1)):
+        j = (r[:, k] % np.uint64(i + 1)).astype(np.int64)
+        ti = t[rows, i].copy()
+        t[rows, i] = t[rows, j]
+        t[rows, j] = ti
+    return t
+
+
 def pairs_per_scan(n: int) -> int:
     return (n - 3) * (n - 2) // 2
 
@@ -299,6 +318,134 @@ def run_reference(args, rank: int, world: int):
 
 # ---- product arm -------------------------------------------------------------------------------------
 
+def run_partitioned(args, T, ctx, torch, dist, rank: int, world: int, hbm_peak: float) -> dict:
+    """The two cases of BASELINE.json that split ONE job over the GPUs.
+
+    config 4: n = 100 000, coordinate recompute, the (i,j) triangle sharded over the ranks; every step
+              the per-rank minima are exchanged inside the scan kernel over NVLink peer memory
+              (csrc/shard_exchange.cuh) and every rank applies the same move to its replica.
+    config 5: 1024 start tours on the 1k instance, tours sharded by index, no data-path collective.
+    Every figure is measured in this run: the unsharded single-GPU baseline first (same process, same
+    instance), then the sharded run; times are CUDA-event / wall times, max over ranks."""
+    from teeline_b200 import multi
+
+    def rmax(v):
+        if dist is None:
+            return float(v)
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def rmin_flag(ok):
+        if dist is None:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {"n_gpus": world}
+    if world > 1:
+        multi.attach_nccl(ctx, dist)
+
+    # ---- config 4 ------------------------------------------------------------------------------------
+    n, seed = WORKLOADS["n100k"]
+    P4 = pairs_per_scan(n)
+    x, y = gen_uniform(n, seed)
+    prob = T.Problem.euc2d(ctx, x, y)
+    start = prob.nn_tour(3)
+    W4, K4 = 5, max(50, min(args.partitioned_steps, 400))
+
+    def timed_steps(sess):
+        sess.enqueue(W4)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sess.enqueue(K4)
+        e1.record()
+        sync()
+        return rmax(e0.elapsed_time(e1)) / K4
+
+    base = prob.session(T.ALGO_TWO_OPT_BEST, start, T.PATH_RECOMPUTE)
+    base_step = timed_steps(base)
+    base_log, base_tour = base.log(W4 + K4), base.tour()
+    base_scan = rmax(base.time_scans(20))
+    base.close()
+    ffma, _ = ctx.microbench_fp32()
+    c4 = {"workload": f"n={n} uniform f32 (seed {seed}), coordinate recompute, NN start, Mode B, {K4} timed steps "
+                      f"after {W4} warm-up", "pairs_per_scan": P4,
+          "single_gpu": {"step_ms": base_step, "scan_ms": base_scan, "moves_per_s": P4 / (base_step * 1e-3),
+                         "roofline_frac_fp32_issue": 15.0 * P4 / (base_scan * 1e-3) / ffma}}
+    if world > 1:
+        sh = prob.session(T.ALGO_TWO_OPT_BEST, start, T.PATH_RECOMPUTE)
+        sh.set_shard(rank, world)
+        first = sh.scan()  # (all-gather + host reduction path) the global best move from the start tour
+        step = timed_steps(sh)
+        log, tour = sh.log(W4 + K4), sh.tour()
+        scan = rmax(sh.time_scans(20))
+        sh.close()
+        same = log == base_log and bool((tour == base_tour).all()) and first is not None and \
+            first[1:3] == base_log[0][1:3]
+        c4["sharded"] = {
+            "step_ms": step, "scan_ms_slowest_rank": scan, "exchange_plus_apply_ms": step - scan,
+            "moves_per_s": P4 / (step * 1e-3), "speedup_vs_single_gpu_step": base_step / step,
+            "scan_speedup": base_scan / scan,
+            "roofline_frac_fp32_issue_aggregate": 15.0 * P4 / (scan * 1e-3) / (ffma * world),
+            "identical_to_unsharded": rmin_flag(same),
+            "transport": os.environ.get("TL_SHARD_TRANSPORT", "peer mailboxes over NVLink inside the scan kernel "
+                                                                 "(ncclAllGather only if peers cannot be mapped)")}
+    if rank == 0 and args.partitioned_oracle_check:
+        # one oracle-checked scan (the checker, outside every timed region): the first logged move of
+        # the (sharded) search must be the CPU oracle's best move from the same start tour
+        import oracle as O
+        t0 = time.perf_counter()
+        want = O.two_opt_best_scan(O.Problem(x, y), start, nthreads=os.cpu_count() or 1)
+        got = base_log[0]
+        c4["oracle_checked_first_move"] = {
+            "ok": bool(want is not None and (want[1], want[2]) == (got[1], got[2]) and
+                       np.float32(want[0]) == np.float32(got[0])),
+            "oracle_scan_s": time.perf_counter() - t0, "move": [float(got[0]), int(got[1]), int(got[2])]}
+    prob.close()
+    out["config4_100k_sharded_triangle"] = c4
+
+    # ---- config 5 ------------------------------------------------------------------------------------
+    n, seed = WORKLOADS["n1k"]
+    B = 1024
+    x, y = gen_uniform(n, seed)
+    prob = T.Problem.euc2d(ctx, x, y)
+    tours = np.concatenate([prob.nn_tour(3)[None, :], shuffle_tours(n, range(1, B))])
+    prob.two_opt_batch(tours[:8], max_moves=2)  # warm
+    sync()
+    t0 = time.perf_counter()
+    got, st, lengths = prob.two_opt_batch(tours)
+    torch.cuda.synchronize()
+    single_wall = rmax(time.perf_counter() - t0)
+    evals = int(st.evals)
+    c5 = {"workload": f"{B} start tours (NN + {B - 1} splitmix64 shuffles) on the n={n} instance, every tour to its "
+                      "2-opt local optimum, host buffers in and out",
+          "evals": evals, "moves_applied": int(st.moves),
+          "single_gpu": {"wall_s": single_wall, "device_ms": float(st.device_ms), "moves_per_s": evals / single_wall,
+                         "best_length": float(lengths.min())}}
+    if world > 1:
+        sync()
+        t0 = time.perf_counter()
+        (lo, hi), mine, all_len, best, best_tour = multi.sharded_population(
+            tours, lambda t: prob.two_opt_batch(t)[::2], dist)
+        torch.cuda.synchronize()
+        wall = rmax(time.perf_counter() - t0)
+        same = bool((np.float32(all_len) == lengths).all()) and best == int(np.argmin(lengths)) and \
+            bool((best_tour == got[best]).all()) and bool((mine == got[lo:hi]).all())
+        c5["sharded"] = {"wall_s": wall, "moves_per_s": evals / wall, "speedup_vs_single_gpu": single_wall / wall,
+                         "identical_lengths_and_best_tour": rmin_flag(same), "tours_per_gpu": B // world}
+    prob.close()
+    out["config5_1024_tours"] = c5
+    return out
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import teeline_b200 as T
@@ -429,6 +576,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             if (p_path, p_dist) != (args.path, args.dist):
                 other_paths[label] = probe(label, p_path, p_dist)
 
+    # --- the partitioned cases (configs 4 and 5): sharded across the ranks, measured against this
+    #     run's own single-GPU baseline
+    partitioned = None
+    if not args.no_partitioned:
+        peaks0 = {}
+        try:
+            peaks0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        partitioned = run_partitioned(args, T, ctx, torch, dist, rank, world, float(peaks0.get("hbm_gbs", 6650.0)))
+
     # --- end to end through the C ABI with host buffers (pinned), copies inside the timed region:
     #     coordinates up, the whole local search to the 2-opt optimum, tour back
     e2e_steps = max(1, args.e2e_steps)
@@ -558,6 +716,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "cpu_baseline": cpu_baseline,
         "other_paths": other_paths,
         "moves_applied": moves_applied,
+        "partitioned": partitioned,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -573,6 +732,10 @@ def main():
     ap.add_argument("--workload", default="n10k", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="matrix", choices=["recompute", "matrix"])
     ap.add_argument("--dist", default="nint", choices=["nint", "f32"])
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the configs 4/5 block")
+    ap.add_argument("--partitioned-steps", type=int, default=60, help="timed steps of the 100k sharded case")
+    ap.add_argument("--partitioned-oracle-check", type=int, default=1,
+                    help="rank 0 checks the first 100k move against one CPU oracle scan (5-15 s)")
     ap.add_argument("--e2e-moves", type=int, default=-1, help="-1: to the local optimum")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-budget", type=float, default=10.0)

@@ -114,8 +114,12 @@ const char *tl_version(void);
 uint64_t tl_ctx_launch_count(const tl_ctx *ctx);
 
 /* Multi-GPU (one process per GPU).  Rank 0 makes the id, the host runtime
- * (torch.distributed) broadcasts it, every rank attaches.  Used by the sharded
- * Mode B scan: per-rank best records are exchanged with one ncclAllGather. */
+ * (torch.distributed) broadcasts it, every rank attaches (collective call).  Attaching
+ * also maps every rank's 1 KB "mailbox" into every other process (cudaIpc over NVLink):
+ * a sharded Mode B step then exchanges the per-rank best records INSIDE the scan kernel
+ * (peer stores + polling by the last CTA, csrc/shard_exchange.cuh) and applies the move in
+ * the same launch.  If peers cannot be mapped (or TL_SHARD_TRANSPORT=nccl) the step is
+ * scan -> ncclAllGather -> apply kernel instead; results are identical. */
 #define TL_NCCL_ID_BYTES 128
 tl_status tl_nccl_unique_id(uint8_t id_out[TL_NCCL_ID_BYTES]);
 tl_status tl_ctx_attach_nccl(tl_ctx *ctx, const uint8_t id[TL_NCCL_ID_BYTES], int32_t rank,
@@ -173,13 +177,16 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
 tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uint32_t *tour,
                             tl_session **out);
 void tl_session_destroy(tl_session *s);
-/* Shard the move space: this session scans shard `index` of `count` and, when the
- * context has NCCL attached, exchanges per-rank bests after every scan. */
+/* Shard the move space: this session scans shard `index` of `count` and exchanges per-rank
+ * bests with the other ranks after every scan (see tl_ctx_attach_nccl).  Every rank must
+ * call it with its own rank and the world size, create/step its sharded sessions in the same
+ * order, and step ONE sharded session at a time per context. */
 tl_status tl_session_set_shard(tl_session *s, int32_t index, int32_t count);
 /* One full scan without applying: the best move (found=0 when none improves). */
 tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found);
-/* Launch the scan kernel `reps` times back to back (no apply) between two CUDA events on
- * the context's stream and return the average launch duration: the roofline numerator. */
+/* Launch the scan kernel `reps` times back to back (no apply, no cross-rank exchange) between
+ * two CUDA events on the context's stream and return the average launch duration: the roofline
+ * numerator.  A sharded session times its own share of the move space. */
 tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms);
 /* Enqueue `steps` scan+apply iterations; does not synchronise. */
 tl_status tl_session_enqueue(tl_session *s, uint32_t steps);

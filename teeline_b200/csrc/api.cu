@@ -46,6 +46,21 @@ static bool coords_allow_fast_sqrt(const float *x, const float *y, uint32_t n)
     return true;
 }
 
+// dist_nint_grid (common.cuh): every coordinate an integer, |c| <= 2^22, axis ranges <= 2^20
+static bool coords_allow_grid_nint(const float *x, const float *y, uint32_t n)
+{
+    float lo[2] = {x[0], y[0]}, hi[2] = {x[0], y[0]};
+    for (uint32_t i = 0; i < n; ++i) {
+        const float c[2] = {x[i], y[i]};
+        for (int a = 0; a < 2; ++a) {
+            if (!std::isfinite(c[a]) || c[a] != std::floor(c[a]) || std::fabs(c[a]) > 4194304.0f) return false;
+            lo[a] = std::min(lo[a], c[a]);
+            hi[a] = std::max(hi[a], c[a]);
+        }
+    }
+    return hi[0] - lo[0] <= 1048576.0f && hi[1] - lo[1] <= 1048576.0f;
+}
+
 } // namespace tl
 
 using namespace tl;
@@ -95,16 +110,24 @@ static tl_status ctx_create_impl(int32_t device, void *stream, bool own, tl_ctx 
         c->stream = reinterpret_cast<cudaStream_t>(stream);
     }
     {
-        // keep freed blocks in the stream-ordered pool (host.hpp: g_alloc_stream)
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        // the library's own stream-ordered pool; freed blocks stay cached (host.hpp: dev_alloc)
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&c->pool, &props) == cudaSuccess) {
             uint64_t keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            c->pool = nullptr; // fall back to the device's default pool, untouched
+            cudaGetLastError();
         }
     }
     cudaError_t ce = configure_all_kernels();
     if (ce != cudaSuccess) {
         set_error("kernel attribute setup failed: %s", cudaGetErrorString(ce));
+        if (c->pool) cudaMemPoolDestroy(c->pool);
         if (c->own_stream) cudaStreamDestroy(c->stream);
         delete c;
         return TL_ERR_CUDA;
@@ -113,18 +136,26 @@ static tl_status ctx_create_impl(int32_t device, void *stream, bool own, tl_ctx 
     return TL_OK;
 }
 
-tl_status tl_ctx_create(int32_t device, tl_ctx **out) { return ctx_create_impl(device, nullptr, true, out); }
+tl_status tl_ctx_create(int32_t device, tl_ctx **out)
+{
+    return tl::guarded([&]() -> tl_status { return ctx_create_impl(device, nullptr, true, out); });
+}
 
 tl_status tl_ctx_create_on_stream(int32_t device, void *cuda_stream, tl_ctx **out)
 {
+    return tl::guarded([&]() -> tl_status {
     return ctx_create_impl(device, cuda_stream, false, out);
+    });
 }
 
 void tl_ctx_destroy(tl_ctx *ctx)
 {
     if (!ctx) return;
     DeviceGuard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    release_peer_mailboxes(ctx);
     if (ctx->nccl_comm) nccl_comm_destroy(ctx->nccl_comm);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     for (void *chunk : ctx->pin_chunks) cudaFreeHost(chunk);
     delete ctx;
@@ -132,22 +163,27 @@ void tl_ctx_destroy(tl_ctx *ctx)
 
 tl_status tl_ctx_sync(tl_ctx *ctx)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!ctx) { set_error("tl_ctx_sync: null ctx"); return TL_ERR_INVALID; }
     DeviceGuard g(ctx);
     TL_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return TL_OK;
+    });
 }
 
 uint64_t tl_ctx_launch_count(const tl_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 tl_status tl_nccl_unique_id(uint8_t id_out[TL_NCCL_ID_BYTES])
 {
+    return tl::guarded([&]() -> tl_status {
     if (!id_out) { set_error("tl_nccl_unique_id: null"); return TL_ERR_INVALID; }
     return nccl_get_unique_id(id_out);
+    });
 }
 
 tl_status tl_ctx_attach_nccl(tl_ctx *ctx, const uint8_t id[TL_NCCL_ID_BYTES], int32_t rank, int32_t world)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!ctx || !id || world < 1 || rank < 0 || rank >= world) {
         set_error("tl_ctx_attach_nccl: bad arguments");
         return TL_ERR_INVALID;
@@ -158,7 +194,9 @@ tl_status tl_ctx_attach_nccl(tl_ctx *ctx, const uint8_t id[TL_NCCL_ID_BYTES], in
     if (s != TL_OK) return s;
     ctx->rank = rank;
     ctx->world = world;
-    return TL_OK;
+    ctx->shard_epoch = 0;
+    return setup_peer_mailboxes(ctx); // collective; falls back to the all-gather path if peers cannot be mapped
+    });
 }
 
 // ---- problem ---------------------------------------------------------------------
@@ -166,6 +204,7 @@ tl_status tl_ctx_attach_nccl(tl_ctx *ctx, const uint8_t id[TL_NCCL_ID_BYTES], in
 tl_status tl_problem_create_euc2d(tl_ctx *ctx, uint32_t n, const float *x, const float *y,
                                   int32_t dist_kind, tl_problem **out)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!ctx || !x || !y || !out) { set_error("tl_problem_create_euc2d: null argument"); return TL_ERR_INVALID; }
     *out = nullptr;
     if (n < 2) {
@@ -177,12 +216,31 @@ tl_status tl_problem_create_euc2d(tl_ctx *ctx, uint32_t n, const float *x, const
         set_error("unknown dist_kind %d", dist_kind);
         return TL_ERR_INVALID;
     }
+    if (dist_kind == TL_DIST_NINT_I32) {
+        // The int32 metric keeps sentinels at +-2^29 and adds up to four edges in int32, and the k-NN
+        // kernels compare nint distances as f32 (exact below 2^24): reject what would overflow silently.
+        double x0 = x[0], x1 = x[0], y0 = y[0], y1 = y[0];
+        for (uint32_t i = 0; i < n; ++i) {
+            if (!std::isfinite(x[i]) || !std::isfinite(y[i])) {
+                set_error("tl_problem_create_euc2d: NINT_I32 needs finite coordinates (city %u)", i);
+                return TL_ERR_INVALID;
+            }
+            x0 = std::min<double>(x0, x[i]); x1 = std::max<double>(x1, x[i]);
+            y0 = std::min<double>(y0, y[i]); y1 = std::max<double>(y1, y[i]);
+        }
+        if (std::hypot(x1 - x0, y1 - y0) >= 16777216.0) {
+            set_error("tl_problem_create_euc2d: NINT_I32 supports bounding-box diagonals below 2^24 (got %.3g)",
+                      std::hypot(x1 - x0, y1 - y0));
+            return TL_ERR_UNSUPPORTED;
+        }
+    }
     DeviceGuard g(ctx);
     tl_problem *p = new tl_problem();
     p->ctx = ctx;
     p->n = n;
     p->kind = dist_kind == TL_DIST_NINT_I32 ? PK_EUC_NINT : PK_EUC_F32;
     p->fast_sqrt = coords_allow_fast_sqrt(x, y, n);
+    p->grid_nint = p->kind == PK_EUC_NINT && !getenv("TL_NINT_F64") && coords_allow_grid_nint(x, y, n);
     if (p->fast_sqrt) {
         double x0 = x[0], x1 = x[0], y0 = y[0], y1 = y[0];
         for (uint32_t i = 1; i < n; ++i) {
@@ -206,10 +264,12 @@ tl_status tl_problem_create_euc2d(tl_ctx *ctx, uint32_t n, const float *x, const
     }
     *out = p;
     return TL_OK;
+    });
 }
 
 tl_status tl_problem_create_explicit(tl_ctx *ctx, uint32_t n, const float *packed_tri, tl_problem **out)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!ctx || !packed_tri || !out) { set_error("tl_problem_create_explicit: null argument"); return TL_ERR_INVALID; }
     *out = nullptr;
     if (n < 2) { set_error("distance matrix requires at least 2 points"); return TL_ERR_INVALID; }
@@ -231,6 +291,7 @@ tl_status tl_problem_create_explicit(tl_ctx *ctx, uint32_t n, const float *packe
     }
     *out = p;
     return TL_OK;
+    });
 }
 
 void tl_problem_destroy(tl_problem *p)
@@ -260,7 +321,7 @@ static tl_status matrix_packed_impl(tl_problem *p, void *out, bool want_int)
     }
     DevBuf<uint32_t> d;
     if (d.alloc(cnt) != cudaSuccess) { set_error("packed matrix of %zu entries does not fit", cnt); return TL_ERR_NOMEM; }
-    launch_k1_packed(p->d_xy, p->n, p->fast_sqrt, want_int, d.p, c->sm_count, c->stream);
+    launch_k1_packed(p->d_xy, p->n, p->fast_sqrt, p->nint_mode(), d.p, c->sm_count, c->stream);
     c->launches++;
     TL_CUDA_TRY(cudaGetLastError());
     if (getenv("TL_K1_TIMING")) { // tuning aid: warm kernel time (CUDA events, 20 back-to-back launches) on stderr
@@ -268,13 +329,13 @@ static tl_status matrix_packed_impl(tl_problem *p, void *out, bool want_int)
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0, c->stream);
-        for (int r = 0; r < 20; ++r) launch_k1_packed(p->d_xy, p->n, p->fast_sqrt, want_int, d.p, c->sm_count, c->stream);
+        for (int r = 0; r < 20; ++r) launch_k1_packed(p->d_xy, p->n, p->fast_sqrt, p->nint_mode(), d.p, c->sm_count, c->stream);
         cudaEventRecord(e1, c->stream);
         cudaEventSynchronize(e1);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         fprintf(stderr, "[tl] k1_packed n=%u %s: %.2f us per launch, %.1f GB/s written\n", p->n,
-                want_int ? "nint" : (p->fast_sqrt ? "f32-fast" : "f32-safe"), ms / 20 * 1e3, cnt * 4.0 / (ms / 20 * 1e-3) / 1e9);
+                want_int ? (p->grid_nint ? "nint-int32" : "nint-f64") : (p->fast_sqrt ? "f32-fast" : "f32-safe"), ms / 20 * 1e3, cnt * 4.0 / (ms / 20 * 1e-3) / 1e9);
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         c->launches += 20;
@@ -284,8 +345,14 @@ static tl_status matrix_packed_impl(tl_problem *p, void *out, bool want_int)
     return TL_OK;
 }
 
-tl_status tl_dist_matrix_packed(tl_problem *p, float *out) { return matrix_packed_impl(p, out, false); }
-tl_status tl_dist_matrix_packed_i32(tl_problem *p, int32_t *out) { return matrix_packed_impl(p, out, true); }
+tl_status tl_dist_matrix_packed(tl_problem *p, float *out)
+{
+    return tl::guarded([&]() -> tl_status { return matrix_packed_impl(p, out, false); });
+}
+tl_status tl_dist_matrix_packed_i32(tl_problem *p, int32_t *out)
+{
+    return tl::guarded([&]() -> tl_status { return matrix_packed_impl(p, out, true); });
+}
 
 // ---- k-NN and the nearest-neighbour constructor ----------------------------------------
 
@@ -293,6 +360,7 @@ static int metric_id(const tl_problem *p) { return p->kind == PK_EUC_NINT ? 2 : 
 
 tl_status tl_knn(tl_problem *p, uint32_t k, uint32_t *out)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!p || !out) { set_error("tl_knn: null argument"); return TL_ERR_INVALID; }
     if (k == 0) return TL_OK;
     if (k > 32) { set_error("tl_knn: k = %u > 32 is not supported", k); return TL_ERR_UNSUPPORTED; }
@@ -306,10 +374,12 @@ tl_status tl_knn(tl_problem *p, uint32_t k, uint32_t *out)
     TL_CUDA_TRY(cudaMemcpyAsync(out, d.p, (size_t)p->n * k * 4, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return TL_OK;
+    });
 }
 
 tl_status tl_nn_tour(tl_problem *p, uint32_t k, uint32_t *tour_out)
 {
+    return tl::guarded([&]() -> tl_status {
     // k only changes which candidates the reference looks at first; with its buffer rule the
     // chosen city is the nearest unvisited one (ties to the lower position) for every k.
     (void)k;
@@ -330,12 +400,14 @@ tl_status tl_nn_tour(tl_problem *p, uint32_t k, uint32_t *tour_out)
     TL_CUDA_TRY(cudaMemcpyAsync(tour_out, d_tour.p, (size_t)p->n * 4, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return TL_OK;
+    });
 }
 
 // ---- tour lengths --------------------------------------------------------------------
 
 tl_status tl_tour_lengths(tl_problem *p, const uint32_t *tours, size_t batch, int32_t mode, float *out_f32)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!p || (!tours && batch) || (!out_f32 && batch)) { set_error("tl_tour_lengths: null argument"); return TL_ERR_INVALID; }
     if (mode != TL_LEN_EXACT && mode != TL_LEN_FAST) { set_error("tl_tour_lengths: unknown mode %d", mode); return TL_ERR_INVALID; }
     if (p->kind == PK_EUC_NINT) { set_error("NINT_I32 problem: use tl_tour_lengths_i64"); return TL_ERR_UNSUPPORTED; }
@@ -375,10 +447,12 @@ tl_status tl_tour_lengths(tl_problem *p, const uint32_t *tours, size_t batch, in
     TL_CUDA_TRY(cudaMemcpyAsync(out_f32, d_o.p, batch * 4, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return TL_OK;
+    });
 }
 
 tl_status tl_tour_lengths_i64(tl_problem *p, const uint32_t *tours, size_t batch, int64_t *out)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!p || (!tours && batch) || (!out && batch)) { set_error("tl_tour_lengths_i64: null argument"); return TL_ERR_INVALID; }
     if (p->kind != PK_EUC_NINT) { set_error("tl_tour_lengths_i64 needs a NINT_I32 problem"); return TL_ERR_UNSUPPORTED; }
     if (batch == 0) return TL_OK;
@@ -397,12 +471,14 @@ tl_status tl_tour_lengths_i64(tl_problem *p, const uint32_t *tours, size_t batch
     TL_CUDA_TRY(cudaMemcpyAsync(out, d_o.p, batch * 8, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return TL_OK;
+    });
 }
 
 // ---- diagnostics -----------------------------------------------------------------------
 
 tl_status tl_selftest_sqrt(tl_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!ctx || !mismatches || hi_bits < lo_bits) { set_error("tl_selftest_sqrt: bad arguments"); return TL_ERR_INVALID; }
     DeviceGuard g(ctx);
     DevBuf<unsigned long long> d;
@@ -416,10 +492,12 @@ tl_status tl_selftest_sqrt(tl_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint
     TL_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     *mismatches = h;
     return TL_OK;
+    });
 }
 
 tl_status tl_microbench_fp32(tl_ctx *ctx, double *ffma_per_s, double *mufu_per_s)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!ctx || !ffma_per_s || !mufu_per_s) { set_error("tl_microbench_fp32: null argument"); return TL_ERR_INVALID; }
     DeviceGuard g(ctx);
     DevBuf<float> sink;
@@ -453,6 +531,7 @@ tl_status tl_microbench_fp32(tl_ctx *ctx, double *ffma_per_s, double *mufu_per_s
     *ffma_per_s = best_f;
     *mufu_per_s = best_m;
     return TL_OK;
+    });
 }
 
 } // extern "C"

@@ -12,11 +12,14 @@
 
 namespace tl {
 
-// one matrix entry as raw bits: NINT = 0 f32 (FAST: guarded fast sqrt), 1 TSPLIB nint in double
+// one matrix entry as raw bits: NINT = 0 f32 (FAST: guarded fast sqrt), 1 TSPLIB nint in double,
+// 2 TSPLIB nint for integer coordinates in 32-bit integer arithmetic (common.cuh: dist_nint_grid)
 template <bool FAST, int NINT>
 __device__ __forceinline__ uint32_t k1_dist(const float2 a, const float2 b)
 {
-    if constexpr (NINT == 1)
+    if constexpr (NINT == 2)
+        return (uint32_t)dist_nint_grid(a.x, a.y, b.x, b.y);
+    else if constexpr (NINT == 1)
         return (uint32_t)dist_nint(a.x, a.y, b.x, b.y);
     else
         return __float_as_uint(dist_f32<FAST>(a.x, a.y, b.x, b.y));
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(256) k1_square_from_packed_kernel(const uint32
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
-void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, bool nint, void *out, int sm_count,
+void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, int nint, void *out, int sm_count,
                       cudaStream_t st)
 {
     const uint64_t total = (uint64_t)n * (n - 1) / 2;
@@ -160,7 +163,9 @@ void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, bool nint, void *
     if (per_cta < 4096) per_cta = 4096;
     blocks = (total + per_cta - 1) / per_cta;
     if (blocks == 0) blocks = 1;
-    if (nint)
+    if (nint == 2)
+        k1_packed_kernel<false, 2><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
+    else if (nint)
         k1_packed_kernel<false, 1><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
     else if (fast)
         k1_packed_kernel<true, 0><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
@@ -168,11 +173,13 @@ void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, bool nint, void *
         k1_packed_kernel<false, 0><<<(unsigned)blocks, 256, 0, st>>>(xy, n, total, per_cta, out);
 }
 
-void launch_k1_square(const float2 *sxy, uint32_t n, uint32_t ld, bool fast, bool nint, void *out,
+void launch_k1_square(const float2 *sxy, uint32_t n, uint32_t ld, bool fast, int nint, void *out,
                       cudaStream_t st)
 {
     dim3 grid((ld / 4 + 63) / 64, (n + 63) / 64);
-    if (nint)
+    if (nint == 2)
+        k1_square_kernel<false, 2><<<grid, 256, 0, st>>>(sxy, n, ld, out);
+    else if (nint)
         k1_square_kernel<false, 1><<<grid, 256, 0, st>>>(sxy, n, ld, out);
     else if (fast)
         k1_square_kernel<true, 0><<<grid, 256, 0, st>>>(sxy, n, ld, out);

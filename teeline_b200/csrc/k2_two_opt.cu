@@ -68,7 +68,7 @@ __device__ __forceinline__ int find_band(const int32_t *__restrict__ band_first,
 template <bool FAST>
 __device__ __noinline__ void fused_apply_tail(Pt *__restrict__ pts, const BestF *__restrict__ blockbest, BestF *red,
                                               DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
-                                              uint64_t log_cap)
+                                              uint64_t log_cap, const ShardComm &sc)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // (ordering: thread 0's acq_rel ticket + the caller's __syncthreads; the records are read from L2)
@@ -91,6 +91,24 @@ __device__ __noinline__ void fused_apply_tail(Pt *__restrict__ pts, const BestF 
         const BestF o = red[w];
         if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
     }
+    if (sc.world > 1) {
+        // sharded triangle: this rank's minimum goes to every peer's mailbox over NVLink and the
+        // minimum over all ranks comes back, identical everywhere (shard_exchange.cuh)
+        __shared__ BestF s_peer[kMaxPeers];
+        __shared__ int s_fail;
+        __shared__ unsigned int s_step;
+        if (threadIdx.x == 0) s_step = (unsigned int)hdr.h0.y + 1u; // scans completed so far + 1
+        __syncthreads();
+        v = shard_exchange_2opt(sc, v, s_step, s_peer, &s_fail);
+        if (s_fail) { // a peer never answered: stop the search instead of hanging the box
+            if (threadIdx.x == 0) {
+                *ticket = 0u;
+                state->error = 1;
+                state->done = 1;
+            }
+            return;
+        }
+    }
     const bool found = v.i != 0xffffffffu;
     if (found) reverse_segment_inplace(EucPol<FAST>{pts}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0) {
@@ -108,7 +126,7 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
     two_opt_scan_recompute_kernel(Pt *__restrict__ pts, const ScanGeom g,
                                   const int32_t *__restrict__ band_first, BestF *__restrict__ blockbest,
                                   DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
-                                  uint64_t log_cap, int fuse_apply)
+                                  uint64_t log_cap, int fuse_apply, const __grid_constant__ ShardComm sc)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // PDL: let the next step's launch start as soon as SMs free up; everything up to
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(WARPS * 32, kScanMinBlocks)
     if (threadIdx.x == 0) s_last = (ticket_take_acq_rel(ticket) == gridDim.x - 1) ? 1u : 0u; // thread 0 wrote blockbest
     __syncthreads();
     if (!s_last) return;
-    fused_apply_tail<FAST>(pts, blockbest, red, state, ticket, log, log_cap);
+    fused_apply_tail<FAST>(pts, blockbest, red, state, ticket, log, log_cap, sc);
 }
 
 // tour-ordered point records from city coordinates and a tour
@@ -319,9 +337,12 @@ cudaError_t scan_recompute_configure()
 
 void launch_scan_recompute(Pt *pts, const ScanGeom &g, const int32_t *band_first, BestF *blockbest,
                            DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap,
-                           bool fuse_apply, int grid, bool fast, cudaStream_t st)
+                           bool fuse_apply, const ShardComm *shard, int grid, bool fast, cudaStream_t st)
 {
     const size_t smem = scan_recompute_smem_bytes();
+    ShardComm sc{};
+    sc.world = 1;
+    if (shard) sc = *shard;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -336,7 +357,7 @@ void launch_scan_recompute(Pt *pts, const ScanGeom &g, const int32_t *band_first
     auto kern = (fast && g.screen_margin >= 0.0f) ? two_opt_scan_recompute_kernel<true, true>
                 : fast                           ? two_opt_scan_recompute_kernel<true, false>
                                                  : two_opt_scan_recompute_kernel<false, false>;
-    cudaLaunchKernelEx(&cfg, kern, pts, g, band_first, blockbest, state, ticket, log, (uint64_t)log_cap, fuse);
+    cudaLaunchKernelEx(&cfg, kern, pts, g, band_first, blockbest, state, ticket, log, (uint64_t)log_cap, fuse, sc);
 }
 
 void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic,

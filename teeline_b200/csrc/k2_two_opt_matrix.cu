@@ -121,7 +121,8 @@ template <typename V>
 __device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, uint32_t ld, Cs *__restrict__ cs,
                                                      const Best<V> *__restrict__ blockbest, Best<V> *red,
                                                      DevState *state, unsigned int *ticket,
-                                                     tl_move *__restrict__ log, uint64_t log_cap)
+                                                     tl_move *__restrict__ log, uint64_t log_cap,
+                                                     const ShardComm &sc)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef TL_TIMELINE
@@ -156,6 +157,22 @@ __device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, ui
     for (int w = 1; w < WARPS; ++w) {
         const Best<V> o = red[w];
         if (better_2opt(o.delta, o.i, o.j, v.delta, v.i, v.j)) v = o;
+    }
+    if (sc.world > 1) { // sharded triangle: exchange the per-rank minima over NVLink (shard_exchange.cuh)
+        __shared__ Best<V> s_peer[kMaxPeers];
+        __shared__ int s_fail;
+        __shared__ unsigned int s_step;
+        if (threadIdx.x == 0) s_step = (unsigned int)hdr.h0.y + 1u;
+        __syncthreads();
+        v = shard_exchange_2opt(sc, v, s_step, s_peer, &s_fail);
+        if (s_fail) {
+            if (threadIdx.x == 0) {
+                *ticket = 0u;
+                state->error = 1;
+                state->done = 1;
+            }
+            return;
+        }
     }
     const bool found = v.i != 0xffffffffu;
 #ifdef TL_TIMELINE
@@ -193,7 +210,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
     two_opt_scan_matrix_kernel(const V *__restrict__ M, uint32_t ld, Cs *__restrict__ cs, const ScanGeom g,
                                const int32_t *__restrict__ band_first_g, Best<V> *__restrict__ blockbest,
                                DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
-                               uint64_t log_cap, int fuse_apply, int pin_rows, int pf_rows)
+                               uint64_t log_cap, int fuse_apply, int pin_rows, int pf_rows, const __grid_constant__ ShardComm sc)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     griddep_launch_dependents(); // PDL, as in k2_two_opt.cu
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
         if (threadIdx.x == 0) *ticket = 0u;
         return;
     }
-    fused_apply_tail_matrix<V>(M, ld, cs, blockbest, red, state, ticket, log, log_cap);
+    fused_apply_tail_matrix<V>(M, ld, cs, blockbest, red, state, ticket, log, log_cap, sc);
 }
 
 // cs[q] = {slot q, entering edge M[slot q-1][slot q], city}; wrap copy at n when cyclic; -inf padding
@@ -511,9 +528,12 @@ cudaError_t scan_matrix_configure()
 
 void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_first, void *blockbest,
                         DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap, bool fuse_apply,
-                        int grid, const MatPin &pin, cudaStream_t st)
+                        const ShardComm *shard, int grid, const MatPin &pin, cudaStream_t st)
 {
     const size_t smem = scan_matrix_smem_bytes();
+    ShardComm sc{};
+    sc.world = 1;
+    if (shard) sc = *shard;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -543,7 +563,7 @@ void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_f
     const int pf_rows = pf_default;
 #define TL_LAUNCH_MAT(V, PINNED, BEST)                                                                          \
     cudaLaunchKernelEx(&cfg, two_opt_scan_matrix_kernel<V, PINNED>, (const V *)src.M, src.ld, src.cs, g,        \
-                       band_first, (BEST *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse, pin_rows, pf_rows)
+                       band_first, (BEST *)blockbest, state, ticket, log, (uint64_t)log_cap, fuse, pin_rows, pf_rows, sc)
     if (src.is_int()) {
         if (pin_rows > 0) TL_LAUNCH_MAT(int32_t, true, BestI); else TL_LAUNCH_MAT(int32_t, false, BestI);
     } else {

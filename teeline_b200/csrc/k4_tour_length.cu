@@ -17,6 +17,8 @@
 // launch-latency bound.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace tl {
 
 namespace {
@@ -137,6 +139,72 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Small batches (the reference's GA population is n tours, genetic_algorithm.rs:26: 1000 tours of
+// 1000 cities): with one CTA per 32 tours only batch/32 SMs work.  Here a WARP owns a tour: the 32
+// lanes compute 32 edge lengths at a time from the CTA's shared-memory copy of the coordinates,
+// park them in shared memory, and every lane folds them in order (8 broadcast LDS.128 + 32 FADD per
+// 32 edges); the next chunk's tour entries are already in flight.  Edges past the end of the tour
+// are stored as +0.0, and x + 0.0 == x exactly, so the fold needs no bounds.  The serial f32 chain
+// of the reference (1000 dependent adds = ~2 us) is the floor of this kernel.
+template <bool FAST, bool FASTMODE>
+__global__ void __launch_bounds__(256)
+    tour_lengths_warp_kernel(const float2 *__restrict__ gxy, uint32_t n, const uint32_t *__restrict__ tours,
+                             uint64_t batch, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float2 s_xy[]; // all n coordinates
+    __shared__ __align__(16) float s_len[8][32];
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) s_xy[t] = __ldg(&gxy[t]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nchunks = n < 2 ? 0 : (n - 1 + 31) / 32;
+    for (uint64_t b = (uint64_t)blockIdx.x * 8 + warp; b < batch; b += (uint64_t)gridDim.x * 8) {
+        const uint32_t *t = tours + b * n;
+        float acc = 0.0f;
+        double dacc = 0.0;
+        bool bad = false;
+        uint32_t a_next = (uint32_t)lane < n ? __ldg(&t[lane]) : 0u;
+        uint32_t x_next = 32u < n ? __ldg(&t[32]) : 0u;
+        if (n >= 2) { // closing edge first (distance_matrix.rs:240)
+            const uint32_t first = __ldg(&t[0]), last = __ldg(&t[n - 1]);
+            bad = first >= n || last >= n;
+            const float e0 = bad ? 0.0f : edge_f32<FAST, true>(s_xy, nullptr, last, first);
+            acc = e0;
+            dacc = (double)e0;
+        }
+        for (uint32_t ch = 0; ch < nchunks; ++ch) {
+            const uint32_t k0 = ch * 32;
+            const uint32_t cnt = min(32u, n - 1 - k0);
+            const uint32_t a = a_next;
+            uint32_t c = __shfl_down_sync(0xffffffffu, a, 1);
+            if (lane == 31) c = x_next;
+            if (ch + 1 < nchunks) { // next chunk's entries: in flight while this one is folded
+                const uint32_t q = k0 + 32 + (uint32_t)lane;
+                a_next = q < n ? __ldg(&t[q]) : 0u;
+                x_next = k0 + 64 < n ? __ldg(&t[k0 + 64]) : 0u;
+            }
+            const bool in = (uint32_t)lane < cnt;
+            const bool oob = in && (a >= n || c >= n);
+            bad = bad || oob;
+            s_len[warp][lane] = (in && !oob) ? edge_f32<FAST, true>(s_xy, nullptr, a, c) : 0.0f;
+            __syncwarp();
+            const float4 *v = reinterpret_cast<const float4 *>(s_len[warp]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 w = v[q];
+                if (FASTMODE) {
+                    dacc += (double)w.x; dacc += (double)w.y; dacc += (double)w.z; dacc += (double)w.w;
+                } else {
+                    acc = __fadd_rn(acc, w.x); acc = __fadd_rn(acc, w.y);
+                    acc = __fadd_rn(acc, w.z); acc = __fadd_rn(acc, w.w);
+                }
+            }
+            __syncwarp();
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) out[b] = (bad || n < 2) ? 0.0f : (FASTMODE ? (float)dacc : acc);
+    }
+}
+
 __global__ void __launch_bounds__(256)
     tour_lengths_nint_kernel(const float2 *__restrict__ xy, uint32_t n, const uint32_t *__restrict__ tours,
                              uint64_t batch, long long *__restrict__ out)
@@ -169,10 +237,31 @@ void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, con
                              uint64_t batch, bool fast_sqrt, bool fast_mode, float *out, int sm_count,
                              cudaStream_t st)
 {
+    if (batch == 0) return;
+    // small batch: a warp per tour (8 tours per CTA) keeps every SM busy; large batches take the
+    // CTA-per-32-tours kernel, whose in-order fold costs 2 warp instructions per 32 edges instead of 40
+    if (!tri && (size_t)n * sizeof(float2) <= 190 * 1024 && batch < (uint64_t)sm_count * 32 &&
+        !getenv("TL_K4_NO_WARP")) {
+        uint64_t wb = (batch + 7) / 8;
+        if (wb > (uint64_t)sm_count * 4) wb = (uint64_t)sm_count * 4;
+        const size_t smem = (size_t)n * sizeof(float2);
+#define TL_LAUNCH_K4W(FS, FM)                                                                                     \
+    do {                                                                                                          \
+        cudaFuncSetAttribute(tour_lengths_warp_kernel<FS, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                             190 * 1024);                                                                         \
+        tour_lengths_warp_kernel<FS, FM><<<(unsigned)wb, 256, smem, st>>>(xy, n, tours, batch, out);              \
+    } while (0)
+        if (fast_sqrt) {
+            if (fast_mode) TL_LAUNCH_K4W(true, true); else TL_LAUNCH_K4W(true, false);
+        } else {
+            if (fast_mode) TL_LAUNCH_K4W(false, true); else TL_LAUNCH_K4W(false, false);
+        }
+#undef TL_LAUNCH_K4W
+        return;
+    }
     uint64_t blocks = (batch + 31) / 32; // one CTA per 32 tours
     const uint64_t cap = (uint64_t)sm_count * 8;
     if (blocks > cap) blocks = cap;
-    if (blocks == 0) return;
     const unsigned g = (unsigned)blocks;
     // coordinates in shared memory when they fit beside the edge buffer and there are enough tours
     // per CTA to pay for the copy

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "shard_exchange.cuh"
 #include "../../include/teeline_cuda.h"
 
 namespace tl {
@@ -48,7 +49,7 @@ struct DevState {
     unsigned long long passes;
     unsigned long long found_key; // Mode R: (i << 32 | j) of the first improving pair, ~0 if none
     float last_delta;
-    int32_t pad1;
+    int32_t error; // 1: a sharded step timed out waiting for a peer's record (shard_exchange.cuh)
 };
 
 
@@ -74,9 +75,10 @@ struct Src {
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, bool nint, void *out, int sm_count,
+// nint: 0 = f32 metric, 1 = TSPLIB nint through f64, 2 = TSPLIB nint in 32-bit integers (integer coordinates)
+void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, int nint, void *out, int sm_count,
                       cudaStream_t st);
-void launch_k1_square(const float2 *sxy, uint32_t n, uint32_t ld, bool fast, bool nint, void *out,
+void launch_k1_square(const float2 *sxy, uint32_t n, uint32_t ld, bool fast, int nint, void *out,
                       cudaStream_t st);
 void launch_k1_square_from_packed(const uint32_t *tri, const int32_t *slot_city, uint32_t n,
                                   uint32_t ld, uint32_t *out, cudaStream_t st);
@@ -101,9 +103,11 @@ constexpr int kScanWarps = 8;           // warps per CTA
 constexpr int kScanMinBlocks = TL_SCAN_MINB; // resident CTAs per SM the kernel is compiled for
 size_t scan_recompute_smem_bytes();
 cudaError_t scan_recompute_configure();
+// fuse_apply: the last CTA reduces the per-CTA records and applies the move; with `shard` non-null it
+// first exchanges this rank's record with every peer over NVLink (shard_exchange.cuh)
 void launch_scan_recompute(Pt *pts, const ScanGeom &g, const int32_t *band_first, BestF *blockbest,
                            DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap,
-                           bool fuse_apply, int grid, bool fast, cudaStream_t st);
+                           bool fuse_apply, const ShardComm *shard, int grid, bool fast, cudaStream_t st);
 void launch_build_pts(const float2 *xy, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic,
                       bool fast, Pt *pts, cudaStream_t st);
 void launch_apply_two_opt(const Src &src, const void *cand, int ncand, DevState *state, unsigned int *ticket,
@@ -218,7 +222,7 @@ struct MatPin {
 };
 void launch_scan_matrix(const Src &src, const ScanGeom &g, const int32_t *band_first, void *blockbest,
                         DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap, bool fuse_apply,
-                        int grid, const MatPin &pin, cudaStream_t st);
+                        const ShardComm *shard, int grid, const MatPin &pin, cudaStream_t st);
 // cs[q] = {slot = q, sp = M[q-1][q], city = tour[q]} (+ wrap copy at n when cyclic, -inf padding)
 void launch_build_cs(const Src &src, const uint32_t *tour, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st);
 // slot-ordered scratch for (re)building the matrix in tour order: from `tour` (session start)

@@ -9,6 +9,9 @@
 
 #include <dlfcn.h>
 
+#include <cstdlib>
+#include <vector>
+
 namespace tl {
 
 namespace {
@@ -99,6 +102,95 @@ void nccl_comm_destroy(void *comm)
 {
     NcclApi *a = api();
     if (a && comm) a->CommDestroy(comm);
+}
+
+tl_status nccl_barrier(tl_ctx *c)
+{
+    if (!c->nccl_comm) { set_error("NCCL communicator not attached"); return TL_ERR_NCCL; }
+    int *d = nullptr;
+    TL_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d), sizeof(int) * c->world));
+    TL_CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(int) * c->world, c->stream));
+    tl_status rc = nccl_all_gather_bytes(c->nccl_comm, d + c->rank, d, sizeof(int), c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (rc != TL_OK) return rc;
+    TL_CUDA_TRY(e);
+    return TL_OK;
+}
+
+// ---- peer mailboxes ------------------------------------------------------------------------------
+// Collective over the context's NCCL communicator: every rank allocates its mailbox, exports it with
+// cudaIpcGetMemHandle, the 64-byte handles travel through one ncclAllGather, every rank opens every
+// peer's handle (NVLink peer mapping), and a second all-gather of one flag makes the outcome
+// unanimous: the in-kernel exchange is used only if EVERY rank mapped EVERY mailbox; otherwise all
+// ranks keep the ncclAllGather + apply-kernel path.
+tl_status setup_peer_mailboxes(tl_ctx *c)
+{
+    release_peer_mailboxes(c);
+    if (c->world < 2 || c->world > kMaxPeers || getenv("TL_SHARD_NO_P2P")) return TL_OK;
+    cudaStream_t st = c->stream;
+    struct Slot { cudaIpcMemHandle_t h; int ok; int pad[3]; }; // 80 bytes
+    void *mb = nullptr;
+    Slot mine{};
+    mine.ok = 0;
+    if (cudaMalloc(&mb, kMailboxBytes) == cudaSuccess && cudaMemset(mb, 0, kMailboxBytes) == cudaSuccess &&
+        cudaIpcGetMemHandle(&mine.h, mb) == cudaSuccess)
+        mine.ok = 1;
+    cudaGetLastError();
+    Slot *d_all = nullptr;
+    TL_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_all), sizeof(Slot) * c->world));
+    std::vector<Slot> all(c->world);
+    auto gather = [&]() -> tl_status {
+        TL_CUDA_TRY(cudaMemcpyAsync(d_all + c->rank, &mine, sizeof(Slot), cudaMemcpyHostToDevice, st));
+        tl_status rc = nccl_all_gather_bytes(c->nccl_comm, d_all + c->rank, d_all, sizeof(Slot), st);
+        if (rc != TL_OK) return rc;
+        TL_CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(Slot) * c->world, cudaMemcpyDeviceToHost, st));
+        TL_CUDA_TRY(cudaStreamSynchronize(st));
+        return TL_OK;
+    };
+    tl_status rc = gather();
+    if (rc != TL_OK) { cudaFree(d_all); if (mb) cudaFree(mb); return rc; }
+    bool ok = true;
+    for (int r = 0; r < c->world; ++r) ok = ok && all[r].ok;
+    if (ok) {
+        for (int r = 0; r < c->world && ok; ++r) {
+            if (r == c->rank) { c->peer_mailbox[r] = static_cast<unsigned long long *>(mb); continue; }
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+            } else {
+                c->peer_mailbox[r] = static_cast<unsigned long long *>(p);
+            }
+        }
+    }
+    mine.ok = ok ? 1 : 0; // second round: did every rank map everything?
+    rc = gather();
+    cudaFree(d_all);
+    if (rc == TL_OK)
+        for (int r = 0; r < c->world; ++r) ok = ok && all[r].ok;
+    c->mailbox = static_cast<unsigned long long *>(mb);
+    c->p2p_ready = rc == TL_OK && ok;
+    if (!c->p2p_ready) {
+        const bool keep_err = rc != TL_OK;
+        release_peer_mailboxes(c);
+        if (keep_err) return rc;
+    }
+    if (getenv("TL_DEBUG_SHARD"))
+        fprintf(stderr, "[tl] rank %d/%d: peer mailboxes %s\n", c->rank, c->world, c->p2p_ready ? "mapped (in-kernel exchange)" : "unavailable (ncclAllGather path)");
+    return TL_OK;
+}
+
+void release_peer_mailboxes(tl_ctx *c)
+{
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (c->peer_mailbox[r] && c->peer_mailbox[r] != c->mailbox) cudaIpcCloseMemHandle(c->peer_mailbox[r]);
+        c->peer_mailbox[r] = nullptr;
+    }
+    if (c->mailbox) cudaFree(c->mailbox);
+    c->mailbox = nullptr;
+    c->p2p_ready = false;
+    cudaGetLastError();
 }
 
 } // namespace tl

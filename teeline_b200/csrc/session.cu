@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -67,6 +68,8 @@ struct tl_session {
     int nitems = 0;
     int grid = 1;
     int shard_index = 0, shard_count = 1;
+    bool use_mailbox = false; // sharded 2-opt: per-rank minima exchanged inside the scan kernel (shard_exchange.cuh)
+    ShardComm comm{};
 
     DevBuf<BestF> cand; // shard_count * grid records (BestF and BestI have the same layout)
     DevBuf<DevState> state;
@@ -162,7 +165,7 @@ void build_or_geometry(tl_session *s)
     const int per_cb = (int)std::max<int64_t>(1, target / ncb);
     s->or_chunk = std::max(16, (n + per_cb - 1) / per_cb);
     s->or_items_per_cb = (n + s->or_chunk - 1) / s->or_chunk;
-    s->nitems = ncb * s->or_items_per_cb;
+    s->nitems = ncb * s->or_items_per_cb; // <= ~(n/256) * max(n/16, target/ncb): fits int32 for every n that fits HBM
     const int64_t per = ((int64_t)s->nitems + s->shard_count - 1) / s->shard_count;
     s->or_item_begin = (int)std::min<int64_t>(s->nitems, per * s->shard_index);
     s->or_item_end = (int)std::min<int64_t>(s->nitems, per * (s->shard_index + 1));
@@ -185,6 +188,13 @@ void build_or_geometry(tl_session *s)
 tl_status upload_three_geometry(tl_session *s)
 {
     const int n = (int)s->n;
+    // ~n^2/64 work items: the table is int32, so refuse instances whose count would not fit
+    int64_t total_items = 0;
+    for (int i = 0; i + 2 < n; ++i) total_items += (n - 2 - i + 31) / 32;
+    if (total_items > INT32_MAX) {
+        set_error("3-opt on n = %d needs %lld work items (> 2^31): not supported", n, (long long)total_items);
+        return TL_ERR_UNSUPPORTED;
+    }
     std::vector<int32_t> rf(n - 1, 0); // rows i = 0 .. n-3, plus the total
     for (int i = 0; i + 2 < n; ++i) rf[i + 1] = rf[i] + (n - 2 - i + 31) / 32;
     s->nitems = rf[n - 2];
@@ -243,7 +253,7 @@ void build_matrix(tl_session *s, const uint32_t *d_tour)
                                      s->M.p, st);
     } else {
         launch_gather_slots(p->d_xy, d_tour, s->cs.p, s->n, s->sxy.p, nullptr, st);
-        launch_k1_square(s->sxy.p, s->n, s->ld, p->fast_sqrt, p->kind == PK_EUC_NINT, s->M.p, st);
+        launch_k1_square(s->sxy.p, s->n, s->ld, p->fast_sqrt, p->nint_mode(), s->M.p, st);
     }
     s->c->launches += 2;
 }
@@ -299,9 +309,13 @@ void repermute(tl_session *s)
     s->steps_since_permute = 0;
 }
 
-// fuse: let the 2-opt scan kernel's last CTA apply the move (single-GPU stepping only)
-tl_status launch_scan(tl_session *s, bool fuse)
+// fuse: let the 2-opt scan kernel's last CTA apply the move -- single-GPU stepping, and sharded
+// stepping when the peers' mailboxes are mapped (the last CTA then exchanges the per-rank minima
+// over NVLink before it applies the move)
+tl_status launch_scan(tl_session *s, bool fuse, bool exchange = true)
 {
+    const bool fused = fuse && (s->shard_count == 1 || s->use_mailbox);
+    const ShardComm *comm = (fused && s->shard_count > 1) ? &s->comm : nullptr;
     BestF *mine = s->cand.p + (size_t)s->shard_index * s->grid;
     cudaStream_t st = s->c->stream;
     if (s->algo == TL_ALGO_THREE_OPT) {
@@ -315,14 +329,14 @@ tl_status launch_scan(tl_session *s, bool fuse)
         s->c->launches += 2;
     } else if (s->matrix()) {
         launch_scan_matrix(s->src, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p, s->log_cap,
-                           fuse && s->shard_count == 1, s->grid, s->pin, st);
+                           fused, comm, s->grid, s->pin, st);
         s->c->launches++;
     } else {
         launch_scan_recompute(s->pts.p, s->geom, s->band_first.p, mine, s->state.p, s->ticket.p, s->log.p,
-                              s->log_cap, fuse && s->shard_count == 1, s->grid, s->src.kind == SRC_EUC_FAST, st);
+                              s->log_cap, fused, comm, s->grid, s->src.kind == SRC_EUC_FAST, st);
         s->c->launches++;
     }
-    if (s->shard_count > 1) {
+    if (s->shard_count > 1 && !comm && exchange) {
         if (!s->c->nccl_comm) { set_error("sharded session needs tl_ctx_attach_nccl first"); return TL_ERR_NCCL; }
         // in-place all-gather: every rank contributes its `grid` block records
         tl_status rc = nccl_all_gather_bytes(s->c->nccl_comm, mine, s->cand.p, (size_t)s->grid * sizeof(BestF), st);
@@ -372,7 +386,7 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
             s->c->launches += 2;
             continue;
         }
-        if (s->shard_count == 1) continue; // the scan kernel's last CTA applied the move
+        if (s->shard_count == 1 || s->use_mailbox) continue; // the scan kernel's last CTA applied the move
         launch_apply_two_opt(s->src, s->cand.p, s->grid * s->shard_count, s->state.p, s->ticket.p, s->log.p,
                              s->log_cap, apply_grid, st);
         s->c->launches++;
@@ -444,6 +458,7 @@ extern "C" {
 
 tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uint32_t *tour, tl_session **out)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!p || !tour || !out) { set_error("tl_session_create: null argument"); return TL_ERR_INVALID; }
     *out = nullptr;
     if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC && algo != TL_ALGO_TWO_OPT_REF &&
@@ -526,8 +541,16 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     if (want_matrix) {
         s->ld = (p->n + 31u) & ~31u;
         const size_t bytes = (size_t)p->n * s->ld * 4;
+        // what a new block can come from: the driver's free memory plus what this context's pool
+        // holds cached from earlier sessions (reserved but not in use)
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
+        if (c->pool) {
+            uint64_t reserved = 0, used = 0;
+            if (cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+                free_b += (size_t)(reserved - used);
+        }
         if (bytes > free_b - std::min<size_t>(free_b, (size_t)1 << 30)) {
             set_error("the %u x %u distance matrix (%.1f GB) does not fit device memory (%.1f GB free); "
                       "use TL_PATH_RECOMPUTE", p->n, s->ld, bytes / 1e9, free_b / 1e9);
@@ -580,6 +603,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     if (cudaGetLastError() != cudaSuccess) { set_error("tl_session_create: kernel launch failed"); return fail(TL_ERR_CUDA); }
     *out = s;
     return TL_OK;
+    });
 }
 
 void tl_session_destroy(tl_session *s)
@@ -597,6 +621,7 @@ void tl_session_destroy(tl_session *s)
 
 tl_status tl_session_set_shard(tl_session *s, int32_t index, int32_t count)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!s || count < 1 || index < 0 || index >= count) { set_error("tl_session_set_shard: bad arguments"); return TL_ERR_INVALID; }
     if (s->algo == TL_ALGO_TWO_OPT_REF) {
         if (count > 1) { set_error("Mode R does not shard (replicas only)"); return TL_ERR_UNSUPPORTED; }
@@ -605,12 +630,39 @@ tl_status tl_session_set_shard(tl_session *s, int32_t index, int32_t count)
     DeviceGuard g(s->c);
     s->shard_index = index;
     s->shard_count = count;
+    s->use_mailbox = false;
+    tl_ctx *c = s->c;
+    const bool two_opt_best = s->algo == TL_ALGO_TWO_OPT_BEST || s->algo == TL_ALGO_TWO_OPT_BEST_CYCLIC;
+    const char *tr = getenv("TL_SHARD_TRANSPORT"); // "nccl": force the all-gather + apply-kernel path
+    if (count > 1 && two_opt_best && c->p2p_ready && count == c->world && index == c->rank &&
+        !(tr && !strcmp(tr, "nccl"))) {
+        // One sharded session steps at a time per context; its records are tagged with an epoch so
+        // that a mailbox slot left over from an earlier session can never look current.  Every 255
+        // sessions the epochs are recycled behind a collective reset of the mailboxes.
+        if (c->shard_epoch > 0 && c->shard_epoch % 255 == 0) {
+            TL_CUDA_TRY(cudaStreamSynchronize(c->stream));
+            tl_status rc = nccl_barrier(c);
+            if (rc != TL_OK) return rc;
+            TL_CUDA_TRY(cudaMemsetAsync(c->mailbox, 0, kMailboxBytes, c->stream));
+            rc = nccl_barrier(c);
+            if (rc != TL_OK) return rc;
+        }
+        s->comm = ShardComm{};
+        for (int r = 0; r < count; ++r) s->comm.peer[r] = c->peer_mailbox[r];
+        s->comm.rank = index;
+        s->comm.world = count;
+        s->comm.epoch = c->shard_epoch % 255 + 1;
+        c->shard_epoch++;
+        s->use_mailbox = true;
+    }
     if (s->trivial) return TL_OK;
     return upload_geometry(s);
+    });
 }
 
 tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!s || !found) { set_error("tl_session_scan: null argument"); return TL_ERR_INVALID; }
     *found = 0;
     if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_scan: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
@@ -639,10 +691,12 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
     }
     *found = any ? 1 : 0;
     return TL_OK;
+    });
 }
 
 tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!s || !avg_ms || reps == 0) { set_error("tl_session_time_scans: bad arguments"); return TL_ERR_INVALID; }
     if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_time_scans: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
     *avg_ms = 0.0;
@@ -655,10 +709,10 @@ tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
     cudaEvent_t a, b;
     TL_CUDA_TRY(cudaEventCreate(&a));
     TL_CUDA_TRY(cudaEventCreate(&b));
-    rc = launch_scan(s, false); // warm
+    rc = launch_scan(s, false, false); // warm; a sharded session times its own share of the scan, no exchange
     if (rc == TL_OK) {
         cudaEventRecord(a, s->c->stream);
-        for (uint32_t r = 0; r < reps && rc == TL_OK; ++r) rc = launch_scan(s, false);
+        for (uint32_t r = 0; r < reps && rc == TL_OK; ++r) rc = launch_scan(s, false, false);
         cudaEventRecord(b, s->c->stream);
         cudaEventSynchronize(b);
         float ms = 0.f;
@@ -671,17 +725,21 @@ tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
     TL_CUDA_TRY(cudaGetLastError());
     if (was_done) { s->h.done = was_done; rc = push_state(s); }
     return rc;
+    });
 }
 
 tl_status tl_session_enqueue(tl_session *s, uint32_t steps)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!s) { set_error("tl_session_enqueue: null session"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c);
     return enqueue_steps(s, steps);
+    });
 }
 
 tl_status tl_session_run(tl_session *s, int64_t max_moves)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!s) { set_error("tl_session_run: null session"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
@@ -739,11 +797,18 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
         head = (head + 1) % kSlots;
         --queued;
     }
-    return close_timing(s);
+    rc = close_timing(s);
+    if (rc == TL_OK && s->h.error) {
+        set_error("sharded step: a peer's best-move record did not arrive (rank down or not stepping the same session)");
+        return TL_ERR_NCCL;
+    }
+    return rc;
+    });
 }
 
 tl_status tl_session_tour(tl_session *s, uint32_t *tour_out)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!s || !tour_out) { set_error("tl_session_tour: null argument"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c);
     DevBuf<uint32_t> d;
@@ -754,10 +819,12 @@ tl_status tl_session_tour(tl_session *s, uint32_t *tour_out)
     TL_CUDA_TRY(cudaMemcpyAsync(tour_out, d.p, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->c->stream));
     TL_CUDA_TRY(cudaStreamSynchronize(s->c->stream));
     return TL_OK;
+    });
 }
 
 tl_status tl_session_stats(tl_session *s, tl_stats *stats)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!s || !stats) { set_error("tl_session_stats: null argument"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
@@ -773,11 +840,17 @@ tl_status tl_session_stats(tl_session *s, tl_stats *stats)
     stats->device_ms = s->device_ms;
     stats->converged = s->h.converged;
     stats->path_used = s->path_used;
+    if (s->h.error) {
+        set_error("sharded step: a peer's best-move record did not arrive (rank down or not stepping the same session)");
+        return TL_ERR_NCCL;
+    }
     return TL_OK;
+    });
 }
 
 tl_status tl_session_log(tl_session *s, tl_move *log, size_t log_cap, size_t *n_out)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!s || !n_out) { set_error("tl_session_log: null argument"); return TL_ERR_INVALID; }
     DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
@@ -790,11 +863,13 @@ tl_status tl_session_log(tl_session *s, tl_move *log, size_t log_cap, size_t *n_
     }
     *n_out = cnt;
     return TL_OK;
+    });
 }
 
 tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *tour_inout, int64_t max_moves,
                           tl_stats *stats, tl_move *log, size_t log_cap)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!p || !tour_inout) { set_error("tl_local_search: null argument"); return TL_ERR_INVALID; }
     tl_session *s = nullptr;
     const bool trace = getenv("TL_DEBUG_TIMING") != nullptr; // host wall time of each phase on stderr
@@ -826,6 +901,7 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
         fprintf(stderr, "[tl] local_search: create %.2f ms, run %.2f ms, tour+stats+log %.2f ms, destroy %.2f ms\n",
                 t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
+    });
 }
 
 // ---- batched multi-start 2-opt (GA / multi-start populations) ----------------------------------
@@ -833,6 +909,7 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
 tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, size_t batch, int64_t max_moves,
                            tl_stats *stats, float *lengths_out)
 {
+    return tl::guarded([&]() -> tl_status {
     if (!p || (!tours_inout && batch)) { set_error("tl_two_opt_batch: null argument"); return TL_ERR_INVALID; }
     if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC) {
         set_error("tl_two_opt_batch: only TL_ALGO_TWO_OPT_BEST[_CYCLIC] is batched");
@@ -914,6 +991,7 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
         stats->path_used = TL_PATH_RECOMPUTE;
     }
     return TL_OK;
+    });
 }
 
 } // extern "C"

@@ -929,3 +929,67 @@ def test_config5_full_population_to_local_optimum(T, ctx):
         moves += want_st.moves
     assert f5(lengths[0]) == "25282.04297"  # tour 0 is the survey probe's NN -> Mode B result
     assert int(st.moves) > moves and int(st.passes) == int(st.moves) + B
+
+
+# ---- round 2 additions: K4 small/large batch kernels, integer nint, argument checks -----------------------
+
+def test_k4_both_kernels_match_oracle(T, ctx):
+    """Small batches take the warp-per-tour kernel, large ones the CTA-per-32-tours kernel: both are the
+    reference's sequential f32 sum, bit for bit (incl. n not a multiple of 32 and a tour with an
+    unknown position)."""
+    for n, B in ((1000, 1000), (999, 37), (33, 9), (200, 5000)):
+        x, y = O.gen_uniform(n, n + 1)
+        P = O.Problem(x, y)
+        p = T.Problem.euc2d(ctx, x, y)
+        tours = np.stack([O.shuffle_tour(n, s) for s in range(1, min(B, 64) + 1)])
+        tours = np.concatenate([tours] * ((B + len(tours) - 1) // len(tours)))[:B].astype(np.uint32)
+        tours[B // 2, n // 3] = n + 7  # unknown position -> 0.0 (distance_matrix.rs:221-231)
+        want = O.tour_lengths(P, tours[:64]).astype(np.float32)
+        got = p.tour_lengths(tours, T.LEN_EXACT)
+        assert got[B // 2] == 0.0
+        m = np.ones(B, dtype=bool)
+        m[B // 2] = False
+        ref = np.concatenate([want] * ((B + 63) // 64))[:B]
+        assert (bits(got[m]) == bits(ref[m])).all(), (n, B)
+        fast = p.tour_lengths(tours, T.LEN_FAST)
+        assert np.allclose(fast[m], ref[m], rtol=1e-5)
+
+
+def test_k1_nint_integer_path_equals_f64_path(T, ctx, monkeypatch):
+    """Integer coordinates take the 32-bit integer TSPLIB nint (no FP64 pipe); it must equal both the
+    oracle and the library's own f64 path, also at distances 0, 1, r(r+1) boundaries and 1.48e6."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    x = rng.integers(0, 1048577, n).astype(np.float32)
+    y = rng.integers(0, 1048577, n).astype(np.float32)
+    x[:3], y[:3] = [0, 1048576, 0], [0, 1048576, 0]
+    # pairs with d2 = r(r+1) and r(r+1)+1 (the rounding boundary): (0,0)-(r, .) with small offsets
+    for k, r in enumerate((1, 2, 3, 7, 20, 99, 1000, 65535)):
+        x[10 + 2 * k], y[10 + 2 * k] = 5000.0, 5000.0 + k
+        x[11 + 2 * k], y[11 + 2 * k] = 5000.0 + r, 5000.0 + k + (r + 1 if r < 1000 else 1)
+    want = O.matrix_packed_nint(x, y)
+    got_int = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32).matrix_packed()
+    monkeypatch.setenv("TL_NINT_F64", "1")
+    got_f64 = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32).matrix_packed()
+    assert (got_int == want).all() and (got_f64 == want).all()
+
+
+def test_nint_rejects_coordinates_that_would_overflow(T, ctx):
+    with pytest.raises(T.TeelineError):
+        T.Problem.euc2d(ctx, [0.0, np.inf, 3.0], [0.0, 1.0, 2.0], T.DIST_NINT_I32)
+    with pytest.raises(T.TeelineError):
+        T.Problem.euc2d(ctx, [0.0, 3.0e7, 3.0], [0.0, 1.0, 2.0], T.DIST_NINT_I32)
+    p = T.Problem.euc2d(ctx, [0.0, 1.0e7, 3.0], [0.0, 1.0, 2.0], T.DIST_NINT_I32)  # below 2^24: accepted
+    assert p.matrix_packed().tolist() == O.matrix_packed_nint(np.float32([0, 1e7, 3]), np.float32([0, 1, 2])).tolist()
+
+
+def test_second_large_matrix_session_reuses_the_pool(T, ctx):
+    """Two consecutive matrix sessions whose matrices together exceed nothing, but whose first block
+    stays cached in the library's pool: the size check must count the cached block as available."""
+    n = 6000
+    x, y = O.gen_uniform(n, 3)
+    p = T.Problem.euc2d(ctx, x, y)
+    for _ in range(3):
+        s = p.session(T.ALGO_TWO_OPT_BEST, O.shuffle_tour(n, 1), T.PATH_MATRIX)
+        assert s.scan() is not None
+        s.close()
