@@ -1,4 +1,4 @@
-// teeline_cli.cpp -- stand-in for `teeline solve|pipeline|solvers` (teeline-cli/src/main.rs) over the
+// teeline_cli.cpp -- stand-in for `teeline solve|pipeline|convert|solvers` (teeline-cli/src/main.rs) over the
 // C++ host mirror, for the solvers on the accelerated path.  Same argument names, same stdout
 // format ("{total:.5} {0|1}\n<ids...>\n", main.rs:645-652; JSON object :694-707), same auto-expansion
 // (`solve 2opt` = nn -> 2opt unless --no-seed, main.rs:387-397), same exit codes for config errors.
@@ -19,7 +19,7 @@ using namespace teeline::tsp;
 namespace {
 
 struct Args {
-    std::string cmd, solver, input, config, output_format = "text", distance_type, mode, path;
+    std::string cmd, solver, input, output, config, output_format = "text", distance_type, mode, path;
     std::vector<std::string> steps;
     bool no_seed = false, verbose = false;
     std::optional<size_t> epochs, platoo_epochs, n_nearest;
@@ -44,7 +44,7 @@ std::vector<std::string> split(const std::string &s, char sep)
 Args parse_args(int argc, char **argv)
 {
     Args a;
-    if (argc < 2) die("usage: teeline <solve|pipeline|solvers> ...", 2);
+    if (argc < 2) die("usage: teeline <solve|pipeline|convert|solvers> ...", 2);
     a.cmd = argv[1];
     for (int k = 2; k < argc; ++k) {
         const std::string s = argv[k];
@@ -53,6 +53,7 @@ Args parse_args(int argc, char **argv)
             return argv[++k];
         };
         if (s == "-i" || s == "--input") a.input = next("--input");
+        else if ((s == "-o" || s == "--output") && a.cmd == "convert") a.output = next("--output");
         else if (s == "--no-seed") a.no_seed = true;
         else if (s == "-v" || s == "--verbose") a.verbose = true;
         else if (s == "--output-format") a.output_format = next("--output-format");
@@ -187,6 +188,27 @@ int run_pipeline_cmd(const Args &a)
     return run_stages(cfg, a);
 }
 
+// `teeline convert -i <DiscOpt file> [-o <file or dir>]` (teeline-cli/src/main.rs:532-562, single-file form)
+int run_convert(const Args &a)
+{
+    if (a.input.empty()) die("the following required arguments were not provided: --input <PATH>", 2);
+    std::string out = a.output.empty() ? "./data/discopt" : a.output;
+    std::string stem = a.input.substr(a.input.find_last_of('/') == std::string::npos ? 0 : a.input.find_last_of('/') + 1);
+    const size_t dot = stem.find_last_of('.');
+    if (dot != std::string::npos && dot != 0) stem = stem.substr(0, dot);
+    // an output without extension (or an existing directory) is a directory: <out>/<stem>.tsp
+    const std::string leaf = out.substr(out.find_last_of('/') == std::string::npos ? 0 : out.find_last_of('/') + 1);
+    const bool has_ext = leaf.find('.') != std::string::npos && leaf.find_last_of('.') != 0;
+    if (!has_ext) {
+        std::string cmd = "mkdir -p '" + out + "'";
+        if (std::system(cmd.c_str()) != 0) die("cannot create " + out);
+        out += "/" + stem + ".tsp";
+    }
+    auto r = tsp::convert::convert_file(a.input, out);
+    if (r.is_err()) die(r.error);
+    return 0;
+}
+
 int run_solvers()
 {
     std::printf("solvers on the accelerated (CUDA, sm_100a) path of this build:\n");
@@ -208,6 +230,7 @@ int main(int argc, char **argv)
         if (a.cmd == "solve") return run_solve(a);
         if (a.cmd == "pipeline") return run_pipeline_cmd(a);
         if (a.cmd == "solvers") return run_solvers();
+        if (a.cmd == "convert") return run_convert(a);
         die("unrecognized subcommand '" + a.cmd + "'", 2);
     } catch (const std::exception &e) { // the reference would panic: exit code 101
         std::fprintf(stderr, "thread 'main' panicked: %s\n", e.what());

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cctype>
 #include <chrono>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -934,6 +935,91 @@ Result<TspLibData> read_from_str(const std::string &input)
 }
 
 } // namespace tsplib
+
+// ---- convert: DiscOpt coordinate files (src/tsp/convert.rs) --------------------------------------------------
+
+namespace convert {
+
+namespace {
+
+// Rust's `{}` for f32: the shortest decimal that round-trips, never in exponent form
+std::string f32_display(float v)
+{
+    char buf[128];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+}
+
+// Rust's str::parse::<f32>: the whole token must be a float literal (no trailing junk, no hex)
+bool parse_rust_f32(const std::string &tok, float &out)
+{
+    if (tok.empty()) return false;
+    for (char ch : tok)
+        if (ch == 'x' || ch == 'X') return false;
+    char *end = nullptr;
+    const float v = std::strtof(tok.c_str(), &end);
+    if (end == tok.c_str() || *end != '\0') return false;
+    out = v;
+    return true;
+}
+
+} // namespace
+
+// skip the first line (city count), then one `x y` pair per non-empty line (convert.rs:6-29)
+Result<std::vector<std::pair<float, float>>> parse_discopt(const std::string &input)
+{
+    using R = Result<std::vector<std::pair<float, float>>>;
+    std::vector<std::pair<float, float>> coords;
+    std::istringstream is(input);
+    std::string line;
+    bool first = true;
+    while (std::getline(is, line)) {
+        if (first) { first = false; continue; }
+        std::istringstream ls(line);
+        std::string xs, ys;
+        if (!(ls >> xs)) continue; // blank line
+        float x = 0.f, y = 0.f;
+        if (!parse_rust_f32(xs, x)) return R::err("invalid float literal");
+        if (!(ls >> ys)) return R::err("missing y");
+        if (!parse_rust_f32(ys, y)) return R::err("invalid float literal");
+        coords.emplace_back(x, y);
+    }
+    if (coords.empty()) return R::err("no coordinates found");
+    return R::ok(std::move(coords));
+}
+
+void write_tsplib(const std::string &name, const std::vector<std::pair<float, float>> &coords, std::ostream &w)
+{
+    w << "NAME: " << name << "\n";
+    w << "TYPE: TSP\n";
+    w << "COMMENT: converted from DiscOpt dataset " << name << "\n";
+    w << "DIMENSION: " << coords.size() << "\n";
+    w << "EDGE_WEIGHT_TYPE: EUC_2D\n";
+    w << "NODE_COORD_SECTION\n";
+    for (size_t i = 0; i < coords.size(); ++i)
+        w << "\t" << (i + 1) << " " << f32_display(coords[i].first) << " " << f32_display(coords[i].second) << "\n";
+    w << "EOF\n";
+}
+
+Result<bool> convert_file(const std::string &input_path, const std::string &output_path)
+{
+    std::ifstream in(input_path);
+    if (!in) return Result<bool>::err("No such file or directory (os error 2)");
+    std::stringstream ss;
+    ss << in.rdbuf();
+    auto coords = parse_discopt(ss.str());
+    if (coords.is_err()) return Result<bool>::err(coords.error);
+    // NAME = the input file stem
+    std::string stem = input_path.substr(input_path.find_last_of('/') == std::string::npos ? 0 : input_path.find_last_of('/') + 1);
+    const size_t dot = stem.find_last_of('.');
+    if (dot != std::string::npos && dot != 0) stem = stem.substr(0, dot);
+    std::ofstream out(output_path);
+    if (!out) return Result<bool>::err("cannot create " + output_path);
+    write_tsplib(stem, coords.unwrap(), out);
+    return Result<bool>::ok(true);
+}
+
+} // namespace convert
 
 // ---- a minimal TOML reader (the subset the reference's pipeline configs use) ---------------------------------
 

@@ -32,6 +32,7 @@
 #include <memory>
 #include <optional>
 #include <stdexcept>
+#include <ostream>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -249,6 +250,14 @@ struct TspLibData {
 Result<TspLibData> read_from_file(const std::string &path);
 Result<TspLibData> read_from_str(const std::string &input);
 }
+
+// DiscOpt (Coursera "Discrete Optimization") coordinate files -> TSPLIB, src/tsp/convert.rs:6-66
+namespace convert {
+Result<std::vector<std::pair<float, float>>> parse_discopt(const std::string &input);         // convert.rs:6-29
+void write_tsplib(const std::string &name, const std::vector<std::pair<float, float>> &coords,
+                  std::ostream &writer);                                                        // convert.rs:32-45
+Result<bool> convert_file(const std::string &input_path, const std::string &output_path);     // convert.rs:49-66
+} // namespace convert
 
 } // namespace tsp
 

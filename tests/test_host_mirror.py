@@ -39,6 +39,28 @@ def test_cli_builds_and_lists_solvers(bins):
     assert rc == 0 and "2opt" in out and "or_opt" in out and "nn" in out
 
 
+def test_cli_convert_discopt_fixture(bins, tmp_path):
+    """`teeline convert` on the reference's DiscOpt fixture (tests/e2e/convert.bats:18-31;
+    writer format src/tsp/convert.rs:32-45: tab, 1-based id, Rust `{}` floats)."""
+    cli = bins[0]
+    rc, _, err = run([cli, "convert", "-i", os.path.join(GOLDEN, "tiny5_discopt"), "-o", str(tmp_path)])
+    assert rc == 0, err
+    out = tmp_path / "tiny5_discopt.tsp"
+    assert out.read_text() == ("NAME: tiny5_discopt\nTYPE: TSP\nCOMMENT: converted from DiscOpt dataset tiny5_discopt\n"
+                               "DIMENSION: 5\nEDGE_WEIGHT_TYPE: EUC_2D\nNODE_COORD_SECTION\n"
+                               "\t1 0 0\n\t2 10 0\n\t3 10 10\n\t4 0 10\n\t5 5 5\nEOF\n")
+    rc, _, _ = run([cli, "convert", "-i", "/nonexistent/file"])
+    assert rc != 0
+    frac = tmp_path / "frac.txt"
+    frac.write_text("3\n0.5 1e3\n\n-2.25 0.1\n7 8\n")
+    rc, _, _ = run([cli, "convert", "-i", str(frac), "-o", str(tmp_path / "x.tsp")])
+    assert rc == 0 and "\t1 0.5 1000\n\t2 -2.25 0.1\n\t3 7 8\n" in (tmp_path / "x.tsp").read_text()
+    bad = tmp_path / "bad.txt"
+    bad.write_text("2\n1 2\n3\n")
+    rc, _, err = run([cli, "convert", "-i", str(bad), "-o", str(tmp_path)])
+    assert rc == 1 and "missing y" in err
+
+
 def test_cli_config_errors_match_reference_messages(bins, tmp_path):
     cli = bins[0]
     inp = os.path.join(GOLDEN, "berlin52.tsp")
@@ -139,6 +161,36 @@ def test_cli_goldens_berlin52(bins):
     rc, out, _ = run([cli, "solve", "2opt_best", "-i", inp])
     tb = O.two_opt_best(P, nn)[0]
     assert rc == 0 and parse_cli(out) == ("%.5f" % O.tour_length(P, tb), 0, [int(ids[p]) for p in tb])
+
+
+@pytest.mark.gpu
+def test_cli_discopt_to_solve(bins, tmp_path):
+    """DiscOpt input end to end: `teeline convert` then `teeline solve 2opt|or_opt` on the result
+    (src/tsp/convert.rs -> src/tsp/tsplib.rs -> the accelerated stages), against the oracle."""
+    cli = bins[0]
+    rc, _, err = run([cli, "convert", "-i", os.path.join(GOLDEN, "tiny5_discopt"), "-o", str(tmp_path)])
+    assert rc == 0, err
+    inp = str(tmp_path / "tiny5_discopt.tsp")
+    ids, x, y = O.read_tsplib_coords(inp)
+    assert ids.tolist() == [1, 2, 3, 4, 5] and x.tolist() == [0, 10, 10, 0, 5] and y.tolist() == [0, 0, 10, 10, 5]
+    P = O.Problem(x, y)
+    nn = O.nn_tour(P, 3)
+    for name, want in (("nn", nn), ("2opt", O.two_opt_ref(P, nn)[0]), ("or_opt", O.or_opt(P, nn)[0])):
+        rc, out, err = run([cli, "solve", name, "-i", inp])
+        assert rc == 0 and parse_cli(out) == ("%.5f" % O.tour_length(P, want), 0, [int(ids[p]) for p in want]), (name, err)
+    # a 200-city DiscOpt file with fractional coordinates
+    rng = np.random.default_rng(5)
+    pts = (rng.random((200, 2)) * 1000).astype(np.float32)
+    src = tmp_path / "rand200"
+    src.write_text("200\n" + "".join(f"{a!r} {b!r}\n" for a, b in pts.tolist()))
+    rc, _, err = run([cli, "convert", "-i", str(src), "-o", str(tmp_path / "rand200.tsp")])
+    assert rc == 0, err
+    ids, x, y = O.read_tsplib_coords(str(tmp_path / "rand200.tsp"))
+    assert (x == pts[:, 0]).all() and (y == pts[:, 1]).all()  # the shortest round-trip decimals parse back exactly
+    P = O.Problem(x, y)
+    want = O.two_opt_ref(P, O.nn_tour(P, 3))[0]
+    rc, out, _ = run([cli, "solve", "2opt", "-i", str(tmp_path / "rand200.tsp")])
+    assert rc == 0 and parse_cli(out) == ("%.5f" % O.tour_length(P, want), 0, [int(ids[p]) for p in want])
 
 
 @pytest.mark.gpu
