@@ -172,6 +172,28 @@ tl_status tl_local_search(tl_problem *p, int32_t algo, int32_t path, uint32_t *t
 tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, size_t batch,
                            int64_t max_moves, tl_stats *stats, float *lengths_out);
 
+/* ---- Ant System (population solver) ------------------------------- */
+
+/* Replaces the body of ant_colony::solve (src/tsp/ant_colony.rs:92-239): roulette construction of
+ * num_ants tours per epoch over tau^alpha * eta^beta, evaporate-and-floor, per-ant deposits,
+ * incumbent update; tour costs are the exact-order sums of tl_tour_lengths.  The reference draws
+ * from an unseeded RNG; here every draw is Philox4x32-10(seed; step, ant, epoch), so a run is
+ * reproducible.  Option defaults and validation follow AcoOptions (src/tsp/mod.rs:1083-1153).
+ * init_tour (nullable): as `init_tour` of the reference (seeds the incumbent, tau0 = num_ants/cost
+ * and one deposit); null: a Philox-shuffled start and tau0 = 1.  Coordinate (F32_EXACT) and
+ * EXPLICIT problems. */
+typedef struct {
+    float alpha;            /* >= 0, default 1                     */
+    float beta;             /* in [0, 6], default 2                */
+    float evaporation_rate; /* in (0, 1), default 0.5              */
+    uint32_t num_ants;      /* >= 1, default 25                    */
+    uint32_t epochs;        /* default 150                         */
+    uint32_t pad;
+    uint64_t seed;
+} tl_aco_options;
+tl_status tl_aco(tl_problem *p, const tl_aco_options *opts, const uint32_t *init_tour, uint32_t *best_tour_out,
+                 float *best_cost_out, tl_stats *stats);
+
 /* ---- local search, device-resident session (benchmarks, pipelines) ---------------- */
 
 tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uint32_t *tour,

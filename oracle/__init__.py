@@ -248,6 +248,30 @@ def three_opt(p: Problem, tour, max_moves: int = -1, nthreads: int = 1, log_cap:
     return t, st, mv
 
 
+class AcoOptions(C.Structure):
+    _fields_ = [("alpha", C.c_float), ("beta", C.c_float), ("evaporation_rate", C.c_float),
+                ("num_ants", C.c_int32), ("epochs", C.c_int32), ("seed", C.c_uint64)]
+
+
+def philox4x32(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    out = (C.c_uint32 * 4)()
+    lib().tlo_philox4x32(c, k, out)
+    return list(out)
+
+
+def aco(p: Problem, seed: int, init_tour=None, alpha=1.0, beta=2.0, evaporation_rate=0.5, num_ants=25, epochs=150):
+    """Ant System with the reference's defaults (mod.rs:1091-1111).  Returns (best_tour, best_cost, stats)."""
+    o = AcoOptions(alpha, beta, evaporation_rate, num_ants, epochs, seed)
+    best = np.empty(p.n, dtype=np.int32)
+    st = Stats()
+    it = _tour(init_tour) if init_tour is not None else None
+    lib().tlo_aco.restype = C.c_double
+    cost = lib().tlo_aco(p.ref, C.byref(o), _p(it) if it is not None else None, _p(best), C.byref(st))
+    return best, float(cost), st
+
+
 def gen_uniform(n: int, seed: int):
     x = np.empty(n, dtype=np.float32)
     y = np.empty(n, dtype=np.float32)

@@ -551,3 +551,205 @@ int32_t tlo_read_tsplib_coords(const char *path, int32_t cap, int64_t *ids, floa
     fclose(f);
     return n;
 }
+
+/* ---- Ant System (src/tsp/ant_colony.rs:92-239) ---------------------
+ *
+ * The reference draws from an UNSEEDED rand::rng(), so its trajectories cannot be pinned.  This
+ * restatement keeps the reference's algorithm -- tau0 / tau_min, eta^beta, tau^alpha, roulette with
+ * the eta-only and first-candidate fallbacks (select_next, :66-82), strict `acc > target`
+ * (probability.rs:70-80), `cost < best_cost` incumbent update in ant order, evaporate-and-floor then
+ * every ant deposits 1/cost (:24-56, :221-229) -- and replaces the two things that cannot be shared
+ * with a GPU implementation bit for bit:
+ *   1. the RNG: a counter-based Philox4x32-10 stream keyed by (seed), counter (step, ant, epoch,
+ *      stream); u32 -> f32 in [0,1) as (u >> 8) * 2^-24 (what rand's StandardUniform does for f32);
+ *      start city = (u * n) >> 32;
+ *   2. the ORDER of the f32 additions in the roulette sums: the reference accumulates sequentially
+ *      over the unvisited cities; here (and in csrc/k7_aco.cu) the cities are cut into 256 contiguous
+ *      chunks, each chunk is summed sequentially, the 256 partial sums are combined by a 32-wide
+ *      Kogge-Stone scan per group of 32 and a sequential scan over the 8 group totals, and the winner
+ *      is the first chunk whose inclusive prefix exceeds r*total, walked sequentially from its
+ *      exclusive prefix.  In exact arithmetic this is the reference's roulette; in f32 it differs
+ *      from it only by the rounding of the prefix sums.
+ * tau^alpha and eta^beta use exact products for exponents 0, 1, 2, 3 (the defaults are alpha = 1,
+ * beta = 2) and powf otherwise (then CPU and GPU agree only to powf's accuracy).
+ * Parity status: statistical -- tests compare the tour-cost distribution over seeds with the
+ * reference's published berlin52 result, and the CUDA path with this port bit for bit. */
+
+static inline uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t *hi)
+{
+    const uint64_t p = (uint64_t)a * b;
+    *hi = (uint32_t)(p >> 32);
+    return (uint32_t)p;
+}
+
+void tlo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, hi1;
+        const uint32_t lo0 = mulhilo32(0xD2511F53u, c0, &hi0);
+        const uint32_t lo1 = mulhilo32(0xCD9E8D57u, c2, &hi1);
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+enum { ACO_STREAM_ANT = 1, ACO_STREAM_SHUFFLE = 2, ACO_T = 256 };
+
+static inline float u32_to_unit_f32(uint32_t u) { return (float)(u >> 8) * (1.0f / 16777216.0f); }
+
+static float pow_small(float x, float e)
+{
+    if (e == 0.0f) return 1.0f;
+    if (e == 1.0f) return x;
+    if (e == 2.0f) return x * x;
+    if (e == 3.0f) return (x * x) * x;
+    return powf(x, e);
+}
+
+/* blocked roulette over the unvisited cities of one weight row; returns the selected city, or -1
+ * when the weight sum is not a positive finite number */
+static int32_t aco_blocked_select(const float *w, const uint8_t *vis, int32_t n, float r)
+{
+    const int32_t C = (n + ACO_T - 1) / ACO_T;
+    float x[ACO_T], y[ACO_T], I[ACO_T], E[ACO_T];
+    int32_t cnt[ACO_T];
+    for (int32_t t = 0; t < ACO_T; ++t) {
+        float acc = 0.0f;
+        int32_t c = 0;
+        for (int32_t v = t * C; v < (t + 1) * C && v < n; ++v)
+            if (!vis[v]) { acc = acc + w[v]; ++c; }
+        x[t] = acc;
+        cnt[t] = c;
+    }
+    for (int32_t off = 1; off < 32; off <<= 1) { /* Kogge-Stone inside each group of 32 */
+        for (int32_t t = 0; t < ACO_T; ++t) y[t] = ((t & 31) >= off) ? x[t] + x[t - off] : x[t];
+        memcpy(x, y, sizeof x);
+    }
+    float base = 0.0f;
+    for (int32_t g = 0; g < ACO_T / 32; ++g) {
+        for (int32_t l = 0; l < 32; ++l) {
+            const int32_t t = 32 * g + l;
+            I[t] = base + x[t];
+            E[t] = base + (l ? x[t - 1] : 0.0f);
+        }
+        base = base + x[32 * g + 31];
+    }
+    const float total = I[ACO_T - 1];
+    if (!(total > 0.0f) || !isfinite(total)) return -1;
+    const float target = r * total;
+    for (int32_t t = 0; t < ACO_T; ++t) {
+        if (cnt[t] > 0 && I[t] > target) {
+            float acc = E[t];
+            int32_t last = -1;
+            for (int32_t v = t * C; v < (t + 1) * C && v < n; ++v) {
+                if (vis[v]) continue;
+                acc = acc + w[v];
+                last = v;
+                if (acc > target) return v;
+            }
+            return last;
+        }
+    }
+    for (int32_t v = n - 1; v >= 0; --v)
+        if (!vis[v]) return v; /* roulette_select: rounding left the target uncrossed -> last candidate */
+    return -1;
+}
+
+static void aco_deposit_tour(float *ph, int32_t n, const int32_t *tour, float cost)
+{
+    if (n < 2 || !(cost > 0.0f)) return;
+    const float amount = 1.0f / cost;
+    for (int32_t k = 0; k < n; ++k) {
+        const int32_t u = tour[k == 0 ? n - 1 : k - 1], v = tour[k];
+        ph[(size_t)u * n + v] += amount;
+        ph[(size_t)v * n + u] += amount;
+    }
+}
+
+double tlo_aco(const tlo_problem *p, const tlo_aco_options *o, const int32_t *init_tour, int32_t *best_out,
+               tlo_stats *st)
+{
+    const int32_t n = p->n;
+    const uint32_t key[2] = {(uint32_t)o->seed, (uint32_t)(o->seed >> 32)};
+    if (st) st->passes = st->moves = st->evals = 0;
+    if (n <= 2) { /* ant_colony.rs:107-113 */
+        for (int32_t k = 0; k < n; ++k) best_out[k] = k;
+        return tlo_tour_length(p, best_out, n);
+    }
+    int32_t *best = best_out;
+    if (init_tour) {
+        memcpy(best, init_tour, sizeof(int32_t) * (size_t)n);
+    } else { /* positions.shuffle(&mut rng), :132-136 */
+        for (int32_t k = 0; k < n; ++k) best[k] = k;
+        for (int32_t i = n - 1; i > 0; --i) {
+            const uint32_t ctr[4] = {(uint32_t)i, 0u, 0u, ACO_STREAM_SHUFFLE};
+            uint32_t out[4];
+            tlo_philox4x32(ctr, key, out);
+            const int32_t j = (int32_t)(((uint64_t)out[0] * (uint64_t)(i + 1)) >> 32);
+            const int32_t t = best[i]; best[i] = best[j]; best[j] = t;
+        }
+    }
+    float best_cost = (float)tlo_tour_length(p, best, n);
+    const float tau0 = (init_tour && best_cost > 0.0f) ? (float)o->num_ants / best_cost : 1.0f;
+    const float tau_min = tau0 * 1e-4f; /* TAU_MIN_RATIO */
+    const size_t nn = (size_t)n * n;
+    float *ph = (float *)malloc(nn * 4), *eta = (float *)malloc(nn * 4), *w = (float *)malloc(nn * 4);
+    int32_t *tours = (int32_t *)malloc(sizeof(int32_t) * (size_t)n * o->num_ants);
+    float *costs = (float *)malloc(4 * (size_t)o->num_ants);
+    uint8_t *vis = (uint8_t *)malloc((size_t)n);
+    for (size_t k = 0; k < nn; ++k) ph[k] = tau0;
+    for (int32_t u = 0; u < n; ++u)
+        for (int32_t v = 0; v < n; ++v) {
+            if (u == v) { eta[(size_t)u * n + v] = 0.0f; continue; }
+            float d = (float)tlo_distance(p, u, v);
+            if (d < 1e-6f) d = 1e-6f; /* MIN_DIST */
+            eta[(size_t)u * n + v] = pow_small(1.0f / d, o->beta);
+        }
+    if (init_tour) aco_deposit_tour(ph, n, best, best_cost);
+    const float keep = 1.0f - o->evaporation_rate;
+    for (int32_t epoch = 0; epoch < o->epochs; ++epoch) {
+        for (size_t k = 0; k < nn; ++k) w[k] = pow_small(ph[k], o->alpha) * eta[k];
+        for (int32_t a = 0; a < o->num_ants; ++a) {
+            int32_t *tour = tours + (size_t)a * n;
+            uint32_t out[4];
+            const uint32_t c0[4] = {0u, (uint32_t)a, (uint32_t)epoch, ACO_STREAM_ANT};
+            tlo_philox4x32(c0, key, out);
+            int32_t cur = (int32_t)(((uint64_t)out[2] * (uint64_t)n) >> 32);
+            memset(vis, 0, (size_t)n);
+            vis[cur] = 1;
+            tour[0] = cur;
+            for (int32_t s = 1; s < n; ++s) {
+                const uint32_t cs[4] = {(uint32_t)s, (uint32_t)a, (uint32_t)epoch, ACO_STREAM_ANT};
+                tlo_philox4x32(cs, key, out);
+                const float r1 = u32_to_unit_f32(out[0]), r2 = u32_to_unit_f32(out[1]);
+                int32_t next = aco_blocked_select(w + (size_t)cur * n, vis, n, r1);
+                if (next < 0) next = aco_blocked_select(eta + (size_t)cur * n, vis, n, r2);
+                if (next < 0) /* fallback.first(): the first unvisited city */
+                    for (int32_t v = 0; v < n; ++v)
+                        if (!vis[v]) { next = v; break; }
+                vis[next] = 1;
+                tour[s] = next;
+                cur = next;
+                if (st) st->evals += n - s;
+            }
+            costs[a] = (float)tlo_tour_length(p, tour, n);
+            if (costs[a] < best_cost) {
+                best_cost = costs[a];
+                memcpy(best, tour, sizeof(int32_t) * (size_t)n);
+                if (st) st->moves++;
+            }
+        }
+        for (size_t k = 0; k < nn; ++k) { /* evaporate_and_floor */
+            ph[k] = ph[k] * keep;
+            if (ph[k] < tau_min) ph[k] = tau_min;
+        }
+        for (int32_t a = 0; a < o->num_ants; ++a) aco_deposit_tour(ph, n, tours + (size_t)a * n, costs[a]);
+        if (st) st->passes++;
+    }
+    free(ph); free(eta); free(w); free(tours); free(costs); free(vis);
+    return (double)best_cost;
+}

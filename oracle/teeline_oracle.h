@@ -119,6 +119,20 @@ void tlo_three_opt_apply(int32_t *path, int32_t i, int32_t j, int32_t k, int32_t
 void tlo_three_opt(const tlo_problem *p, int32_t *path, int64_t max_moves, int nthreads, tlo_stats *st,
                    tlo_move *log, int32_t *ks, int64_t log_cap);
 
+/* ---- Ant System (ant_colony.rs:92-239) with a seeded Philox stream and the CUDA kernel's blocked
+ * roulette sums; see the comment above tlo_aco in teeline_oracle.c.  init_tour nullable (then a
+ * Philox-shuffled start and tau0 = 1).  Returns the best cost (f32 widened); st->passes = epochs,
+ * st->moves = incumbent improvements, st->evals = roulette weights evaluated.  Parity: statistical
+ * against the reference (unseeded RNG), bit-exact between this port and the CUDA path. */
+typedef struct {
+    float alpha, beta, evaporation_rate;
+    int32_t num_ants, epochs;
+    uint64_t seed;
+} tlo_aco_options;
+void tlo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double tlo_aco(const tlo_problem *p, const tlo_aco_options *o, const int32_t *init_tour, int32_t *best_out,
+               tlo_stats *st);
+
 /* ---- synthetic inputs (BASELINE.md "Synthetic inputs") */
 uint64_t tlo_splitmix64(uint64_t *state);
 /* x,y = (splitmix64 >> 40) * (1000 / 2^24) as f32; x then y per city. */

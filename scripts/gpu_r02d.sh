@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, K2-pop first light: parity of both batched engines, then per-rank scaling of each
+out=gpurun_out/r02d
+mkdir -p $out
+echo "== pytest batch"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "batch or config5" 2>&1 | tail -15 | tee $out/pytest_batch.txt
+for eng in pop cta; do
+  echo "== batch scaling engine=$eng"; TL_BATCH_ENGINE=$eng timeout 600 python scripts/batch_scaling.py $out/batch_scaling_$eng.json 2>&1 | tee $out/batch_scaling_$eng.txt
+done
+for ch in 32 16; do
+  echo "== batch scaling engine=pop chunk=$ch"; TL_POP_CHUNK=$ch TL_BATCH_ENGINE=pop WORLDS=1,8 timeout 600 python scripts/batch_scaling.py $out/batch_scaling_pop_chunk$ch.json 2>&1 | tee $out/batch_scaling_pop_chunk$ch.txt
+done

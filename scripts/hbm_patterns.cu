@@ -128,6 +128,101 @@ __global__ void __launch_bounds__(256, MINB) rect_kernel(const int *__restrict__
     if (acc == 0x12345678) *sink = acc;
 }
 
+// rect1<D>: fixed columns like rect, but 4-byte loads (lane owns columns c0 + lane + 32 r), i.e. the
+// band walk without the one-column shift per row: every warp request is an ALIGNED 128-byte line
+// when ALIGN, and starts 4*off bytes into a line otherwise.
+template <int D, int MINB, bool ALIGN>
+__global__ void __launch_bounds__(256, MINB) rect1_kernel(const int *__restrict__ M, uint32_t ld, const Item *__restrict__ items, int nitems, int *sink)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int acc = 0;
+    for (int it = blockIdx.x * 8 + warp; it < nitems; it += gridDim.x * 8) {
+        const Item I = items[it];
+        const int cnt = I.r1 - I.r0;
+        const int base = min(I.r0 + I.k0, (int)ld - 288);
+        const int c0 = (ALIGN ? (base & ~31) : ((base & ~31) + 13)) + lane;
+        int buf[D][8];
+        auto issue = [&](int d, int t) {
+            const int *row = M + (size_t)(I.r0 + t) * ld + c0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) buf[d][r] = ld_s(row + 32 * r);
+        };
+#pragma unroll
+        for (int d = 0; d < D; ++d) if (d < cnt) issue(d, d);
+        int t = 0;
+#pragma unroll 1
+        for (; t + D <= cnt; t += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                int s = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) s += buf[d][r];
+                acc += s;
+                if (t + d + D < cnt) issue(d, t + d + D);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) if (t + d < cnt) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc += buf[d][r];
+        }
+    }
+    if (acc == 0x12345678) *sink = acc;
+}
+
+// bulk<D>: the band walk with the rows STAGED IN SHARED MEMORY BY THE TMA ENGINE: per row step one
+// lane issues ONE cp.async.bulk of the row's 1 KB window (16-byte aligned superset, 1040 B) into a ring
+// of D+1 shared-memory slots guarded by mbarriers; the lanes then read their 8 elements with LDS.
+// Outstanding bytes are tracked by the copy engine, not by per-lane LSU requests.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int D, int MINB>
+__global__ void __launch_bounds__(256, MINB) bulk_kernel(const int *__restrict__ M, uint32_t ld, const Item *__restrict__ items, int nitems, int *sink)
+{
+    constexpr int NB = D + 1, ROWB = 1024 + 16;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ring = smem + (size_t)warp * NB * ROWB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)8 * NB * ROWB) + warp * NB;
+    if (lane == 0)
+        for (int b = 0; b < NB; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t phase_bits = 0; // bit b: parity to wait for on slot b
+    int acc = 0;
+    for (int it = blockIdx.x * 8 + warp; it < nitems; it += gridDim.x * 8) {
+        const Item I = items[it];
+        const int cnt = I.r1 - I.r0;
+        auto issue = [&](int slot, int t) {
+            if (lane == 0) {
+                const size_t e0 = (size_t)(I.r0 + t) * ld + (size_t)(I.r0 + t + I.k0);
+                const char *src = reinterpret_cast<const char *>(M) + ((e0 * 4) & ~(size_t)15);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[slot])), "r"(ROWB) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ring + slot * ROWB)), "l"(src), "r"(ROWB), "r"(smem_u32(&bars[slot])) : "memory");
+            }
+        };
+        auto wait = [&](int slot) {
+            const uint32_t par = (phase_bits >> slot) & 1u;
+            asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" ::"r"(smem_u32(&bars[slot])), "r"(par) : "memory");
+            phase_bits ^= 1u << slot;
+        };
+        for (int d = 0; d < D && d < cnt; ++d) issue(d, d);
+        for (int t = 0; t < cnt; ++t) {
+            const int slot = t % NB;
+            wait(slot);
+            const size_t e0 = (size_t)(I.r0 + t) * ld + (size_t)(I.r0 + t + I.k0);
+            const int off = (int)(e0 & 3); // elements past the aligned start
+            const int *row = reinterpret_cast<const int *>(ring + slot * ROWB) + off + lane;
+            int s = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) s += row[32 * r];
+            acc += s;
+            __syncwarp(); // everyone has read slot (t-1) % NB ... before it is refilled below
+            if (t + D < cnt) issue((t + D) % NB, t + D);
+        }
+    }
+    if (acc == 0x12345678) *sink = acc;
+}
+
 template <typename F>
 static float time_it(F &&launch, int reps)
 {
@@ -186,7 +281,7 @@ int main(int argc, char **argv)
         const int ni = (int)items.size();
         const double bytes = (double)elems * 4;
         printf("n=%d grid=%d chunk=%d items=%d bytes=%.1f MB\n", n, grid_ctas, chunk, ni, bytes / 1e6);
-        auto rep = [&](const char *name, float ms) { printf("  %-22s %8.2f us  %7.1f GB/s\n", name, ms * 1e3, bytes / (ms * 1e-3) / 1e9); fflush(stdout); };
+        auto rep = [&](const char *name, float ms) { printf("  %-26s %8.2f us  %7.1f GB/s\n", name, ms * 1e3, bytes / (ms * 1e-3) / 1e9); fflush(stdout); };
         const int minb_grid = grid_ctas;
         rep("band<D=2,minb3>", time_it([&] { band_kernel<2, 3><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
         rep("band<D=3,minb3>", time_it([&] { band_kernel<3, 3><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
@@ -194,6 +289,23 @@ int main(int argc, char **argv)
         rep("band<D=2,minb4>", time_it([&] { band_kernel<2, 4><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
         rep("band<D=4,minb4>", time_it([&] { band_kernel<4, 4><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
         rep("band<D=6,minb4>", time_it([&] { band_kernel<6, 4><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
+        rep("rect1<D=4,minb3,aligned>", time_it([&] { rect1_kernel<4, 3, true><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
+        rep("rect1<D=4,minb3,offset13>", time_it([&] { rect1_kernel<4, 3, false><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
+        rep("rect1<D=3,minb3,aligned>", time_it([&] { rect1_kernel<3, 3, true><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
+        rep("rect1<D=2,minb3,aligned>", time_it([&] { rect1_kernel<2, 3, true><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
+        rep("rect1<D=4,minb4,aligned>", time_it([&] { rect1_kernel<4, 4, true><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
+        {
+            auto bulk = [&](auto kern, int Dd, const char *nm) {
+                const size_t sm = (size_t)8 * (Dd + 1) * 1040 + 8 * (Dd + 1) * 8;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                rep(nm, time_it([&] { kern<<<minb_grid, 256, sm>>>(M, ld, d_items, ni, sink); }, 50));
+            };
+            bulk(bulk_kernel<2, 3>, 2, "bulk<D=2,minb3>");
+            bulk(bulk_kernel<4, 3>, 4, "bulk<D=4,minb3>");
+            bulk(bulk_kernel<6, 3>, 6, "bulk<D=6,minb3>");
+            bulk(bulk_kernel<4, 4>, 4, "bulk<D=4,minb4>");
+            bulk(bulk_kernel<8, 4>, 8, "bulk<D=8,minb4>");
+        }
         rep("rect<D=2,minb3>", time_it([&] { rect_kernel<2, 3><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
         rep("rect<D=4,minb3>", time_it([&] { rect_kernel<4, 3><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));
         rep("rect<D=4,minb4>", time_it([&] { rect_kernel<4, 4><<<minb_grid, 256>>>(M, ld, d_items, ni, sink); }, 50));

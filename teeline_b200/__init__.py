@@ -161,6 +161,17 @@ class Problem:
                                               C.byref(st), capi.ptr(lengths)))
         return t, st, lengths
 
+    def aco(self, seed: int, init_tour=None, alpha: float = 1.0, beta: float = 2.0, evaporation_rate: float = 0.5,
+            num_ants: int = 25, epochs: int = 150):
+        """tl_aco with the reference's AcoOptions defaults: returns (best_tour, best_cost, Stats)."""
+        o = capi.AcoOptions(alpha, beta, evaporation_rate, num_ants, epochs, 0, seed)
+        best = np.empty(self.n, dtype=np.uint32)
+        cost, st = C.c_float(), Stats()
+        it = _u32(init_tour) if init_tour is not None else None
+        capi.check(self._lib.tl_aco(self.h, C.byref(o), capi.ptr(it) if it is not None else None, capi.ptr(best),
+                                    C.byref(cost), C.byref(st)))
+        return best, float(cost.value), st
+
     def session(self, algo: int, tour, path: int = PATH_AUTO) -> "Session":
         return Session(self, algo, path, tour)
 

@@ -146,6 +146,8 @@ struct DevBuf {
 };
 
 bool tour_is_permutation(const uint32_t *tour, uint32_t n);
+// K2-pop work decomposition (k2_two_opt_pop.cu): item count of one scan; fills band_first
+int two_opt_pop_geometry(uint32_t n, int cyclic, int *chunk_out, std::vector<int32_t> &band_first);
 
 // Nothing is thrown across the C ABI: every extern "C" body that can allocate on the host runs
 // inside this guard (std::bad_alloc -> TL_ERR_NOMEM, anything else -> TL_ERR_INVALID).

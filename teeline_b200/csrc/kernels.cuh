@@ -246,6 +246,57 @@ void launch_two_opt_batch(int cfg, const float2 *xy, uint32_t *tours, uint32_t n
                           long long max_moves, float screen_margin, void *counters, int grid, bool fast,
                           cudaStream_t st);
 
+// K2-pop: population 2-opt scheduled at work-item granularity over the whole GPU (k2_two_opt_pop.cu)
+constexpr int kPopR = 5;        // diagonals per lane (odd => conflict-free LDS.128)
+constexpr int kPopTI = 96;      // rows per work item (default; TL_POP_CHUNK overrides up to kPopMaxTI)
+constexpr int kPopMaxTI = 128;  // two tiles per warp: 8 x 2 x (2*128 + 162) x 16 B = 107 KB per CTA
+constexpr int kPopWarps = 8;
+constexpr int kPopMinBlocks = 3;
+constexpr int kPopBandCap = 512; // band table entries in shared memory (n <= 65535)
+struct __align__(32) PopTourCtl {
+    uint32_t ticket;          // (unused since the FIFO scheduler)
+    uint32_t done;            // items of the current scan completed
+    unsigned long long best;  // min over the scan of (order-preserving delta bits << 32 | i*n + j); ~0 = none
+    uint32_t moves;           // moves applied to this tour
+    uint32_t state;           // 0 active, 1 converged, 2 stopped by max_moves
+    uint32_t pad[2];
+};
+struct PopCounters {
+    unsigned long long moves, scans;
+    uint32_t active, unconverged;
+    unsigned long long head;  // work-item slots handed out (slot / items_per_scan = FIFO entry)
+    unsigned long long tail;  // FIFO entries published
+    uint32_t error, pad;      // 1: the ring wrapped past an unread entry
+};
+size_t two_opt_pop_smem_bytes(int chunk);
+cudaError_t two_opt_pop_configure();
+uint32_t two_opt_pop_npad(uint32_t n);
+bool two_opt_pop_supported(uint32_t n);
+uint32_t two_opt_pop_queue_cap(uint64_t batch);
+void launch_pop_init(const float2 *xy, const uint32_t *tours, uint32_t n, uint32_t npad, uint64_t batch, int cyclic,
+                     bool fast, Pt *recs, PopTourCtl *ctl, PopCounters *ctr, unsigned long long *queue, uint32_t qcap,
+                     int sm_count, cudaStream_t st);
+void launch_pop_extract(const Pt *recs, uint32_t n, uint32_t npad, uint64_t batch, uint32_t *tours, int sm_count,
+                        cudaStream_t st);
+void launch_two_opt_pop(Pt *recs, PopTourCtl *ctl, PopCounters *ctr, uint32_t n, uint32_t npad, uint64_t batch,
+                        int cyclic, long long max_moves, float screen_margin, int chunk, int nbands, int nitems,
+                        const int32_t *band_first, unsigned long long *queue, uint32_t qcap, bool fast, int sm_count,
+                        cudaStream_t st);
+
+// K7: Ant System (k7_aco.cu)
+void aco_philox_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]);
+int aco_stream_shuffle();
+void launch_aco_eta(const float2 *xy, const float *tri, uint32_t n, bool fast, float beta, float *eta, int sm_count,
+                    cudaStream_t st);
+void launch_aco_fill(float *p, size_t count, float v, int sm_count, cudaStream_t st);
+void launch_aco_weights(const float *ph, const float *eta, size_t count, float alpha, float *w, int sm_count,
+                        cudaStream_t st);
+void launch_aco_evaporate(float *ph, size_t count, float keep, float tau_min, int sm_count, cudaStream_t st);
+cudaError_t launch_aco_construct(const float *w, const float *eta, uint32_t n, uint32_t ants, uint32_t epoch,
+                                 uint64_t seed, uint32_t *tours, cudaStream_t st);
+void launch_aco_update(float *ph, uint32_t n, const uint32_t *tours, const float *costs, uint32_t ants,
+                       uint32_t *best_tour, float *best_cost, unsigned long long *improvements, cudaStream_t st);
+
 // K4
 void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, const uint32_t *tours,
                              uint64_t batch, bool fast_sqrt, bool fast_mode, float *out, int sm_count,

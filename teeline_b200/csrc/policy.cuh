@@ -12,7 +12,10 @@
 
 namespace tl {
 
-template <bool FAST>
+// CG: record loads bypass L1 (ld.global.cg).  Needed when the same records are rewritten by other
+// SMs within one kernel (K2-pop: whichever worker finishes a scan applies the move), because L1 is
+// not coherent across SMs.
+template <bool FAST, bool CG = false>
 struct EucPol {
     using V = float;
     using Rec = Pt;
@@ -21,7 +24,15 @@ struct EucPol {
     };
     Pt *pts;
 
-    __device__ __forceinline__ Rec load(uint32_t q) const { return pts[q]; }
+    __device__ __forceinline__ Rec load(uint32_t q) const
+    {
+        if constexpr (CG) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(pts + q));
+            return Pt{v.x, v.y, __float_as_int(v.z), v.w};
+        } else {
+            return pts[q];
+        }
+    }
     __device__ __forceinline__ const Rec *base() const { return pts; }
     static __device__ __forceinline__ Col col(const Rec &r) { return Col{r.x, r.y}; }
     static __device__ __forceinline__ V sp(const Rec &r) { return r.sp; }

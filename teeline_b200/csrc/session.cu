@@ -30,6 +30,7 @@ cudaError_t configure_all_kernels()
     if (e == cudaSuccess) e = or_scan_configure();
     if (e == cudaSuccess) e = scan_matrix_configure();
     if (e == cudaSuccess) e = two_opt_batch_configure();
+    if (e == cudaSuccess) e = two_opt_pop_configure();
     return e;
 }
 
@@ -920,8 +921,26 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
         return TL_ERR_UNSUPPORTED;
     }
     if (batch > 0xffffffffull) { set_error("tl_two_opt_batch: batch too large"); return TL_ERR_INVALID; }
-    if (two_opt_batch_smem_bytes(p->n) > (size_t)kBatchMaxSmem) {
-        set_error("tl_two_opt_batch: n = %u does not fit one CTA's shared memory; use tl_local_search per tour", p->n);
+    // Two engines with identical results.  The CTA-per-tour kernel (k2_two_opt_batch.cu) keeps a tour
+    // in one CTA's shared memory for its whole search and is the faster one wherever it applies
+    // (1024 x 1000: 401 vs 451 ms; 128 x 1000: 70 vs 109 ms, profiles/r02k_batch_phases.txt).  K2-pop
+    // (k2_two_opt_pop.cu) schedules single work items of single scans over every warp of the GPU from
+    // tour records in global memory: it takes over when a tour does not fit one CTA's shared memory
+    // (n > ~12 000, up to 65 535).  TL_BATCH_ENGINE=pop|cta overrides.
+    const bool fits_cta = two_opt_batch_smem_bytes(p->n) <= (size_t)kBatchMaxSmem;
+    bool use_pop = !fits_cta && two_opt_pop_supported(p->n);
+    if (const char *ev = getenv("TL_BATCH_ENGINE")) {
+        if (!strcmp(ev, "cta")) use_pop = false;
+        if (!strcmp(ev, "pop")) {
+            if (!two_opt_pop_supported(p->n)) {
+                set_error("tl_two_opt_batch: TL_BATCH_ENGINE=pop does not support n = %u", p->n);
+                return TL_ERR_UNSUPPORTED;
+            }
+            use_pop = true;
+        }
+    }
+    if (!use_pop && p->n >= 4 && two_opt_batch_smem_bytes(p->n) > (size_t)kBatchMaxSmem) {
+        set_error("tl_two_opt_batch: n = %u is beyond both batched engines (65 535 cities); use tl_local_search per tour", p->n);
         return TL_ERR_UNSUPPORTED;
     }
     if (stats) memset(stats, 0, sizeof *stats);
@@ -940,8 +959,9 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
     DevBuf<uint32_t> d_t;
     DevBuf<float> d_len;
     DevBuf<unsigned char> d_ctr;
+    const size_t ctr_bytes = std::max(two_opt_batch_counter_bytes(), sizeof(PopCounters));
     if (d_t.alloc(batch * n) != cudaSuccess || d_len.alloc(batch) != cudaSuccess ||
-        d_ctr.alloc(two_opt_batch_counter_bytes()) != cudaSuccess) {
+        d_ctr.alloc(ctr_bytes) != cudaSuccess) {
         set_error("tl_two_opt_batch: device allocation failed");
         return TL_ERR_NOMEM;
     }
@@ -951,17 +971,46 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
     TL_CUDA_TRY(cudaEventCreate(&e1));
     cudaStream_t st = c->stream;
     cudaError_t e = cudaMemcpyAsync(d_t.p, tours_inout, batch * n * 4, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_ctr.p, 0, two_opt_batch_counter_bytes(), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_ctr.p, 0, ctr_bytes, st);
     if (e == cudaSuccess) e = cudaEventRecord(e0, st);
-    if (e == cudaSuccess && n >= 4) { // n < 4: nothing to scan, tours come back unchanged
+    DevBuf<Pt> d_recs;
+    DevBuf<PopTourCtl> d_ctl;
+    DevBuf<int32_t> d_bands;
+    DevBuf<unsigned long long> d_queue;
+    if (e == cudaSuccess && n >= 4 && max_moves != 0) { // n < 4: nothing to scan, tours come back unchanged
         const float m = p->dmax * kScreenMarginScale;
         const float margin =
             (p->fast_sqrt && std::isfinite(m) && p->dmax >= kScreenMinDmax && !getenv("TL_NO_SCREEN")) ? m : -1.0f;
-        const int cfg = two_opt_batch_config(n, batch, c->sm_count);
-        const int grid = two_opt_batch_grid(cfg, n, batch, c->sm_count, p->fast_sqrt, margin >= 0.0f);
-        launch_two_opt_batch(cfg, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p, grid, p->fast_sqrt, st);
-        c->launches++;
-        e = cudaGetLastError();
+        if (use_pop) {
+            std::vector<int32_t> bf;
+            int chunk = 0;
+            const int nitems = two_opt_pop_geometry(n, cyclic, &chunk, bf);
+            const uint32_t npad = two_opt_pop_npad(n);
+            const uint32_t qcap = two_opt_pop_queue_cap(batch);
+            if (d_recs.alloc(batch * npad) != cudaSuccess || d_ctl.alloc(batch) != cudaSuccess ||
+                d_bands.alloc(bf.size()) != cudaSuccess || d_queue.alloc(qcap) != cudaSuccess) {
+                cudaGetLastError();
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+                set_error("tl_two_opt_batch: device allocation failed (%.1f MB of tour records)", batch * npad * 16.0 / 1e6);
+                return TL_ERR_NOMEM;
+            }
+            e = cudaMemcpyAsync(d_bands.p, bf.data(), bf.size() * 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st); // bf is a local
+            launch_pop_init(p->d_xy, d_t.p, n, npad, batch, cyclic, p->fast_sqrt, d_recs.p, d_ctl.p,
+                            reinterpret_cast<PopCounters *>(d_ctr.p), d_queue.p, qcap, c->sm_count, st);
+            launch_two_opt_pop(d_recs.p, d_ctl.p, reinterpret_cast<PopCounters *>(d_ctr.p), n, npad, batch, cyclic,
+                               max_moves, margin, chunk, (int)bf.size() - 1, nitems, d_bands.p, d_queue.p, qcap,
+                               p->fast_sqrt, c->sm_count, st);
+            launch_pop_extract(d_recs.p, n, npad, batch, d_t.p, c->sm_count, st);
+            c->launches += 3;
+        } else {
+            const int cfg = two_opt_batch_config(n, batch, c->sm_count);
+            const int grid = two_opt_batch_grid(cfg, n, batch, c->sm_count, p->fast_sqrt, margin >= 0.0f);
+            launch_two_opt_batch(cfg, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p, grid, p->fast_sqrt, st);
+            c->launches++;
+        }
+        if (e == cudaSuccess) e = cudaGetLastError();
     }
     if (e == cudaSuccess && lengths_out) {
         launch_tour_lengths_f32(p->d_xy, nullptr, n, d_t.p, batch, p->fast_sqrt, false, d_len.p, c->sm_count, st);
@@ -972,12 +1021,15 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
     if (e == cudaSuccess) e = cudaMemcpyAsync(tours_inout, d_t.p, batch * n * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && lengths_out) e = cudaMemcpyAsync(lengths_out, d_len.p, batch * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_ctr.p, sizeof h, cudaMemcpyDeviceToHost, st);
+    PopCounters hp{};
+    if (e == cudaSuccess && use_pop) e = cudaMemcpyAsync(&hp, d_ctr.p, sizeof hp, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     float ms = 0.f;
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (e != cudaSuccess) { set_error("tl_two_opt_batch: %s", cudaGetErrorString(e)); return TL_ERR_CUDA; }
+    if (hp.error) { set_error("tl_two_opt_batch: work queue overrun (a worker stalled)"); return TL_ERR_CUDA; }
     if (stats) {
         const uint64_t nn = n;
         const uint64_t pairs = n < 4 ? 0 : (cyclic ? nn * (nn - 3) / 2 : (nn - 3) * (nn - 2) / 2);

@@ -594,18 +594,32 @@ def test_matrix_scan_only_10k_f32_and_i32(T, ctx):
 # ---- K2-batch: one CTA per tour, whole search in one launch (multi-start / GA population) ------------
 
 def check_batch(T, ctx, x, y, tours, cyclic=False, max_moves=-1):
+    """Both batched engines -- K2-pop (work items of single scans scheduled over the whole GPU) and the
+    CTA-per-tour kernel -- against the oracle's complete searches, tour by tour."""
     P = O.Problem(x, y)
     p = T.Problem.euc2d(ctx, x, y)
     algo = T.ALGO_TWO_OPT_BEST_CYCLIC if cyclic else T.ALGO_TWO_OPT_BEST
-    got, st, lengths = p.two_opt_batch(tours, algo, max_moves=max_moves)
-    moves = passes = evals = 0
-    for b, start in enumerate(tours):
-        want_t, want_st, _ = O.two_opt_best(P, start, cyclic=cyclic, max_moves=max_moves, nthreads=4)
-        assert (got[b].astype(np.int64) == want_t).all(), f"tour {b} differs"
-        assert bits(lengths[b:b + 1])[0] == bits(np.float32(O.tour_length(P, want_t)))[0]
-        moves, passes, evals = moves + want_st.moves, passes + want_st.passes, evals + want_st.evals
-    assert (int(st.moves), int(st.passes), int(st.evals)) == (moves, passes, evals)
-    assert int(st.launches) == 2  # the whole batch is ONE search launch + ONE length launch
+    want = [O.two_opt_best(P, start, cyclic=cyclic, max_moves=max_moves, nthreads=4) for start in tours]
+    moves = sum(w[1].moves for w in want)
+    passes = sum(w[1].passes for w in want)
+    evals = sum(w[1].evals for w in want)
+    saved = os.environ.get("TL_BATCH_ENGINE")
+    forced = [saved] if saved else ["pop", "cta"]
+    try:
+        for engine in forced:
+            os.environ["TL_BATCH_ENGINE"] = engine
+            got, st, lengths = p.two_opt_batch(tours, algo, max_moves=max_moves)
+            for b, (want_t, _, _) in enumerate(want):
+                assert (got[b].astype(np.int64) == want_t).all(), f"{engine}: tour {b} differs"
+                assert bits(lengths[b:b + 1])[0] == bits(np.float32(O.tour_length(P, want_t)))[0], engine
+            assert (int(st.moves), int(st.passes), int(st.evals)) == (moves, passes, evals), engine
+            # the whole batch is ONE search launch (+ record set-up/extraction for K2-pop) + ONE length launch
+            assert int(st.launches) == (4 if engine == "pop" and len(x) >= 4 and max_moves != 0 else 2), engine
+    finally:
+        if saved is None:
+            os.environ.pop("TL_BATCH_ENGINE", None)
+        else:
+            os.environ["TL_BATCH_ENGINE"] = saved
     return got, st
 
 
@@ -919,7 +933,7 @@ def test_config5_full_population_to_local_optimum(T, ctx):
     tours = np.stack([O.nn_tour(P, 3)] + [O.shuffle_tour(n, s) for s in range(1, B)])
     before = p.tour_lengths(tours)
     got, st, lengths = p.two_opt_batch(tours, T.ALGO_TWO_OPT_BEST)
-    assert st.converged == 1 and int(st.launches) == 2
+    assert st.converged == 1 and int(st.launches) <= 4
     assert (np.sort(got, axis=1) == np.arange(n, dtype=np.uint32)[None, :]).all()
     assert (lengths <= before).all() and (bits(lengths) == bits(p.tour_lengths(got))).all()
     moves = 0
@@ -993,3 +1007,108 @@ def test_second_large_matrix_session_reuses_the_pool(T, ctx):
         s = p.session(T.ALGO_TWO_OPT_BEST, O.shuffle_tour(n, 1), T.PATH_MATRIX)
         assert s.scan() is not None
         s.close()
+
+
+# ---- K7 Ant System (ant_colony.rs) ------------------------------------------
+#
+# The reference's RNG is unseeded and it publishes no ACO result (docs/benchmarks.md:52 "to be
+# measured"; its own tests only check tour validity, tests/ant_colony_test.rs), so parity here is:
+# the CUDA path equals the oracle port -- same Philox stream, same order of f32 additions -- bit for
+# bit (best tour and best cost), over many seeds, plus the reference's validity properties.
+
+def check_aco(T, prob, P, seed, init=None, **kw):
+    want_t, want_c, _ = O.aco(P, seed, init_tour=init, **kw)
+    got_t, got_c, st = prob.aco(seed, init_tour=init, **kw)
+    assert sorted(got_t.tolist()) == list(range(P.n))
+    assert (got_t.astype(np.int64) == want_t).all(), (seed, kw)
+    assert np.float32(got_c) == np.float32(want_c) == np.float32(O.tour_length(P, got_t)), (seed, kw)
+    return got_t, got_c, st
+
+
+def test_aco_berlin52_defaults_equal_the_oracle_port(T, ctx, berlin52):
+    _, x, y = berlin52
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    nn = O.nn_tour(P, 3)
+    for seed in range(6):
+        _, c, st = check_aco(T, prob, P, seed, init=nn)  # AcoOptions::default(): 150 epochs, 25 ants
+        assert c <= np.float32(O.tour_length(P, nn)) and int(st.passes) == 150
+    for seed in (100, 101):
+        check_aco(T, prob, P, seed, init=None, epochs=40)  # no init tour: Philox-shuffled start, flat tau0 = 1
+
+
+def test_aco_distribution_over_200_seeds(T, ctx, berlin52):
+    """200 seeded runs (30 epochs, 10 ants, shuffled warm start as `teeline solve aco` supplies): every
+    run equals the oracle port; the spread is sane (all valid, none worse than its start, mean gap to
+    the f32 optimum 7544.37 below 25 %)."""
+    _, x, y = berlin52
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    costs = []
+    for seed in range(200):
+        init = O.shuffle_tour(52, 1000 + seed)
+        _, c, _ = check_aco(T, prob, P, seed, init=init, epochs=30, num_ants=10)
+        assert c <= np.float32(O.tour_length(P, init))
+        costs.append(c)
+    assert np.mean(costs) < 7544.37 * 1.25 and min(costs) >= 7544.36
+
+
+@pytest.mark.parametrize("n,epochs,ants", [(3, 5, 4), (4, 5, 3), (257, 6, 7), (300, 10, 25), (1000, 3, 25)])
+def test_aco_synthetic_sizes(T, ctx, n, epochs, ants):
+    x, y = O.gen_uniform(n, 900 + n)
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    check_aco(T, prob, P, 7, init=O.shuffle_tour(n, 3), epochs=epochs, num_ants=ants)
+    check_aco(T, prob, P, 8, init=None, epochs=epochs, num_ants=ants)
+
+
+def test_aco_exponents_explicit_and_degenerate_weights(T, ctx, golden_dir):
+    x, y = O.gen_uniform(120, 5)
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    init = O.shuffle_tour(120, 1)
+    for alpha, beta in ((2.0, 3.0), (0.0, 1.0), (3.0, 0.0)):  # exact-product exponents: bit-equal
+        check_aco(T, prob, P, 3, init=init, alpha=alpha, beta=beta, epochs=8)
+    got_t, got_c, _ = prob.aco(3, init_tour=init, alpha=1.5, beta=2.5, epochs=8)  # powf: validity only
+    assert sorted(got_t.tolist()) == list(range(120)) and got_c <= np.float32(O.tour_length(P, init))
+    n, tri = read_explicit(os.path.join(golden_dir, "gr17.tsp"))
+    check_aco(T, T.Problem.explicit(ctx, tri, n), O.Problem(tri=tri, n=n), 5, init=np.arange(n), epochs=20)
+    # distances so large that eta^beta underflows to 0: primary and fallback sums are both 0 and every
+    # step takes `fallback.first()`, the first unvisited city (select_next, ant_colony.rs:66-82)
+    big = (tri * 0 + 1e25).astype(np.float32)
+    pe, Pe = T.Problem.explicit(ctx, big, n), O.Problem(tri=big, n=n)
+    t, _, _ = check_aco(T, pe, Pe, 9, init=None, epochs=2, num_ants=3)
+    # coincident cities: eta = (1 / MIN_DIST)^2 = 1e12 on their edges
+    xd, yd = x.copy(), y.copy()
+    xd[:10], yd[:10] = xd[0], yd[0]
+    check_aco(T, T.Problem.euc2d(ctx, xd, yd), O.Problem(xd, yd), 4, init=init, epochs=6)
+
+
+def test_aco_reference_edge_cases_and_option_validation(T, ctx):
+    # n <= 2: identity order (ant_colony.rs:107-113)
+    p2 = T.Problem.euc2d(ctx, [0.0, 1.0], [0.0, 1.0])
+    t, c, _ = p2.aco(1)
+    assert t.tolist() == [0, 1] and abs(c - 2 * 2 ** 0.5) < 1e-6
+    # epochs = 0: the warm start comes back untouched (test_aco_respects_initial_tour, :358-381)
+    p5 = T.Problem.euc2d(ctx, [0.0, 0.0, 0.0, 1.0, 1.0], [0.0, 0.5, 1.0, 1.0, 0.0])
+    t, c, _ = p5.aco(1, init_tour=[0, 1, 2, 3, 4], epochs=0)
+    assert t.tolist() == [0, 1, 2, 3, 4] and c == 4.0
+    for kw, msg in (({"alpha": -1.0}, "alpha must be >= 0"), ({"beta": 7.0}, "beta must be in [0, 6]"),
+                    ({"evaporation_rate": 1.0}, "evaporation_rate must be in (0, 1)"),
+                    ({"num_ants": 0}, "num_ants must be >= 1"), ({"alpha": float("nan")}, "alpha must be >= 0")):
+        with pytest.raises(T.TeelineError) as ei:
+            p5.aco(1, **kw)
+        assert msg in str(ei.value)
+    with pytest.raises(T.TeelineError):
+        p5.aco(1, init_tour=[0, 1, 2, 3, 3])
+
+
+def test_batch_beyond_one_cta_takes_the_population_engine(T, ctx):
+    """n = 13 000 does not fit one CTA's shared memory: tl_two_opt_batch switches to K2-pop (tour
+    records in global memory, work items scheduled over the whole GPU); same moves as the oracle."""
+    n = 13000
+    x, y = O.gen_uniform(n, n)
+    P, p = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    tours = np.stack([O.shuffle_tour(n, s) for s in (1, 2, 3)])
+    got, st, lengths = p.two_opt_batch(tours, max_moves=4)
+    assert int(st.moves) == 12 and int(st.launches) == 4
+    for b in range(3):
+        want_t, _, _ = O.two_opt_best(P, tours[b], max_moves=4, nthreads=NCPU)
+        assert (got[b].astype(np.int64) == want_t).all(), b
+    assert (bits(lengths) == bits(p.tour_lengths(got))).all()

@@ -261,3 +261,35 @@ def test_three_opt_threads_agree_and_improves():
     assert a == b and a is not None and ev1 == ev2 == 90 * 89 * 88 // 6 - 88
     t2 = O.three_opt_apply(t, a[1], a[2], a[3], a[4])
     assert np.float32(O.tour_length(P, t2)) < np.float32(O.tour_length(P, t))
+
+
+# ---- Ant System port: the pieces the reference pins with unit tests (ant_colony.rs:258-330) ----------
+
+def test_philox_known_answers():
+    """Philox4x32-10 against the Random123 known-answer vectors."""
+    assert O.philox4x32([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert O.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert O.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_aco_port_properties(berlin52):
+    """Validity and monotonicity the reference's own tests ask for (tests/ant_colony_test.rs:43-95,
+    ant_colony.rs:358-381): a permutation, cost == recomputed length, never worse than the warm start,
+    epochs = 0 returns the warm start, reproducible for a seed, different across seeds."""
+    _, x, y = berlin52
+    P = O.Problem(x, y)
+    nn = O.nn_tour(P, 3)
+    a, ca, _ = O.aco(P, 1, init_tour=nn, epochs=40)
+    b, cb, _ = O.aco(P, 1, init_tour=nn, epochs=40)
+    c, cc, _ = O.aco(P, 2, init_tour=nn, epochs=40)
+    assert sorted(a.tolist()) == list(range(52)) and (a == b).all() and ca == cb
+    assert ca <= O.tour_length(P, nn) and abs(O.tour_length(P, a) - ca) < 1e-6
+    assert not (a == c).all() or ca != cc
+    z, cz, _ = O.aco(P, 1, init_tour=nn, epochs=0)
+    assert (z == nn).all() and cz == O.tour_length(P, nn)
+    s, cs_, _ = O.aco(P, 3, init_tour=None, epochs=30)  # flat tau0 = 1 path (ant_colony.rs:152-158)
+    assert sorted(s.tolist()) == list(range(52)) and cs_ > 0
+    sq = O.Problem(np.float32([0, 1]), np.float32([0, 1]))
+    t2, c2, _ = O.aco(sq, 1)
+    assert t2.tolist() == [0, 1]
