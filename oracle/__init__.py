@@ -272,6 +272,30 @@ def aco(p: Problem, seed: int, init_tour=None, alpha=1.0, beta=2.0, evaporation_
     return best, float(cost), st
 
 
+class GaOptions(C.Structure):
+    _fields_ = [("mutation_probability", C.c_float), ("n_elite", C.c_int32), ("epochs", C.c_int32),
+                ("pad", C.c_int32), ("seed", C.c_uint64)]
+
+
+def ox_genes(p1, p2, frm: int, to: int):
+    """ordered_crossover_genes (genetic_algorithm.rs:140-176)."""
+    a, b = _tour(p1), _tour(p2)
+    g1, g2 = np.empty_like(a), np.empty_like(b)
+    lib().tlo_ox_genes(_p(a), _p(b), C.c_int32(len(a)), C.c_int32(frm), C.c_int32(to), _p(g1), _p(g2))
+    return g1, g2
+
+
+def ga(p: Problem, seed: int, init_tour=None, mutation_probability=0.001, n_elite=3, epochs=10000):
+    """GA with the reference's GAOptions defaults.  Returns (best_tour, best_length, stats)."""
+    o = GaOptions(mutation_probability, n_elite, epochs, 0, seed)
+    best = np.empty(p.n, dtype=np.int32)
+    st = Stats()
+    it = _tour(init_tour) if init_tour is not None else None
+    lib().tlo_ga.restype = C.c_double
+    cost = lib().tlo_ga(p.ref, C.byref(o), _p(it) if it is not None else None, _p(best), C.byref(st))
+    return best, float(cost), st
+
+
 def gen_uniform(n: int, seed: int):
     x = np.empty(n, dtype=np.float32)
     y = np.empty(n, dtype=np.float32)

@@ -753,3 +753,201 @@ double tlo_aco(const tlo_problem *p, const tlo_aco_options *o, const int32_t *in
     free(ph); free(eta); free(w); free(tours); free(costs); free(vis);
     return (double)best_cost;
 }
+
+/* ---- Genetic algorithm population step (src/tsp/genetic_algorithm.rs) ---
+ *
+ * Restates solve / solve_ga (:16-107): population = n tours; per epoch a STABLE sort by fitness
+ * descending (:68, :277-280), n_elite elites, then pop/2 - n_elite times: two roulette selections over
+ * the sorted fitnesses (random_selection, :283-299), ordered crossover of the two parents
+ * (ordered_crossover_genes, :140-176, pinned by the book examples :458-475), children's fitness =
+ * 1/tour_length computed BEFORE the optional mutation (the reference never refreshes it, :78-83),
+ * mutation = reversal of a random_position_pair segment (:320-328, route.rs:69-100); best() = the
+ * LAST individual of maximal fitness (Iterator::max_by, :264-269).
+ * As for tlo_aco, the unseeded rand::rng() is replaced by Philox4x32-10 keyed by the seed (counter =
+ * (a, b, c, stream), listed at each draw) and the roulette prefix sums are taken in the blocked order
+ * of the CUDA kernel (256 chunks, Kogge-Stone per 32, sequential over the 8 groups), so that the CUDA
+ * path (csrc/k8_ga.cu) can be compared with this port bit for bit.  Parity status vs the reference:
+ * statistical only (its trajectories are unseeded); the crossover operator itself is pinned by the
+ * reference's unit vectors. */
+
+enum { GA_SHUFFLE = 16, GA_SEEDMUT = 17, GA_SEEDPAIR = 18, GA_SELECT = 19, GA_XPAIR = 20, GA_MUTP = 21, GA_MUTPAIR = 22 };
+
+static inline uint32_t bounded_u32(uint32_t u, uint32_t n) { return (uint32_t)(((uint64_t)u * (uint64_t)n) >> 32); }
+
+/* route.rs:69-100: up to 11 sorted pairs, the first with to - from > 1 (else the last one drawn);
+ * draw t uses counter (a, b, c0 + t, stream) */
+static void ga_position_pair(const uint32_t key[2], uint32_t a, uint32_t b, uint32_t c0, uint32_t stream, uint32_t len,
+                             uint32_t *from, uint32_t *to)
+{
+    for (uint32_t t = 0; t <= 10; ++t) {
+        const uint32_t ctr[4] = {a, b, c0 + t, stream};
+        uint32_t out[4];
+        tlo_philox4x32(ctr, key, out);
+        const uint32_t p1 = bounded_u32(out[0], len), p2 = bounded_u32(out[1], len);
+        *from = p1 < p2 ? p1 : p2;
+        *to = p1 < p2 ? p2 : p1;
+        if (*to - *from > 1) break;
+    }
+}
+
+static void ga_reverse(int32_t *g, uint32_t from, uint32_t to) /* TspGenotype::mutate, :320-328 */
+{
+    while (from < to) {
+        const int32_t t = g[from]; g[from] = g[to]; g[to] = t;
+        ++from; --to;
+    }
+}
+
+void tlo_ox_genes(const int32_t *p1, const int32_t *p2, int32_t len, int32_t from, int32_t to, int32_t *g1, int32_t *g2)
+{
+    /* ordered_crossover_genes, genetic_algorithm.rs:140-176 (values are arbitrary labels) */
+    int32_t maxv = 0;
+    for (int32_t k = 0; k < len; ++k) { if (p1[k] > maxv) maxv = p1[k]; if (p2[k] > maxv) maxv = p2[k]; }
+    uint8_t *in_a = (uint8_t *)calloc((size_t)maxv + 1, 1), *in_b = (uint8_t *)calloc((size_t)maxv + 1, 1);
+    for (int32_t k = from; k <= to; ++k) { in_a[p1[k]] = 1; in_b[p2[k]] = 1; }
+    for (int32_t k = from; k <= to; ++k) { g1[k] = p2[k]; g2[k] = p1[k]; }
+    int32_t k = (to + 1) % len, j1 = k, j2 = k;
+    for (int32_t s = 0; s < len; ++s) {
+        const int32_t xa = p1[k], xb = p2[k];
+        if (!in_b[xa]) { g1[j1] = xa; j1 = (j1 + 1) % len; }
+        if (!in_a[xb]) { g2[j2] = xb; j2 = (j2 + 1) % len; }
+        k = (k + 1) % len;
+    }
+    free(in_a); free(in_b);
+}
+
+static float ga_fitness(const tlo_problem *p, const int32_t *t) /* build_evaluator, :112-124 */
+{
+    const float len = (float)tlo_tour_length(p, t, p->n);
+    return len == 0.0f ? 0.0f : 1.0f / len;
+}
+
+/* blocked roulette over ALL entries of w (no visited mask): first index whose running sum exceeds r,
+ * `r < up_to + f` being the reference's test (:291); the last index when rounding leaves r uncrossed */
+static int32_t ga_blocked_select(const float *w, int32_t n, float u)
+{
+    uint8_t *vis = (uint8_t *)calloc((size_t)n, 1);
+    /* total first (same blocked order), then r = u * total */
+    const int32_t C = (n + ACO_T - 1) / ACO_T;
+    float x[ACO_T], y[ACO_T];
+    for (int32_t t = 0; t < ACO_T; ++t) {
+        float acc = 0.0f;
+        for (int32_t v = t * C; v < (t + 1) * C && v < n; ++v) acc = acc + w[v];
+        x[t] = acc;
+    }
+    for (int32_t off = 1; off < 32; off <<= 1) {
+        for (int32_t t = 0; t < ACO_T; ++t) y[t] = ((t & 31) >= off) ? x[t] + x[t - off] : x[t];
+        memcpy(x, y, sizeof x);
+    }
+    float total = 0.0f;
+    for (int32_t g = 0; g < ACO_T / 32; ++g) total = total + x[32 * g + 31];
+    int32_t res;
+    if (!(total > 0.0f) || !isfinite(total)) {
+        res = n - 1; /* the reference would panic on an empty range; keep its `candidate = last` default */
+    } else {
+        /* aco_blocked_select computes target = r * total with r in [0,1): the same product */
+        res = aco_blocked_select(w, vis, n, u);
+        if (res < 0) res = n - 1;
+    }
+    free(vis);
+    return res;
+}
+
+double tlo_ga(const tlo_problem *p, const tlo_ga_options *o, const int32_t *init_tour, int32_t *best_out, tlo_stats *st)
+{
+    const int32_t n = p->n, P = p->n; /* population_size = cities.len() (:26) */
+    const uint32_t key[2] = {(uint32_t)o->seed, (uint32_t)(o->seed >> 32)};
+    if (st) st->passes = st->moves = st->evals = 0;
+    int32_t *pop = (int32_t *)malloc(sizeof(int32_t) * (size_t)P * n), *nxt = (int32_t *)malloc(sizeof(int32_t) * (size_t)P * n);
+    float *fit = (float *)malloc(4 * (size_t)P), *nfit = (float *)malloc(4 * (size_t)P), *sfit = (float *)malloc(4 * (size_t)P);
+    int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int32_t *c1 = (int32_t *)malloc(sizeof(int32_t) * (size_t)n), *c2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    /* ---- initial population (from_cities / from_cities_seeded, :193-237) */
+    const int32_t n_seeded = init_tour ? (P / 5 > 1 ? P / 5 : 1) : 0;
+    for (int32_t b = 0; b < P; ++b) {
+        int32_t *g = pop + (size_t)b * n;
+        if (b < n_seeded) {
+            memcpy(g, init_tour, sizeof(int32_t) * (size_t)n);
+            if (b > 0) { /* 2..=4 mutations of the seed; counter (b, 0, 0, GA_SEEDMUT) */
+                const uint32_t ctr[4] = {(uint32_t)b, 0u, 0u, GA_SEEDMUT};
+                uint32_t out[4];
+                tlo_philox4x32(ctr, key, out);
+                const uint32_t nm = 2u + bounded_u32(out[0], 3u);
+                for (uint32_t m = 0; m < nm; ++m) {
+                    uint32_t from, to;
+                    ga_position_pair(key, (uint32_t)b, m, 0u, GA_SEEDPAIR, (uint32_t)n, &from, &to);
+                    ga_reverse(g, from, to);
+                }
+            }
+        } else { /* Fisher-Yates shuffle of the identity order; counter (i, b, 0, GA_SHUFFLE) */
+            for (int32_t k = 0; k < n; ++k) g[k] = k;
+            for (int32_t i = n - 1; i > 0; --i) {
+                const uint32_t ctr[4] = {(uint32_t)i, (uint32_t)b, 0u, GA_SHUFFLE};
+                uint32_t out[4];
+                tlo_philox4x32(ctr, key, out);
+                const int32_t j = (int32_t)bounded_u32(out[0], (uint32_t)(i + 1));
+                const int32_t t = g[i]; g[i] = g[j]; g[j] = t;
+            }
+        }
+        fit[b] = ga_fitness(p, g);
+    }
+    /* The Vec of individuals has L entries: n at first, and after every epoch
+     * min(n, elites + 2 * (n/2 - n_elite)) -- the reference's population SHRINKS by n_elite (+1 for odd
+     * n) in the first epoch and keeps that size (:61-86: the loop bounds use the ORIGINAL size). */
+    int32_t L = P;
+    const int32_t pairs = P / 2 - o->n_elite > 0 ? P / 2 - o->n_elite : 0;
+    for (int32_t epoch = 0; epoch < o->epochs; ++epoch) {
+        /* stable descending sort: rank = #better + #equal-before (:68, :277-280) */
+        for (int32_t a = 0; a < L; ++a) {
+            int32_t r = 0;
+            for (int32_t b = 0; b < L; ++b) r += (fit[b] > fit[a]) || (fit[b] == fit[a] && b < a);
+            order[r] = a;
+        }
+        for (int32_t r = 0; r < L; ++r) sfit[r] = fit[order[r]];
+        int32_t cnt = 0;
+        for (int32_t e = 0; e < o->n_elite && e < L && cnt < P; ++e, ++cnt) {
+            memcpy(nxt + (size_t)cnt * n, pop + (size_t)order[e] * n, sizeof(int32_t) * (size_t)n);
+            nfit[cnt] = sfit[e];
+        }
+        for (int32_t k = 0; k < pairs; ++k) { /* for _ in elite_size..(population_size / 2) */
+            const uint32_t cs[4] = {(uint32_t)k, (uint32_t)epoch, 0u, GA_SELECT};
+            uint32_t out[4];
+            tlo_philox4x32(cs, key, out);
+            const int32_t a = order[ga_blocked_select(sfit, L, u32_to_unit_f32(out[0]))];
+            const int32_t b = order[ga_blocked_select(sfit, L, u32_to_unit_f32(out[1]))];
+            uint32_t from, to;
+            ga_position_pair(key, (uint32_t)k, (uint32_t)epoch, 0u, GA_XPAIR, (uint32_t)n, &from, &to);
+            tlo_ox_genes(pop + (size_t)a * n, pop + (size_t)b * n, n, (int32_t)from, (int32_t)to, c1, c2);
+            const float ff[2] = {ga_fitness(p, c1), ga_fitness(p, c2)}; /* before the mutation, never refreshed */
+            int32_t *cc[2] = {c1, c2};
+            for (uint32_t c = 0; c < 2; ++c) {
+                const uint32_t cm[4] = {(uint32_t)k, (uint32_t)epoch, c, GA_MUTP};
+                tlo_philox4x32(cm, key, out);
+                if (o->mutation_probability > u32_to_unit_f32(out[0])) { /* probability(p): p > rng.random() */
+                    uint32_t mf, mt;
+                    ga_position_pair(key, (uint32_t)k, (uint32_t)epoch, 16u * (c + 1u), GA_MUTPAIR, (uint32_t)n, &mf, &mt);
+                    ga_reverse(cc[c], mf, mt);
+                    if (st) st->moves++;
+                }
+                if (cnt < P) { /* TspPopulation::add ignores individuals beyond n (:240-244) */
+                    memcpy(nxt + (size_t)cnt * n, cc[c], sizeof(int32_t) * (size_t)n);
+                    nfit[cnt] = ff[c];
+                    ++cnt;
+                }
+            }
+            if (st) st->evals += 2;
+        }
+        int32_t *tp = pop; pop = nxt; nxt = tp;
+        float *tf = fit; fit = nfit; nfit = tf;
+        L = cnt;
+        if (st) st->passes++;
+        if (L == 0) break; /* n_elite = 0 and n < 2: nothing left (the reference would panic in best()) */
+    }
+    /* best(): the LAST individual of maximal fitness (Iterator::max_by, :264-269) */
+    int32_t bi = 0;
+    for (int32_t b = 1; b < L; ++b) if (fit[b] >= fit[bi]) bi = b;
+    if (L > 0) memcpy(best_out, pop + (size_t)bi * n, sizeof(int32_t) * (size_t)n);
+    const double len = L > 0 ? tlo_tour_length(p, best_out, n) : -1.0;
+    free(pop); free(nxt); free(fit); free(nfit); free(sfit); free(order); free(c1); free(c2);
+    return len;
+}

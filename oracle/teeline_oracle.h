@@ -133,6 +133,19 @@ void tlo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
 double tlo_aco(const tlo_problem *p, const tlo_aco_options *o, const int32_t *init_tour, int32_t *best_out,
                tlo_stats *st);
 
+/* ---- GA population step (genetic_algorithm.rs:16-335) with the same seeded Philox stream and blocked
+ * roulette sums as tlo_aco; see the comment above tlo_ga.  Returns the exact-order length of best(). */
+typedef struct {
+    float mutation_probability; /* default 0.001 (mod.rs:822-830) */
+    int32_t n_elite;            /* default 3 */
+    int32_t epochs;             /* default 10000 */
+    int32_t pad;
+    uint64_t seed;
+} tlo_ga_options;
+/* ordered_crossover_genes (genetic_algorithm.rs:140-176), pinned by the reference's book examples */
+void tlo_ox_genes(const int32_t *p1, const int32_t *p2, int32_t len, int32_t from, int32_t to, int32_t *g1, int32_t *g2);
+double tlo_ga(const tlo_problem *p, const tlo_ga_options *o, const int32_t *init_tour, int32_t *best_out, tlo_stats *st);
+
 /* ---- synthetic inputs (BASELINE.md "Synthetic inputs") */
 uint64_t tlo_splitmix64(uint64_t *state);
 /* x,y = (splitmix64 >> 40) * (1000 / 2^24) as f32; x then y per city. */

@@ -10,6 +10,8 @@
 // with fp64 once per thread, then advanced incrementally.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace tl {
 
 // one matrix entry as raw bits: NINT = 0 f32 (FAST: guarded fast sqrt), 1 TSPLIB nint in double,
@@ -90,34 +92,57 @@ __global__ void __launch_bounds__(256) k1_packed_kernel(const float2 *__restrict
     }
 }
 
-// Square matrix in SLOT order: M[a*ld + b] = d(slot a, slot b), a,b < n; the pad
-// columns [n, ld) are zero.  sxy holds slot-ordered coordinates.  One thread per
-// 4 columns, 128-bit stores; a block covers a 64-row x 256-column tile so the row
-// coordinates are reused from registers.
+// Square matrix in SLOT order: M[a*ld + b] = d(slot a, slot b), a,b < n; the pad columns [n, ld)
+// are zero.  sxy holds slot-ordered coordinates.  The metric is bitwise symmetric (d(a,b) == d(b,a):
+// (a-b)^2 == (b-a)^2 in IEEE arithmetic, and the reference's hi.distance(lo) operand order therefore
+// needs no select), so only the 64 x 64 tiles on or above the diagonal are COMPUTED: a CTA computes
+// tile (bi, bj), bj >= bi -- each thread a 4 x 4 patch from 4 row and 4 column points in registers --
+// stores it with 128-bit stores, and stores its transpose, staged through shared memory, as tile
+// (bj, bi).  Half the arithmetic of the round-1 kernel (which was issue-bound for the nint metric:
+// 141 us for the 10k x 10k int32 matrix against a 61 us write floor) for the same bytes written.
 template <bool FAST, int NINT>
 __global__ void __launch_bounds__(256) k1_square_kernel(const float2 *__restrict__ sxy, uint32_t n,
                                                         uint32_t ld, void *__restrict__ out)
 {
-    const uint32_t col0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-    const uint32_t row0 = blockIdx.y * 64 + (threadIdx.x >> 6) * 16;
-    if (col0 >= ld) return;
-    float2 c[4];
+    if (blockIdx.x < blockIdx.y) return; // the mirror tile writes this one
+    __shared__ uint32_t tile[64][65];
+    const uint32_t tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const uint32_t col0 = blockIdx.x * 64 + tx * 4, row0 = blockIdx.y * 64 + ty * 4;
+    uint32_t *M = reinterpret_cast<uint32_t *>(out);
+    float2 c[4], r[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
+    for (int e = 0; e < 4; ++e) {
         c[e] = (col0 + e < n) ? __ldg(&sxy[col0 + e]) : make_float2(0.f, 0.f);
-    for (uint32_t r = row0; r < row0 + 16 && r < n; ++r) {
-        const float2 p = __ldg(&sxy[r]);
+        r[e] = (row0 + e < n) ? __ldg(&sxy[row0 + e]) : make_float2(0.f, 0.f);
+    }
+    const bool mirror = blockIdx.x != blockIdx.y;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const uint32_t rr = row0 + a;
         uint32_t v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const uint32_t cc = col0 + e;
-            // d(a, b) == d(b, a) bit for bit ((a-b)^2 == (b-a)^2 in IEEE arithmetic), so the
-            // reference's hi.distance(lo) operand order needs no select here
-            const uint32_t d = k1_dist<FAST, NINT>(p, c[e]);
-            v[e] = (cc >= n || cc == r) ? 0u : d;
+            const uint32_t d = k1_dist<FAST, NINT>(r[a], c[e]);
+            v[e] = (cc >= n || rr >= n || cc == rr) ? 0u : d;
+            if (mirror) tile[ty * 4 + a][tx * 4 + e] = v[e];
         }
-        *reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(out) + (size_t)r * ld + col0) =
-            make_uint4(v[0], v[1], v[2], v[3]);
+        if (rr < n && col0 < ld)
+            *reinterpret_cast<uint4 *>(M + (size_t)rr * ld + col0) = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+    if (!mirror) return;
+    __syncthreads();
+    // transpose: this thread writes rows (blockIdx.x * 64 + ty * 4 + a) of the mirror tile, 4 columns
+    // starting at blockIdx.y * 64 + tx * 4
+    const uint32_t tcol0 = blockIdx.y * 64 + tx * 4;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const uint32_t trow = blockIdx.x * 64 + ty * 4 + a;
+        if (trow < n && tcol0 < ld) {
+            const uint32_t lr = ty * 4 + a; // local column of the computed tile
+            *reinterpret_cast<uint4 *>(M + (size_t)trow * ld + tcol0) =
+                make_uint4(tile[tx * 4 + 0][lr], tile[tx * 4 + 1][lr], tile[tx * 4 + 2][lr], tile[tx * 4 + 3][lr]);
+        }
     }
 }
 
@@ -176,7 +201,10 @@ void launch_k1_packed(const float2 *xy, uint32_t n, bool fast, int nint, void *o
 void launch_k1_square(const float2 *sxy, uint32_t n, uint32_t ld, bool fast, int nint, void *out,
                       cudaStream_t st)
 {
-    dim3 grid((ld / 4 + 63) / 64, (n + 63) / 64);
+    // tiles of 64 x 64; the column blocks cover the padded width ld, the row blocks the n rows; the
+    // grid is square so that every tile below the diagonal has a mirror above it
+    const unsigned nb = (std::max(ld, n) + 63) / 64;
+    dim3 grid(nb, nb);
     if (nint == 2)
         k1_square_kernel<false, 2><<<grid, 256, 0, st>>>(sxy, n, ld, out);
     else if (nint)

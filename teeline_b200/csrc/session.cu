@@ -514,6 +514,33 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         tl_session_destroy(s);
         return rc;
     };
+    if (want_matrix) {
+        // The matrix is allocated FIRST: the pool usually holds the previous session's matrix block, and
+        // the small buffers below would otherwise be carved out of it, so that the matrix no longer fits
+        // and the pool has to grow by another n^2 block (8-30 ms per call in the end-to-end path).
+        s->ld = (p->n + 31u) & ~31u;
+        const size_t bytes = (size_t)p->n * s->ld * 4;
+        // what a new block can come from: the driver's free memory plus what this context's pool
+        // holds cached from earlier sessions (reserved but not in use)
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (c->pool) {
+            uint64_t reserved = 0, used = 0;
+            if (cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+                free_b += (size_t)(reserved - used);
+        }
+        if (bytes > free_b - std::min<size_t>(free_b, (size_t)1 << 30)) {
+            set_error("the %u x %u distance matrix (%.1f GB) does not fit device memory (%.1f GB free); "
+                      "use TL_PATH_RECOMPUTE", p->n, s->ld, bytes / 1e9, free_b / 1e9);
+            return fail(TL_ERR_NOMEM);
+        }
+        if (s->M.alloc((size_t)p->n * s->ld) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("tl_session_create: matrix allocation failed");
+            return fail(TL_ERR_NOMEM);
+        }
+    }
     DevBuf<uint32_t> d_tour;
     if (d_tour.alloc(p->n) != cudaSuccess || s->state.alloc(1) != cudaSuccess || s->ticket.alloc(2) != cudaSuccess ||
         s->log.alloc(s->log_cap) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
@@ -540,24 +567,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     if (e != cudaSuccess) { set_error("tl_session_create: %s", cudaGetErrorString(e)); return fail(TL_ERR_CUDA); }
 
     if (want_matrix) {
-        s->ld = (p->n + 31u) & ~31u;
-        const size_t bytes = (size_t)p->n * s->ld * 4;
-        // what a new block can come from: the driver's free memory plus what this context's pool
-        // holds cached from earlier sessions (reserved but not in use)
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        if (c->pool) {
-            uint64_t reserved = 0, used = 0;
-            if (cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-                cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
-                free_b += (size_t)(reserved - used);
-        }
-        if (bytes > free_b - std::min<size_t>(free_b, (size_t)1 << 30)) {
-            set_error("the %u x %u distance matrix (%.1f GB) does not fit device memory (%.1f GB free); "
-                      "use TL_PATH_RECOMPUTE", p->n, s->ld, bytes / 1e9, free_b / 1e9);
-            return fail(TL_ERR_NOMEM);
-        }
-        bool ok = s->cs.alloc(s->npad) == cudaSuccess && s->M.alloc((size_t)p->n * s->ld) == cudaSuccess;
+        bool ok = s->cs.alloc(s->npad) == cudaSuccess;
         if (p->kind == PK_EXPLICIT)
             ok = ok && s->slot_city.alloc(p->n) == cudaSuccess;
         else
@@ -571,6 +581,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         launch_build_cs(s->src, d_tour.p, p->n, s->npad, s->cyclic, c->stream);
         c->launches++;
         // re-lay the matrix in tour order only when it cannot live in L2 (gathers are cheap there)
+        const size_t bytes = (size_t)p->n * s->ld * 4;
         s->repermute_every = bytes > ((size_t)96 << 20) ? 256 : 0;
         if (const char *ev = getenv("TL_REPERMUTE_EVERY")) s->repermute_every = atoi(ev);
         configure_matrix_pin(s, bytes);

@@ -31,5 +31,6 @@ def test_sharded_paths_against_the_oracle(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and f"MULTI_GPU_OK world={world}" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
+    env = dict(os.environ, PYTHONFAULTHANDLER="1")  # a crash in a rank prints its Python stack
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and f"MULTI_GPU_OK world={world}" in r.stdout, (r.stdout[-3000:], r.stderr[-6000:])
