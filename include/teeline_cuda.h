@@ -194,6 +194,27 @@ typedef struct {
 tl_status tl_aco(tl_problem *p, const tl_aco_options *opts, const uint32_t *init_tour, uint32_t *best_tour_out,
                  float *best_cost_out, tl_stats *stats);
 
+/* ---- Genetic algorithm (population solver) ----------------------- */
+
+/* Replaces the body of genetic_algorithm::solve / solve_ga (src/tsp/genetic_algorithm.rs:16-107): a
+ * population of n tours; per epoch a stable sort by fitness, n_elite elites, n/2 - n_elite pairs of
+ * roulette-selected parents, ordered crossover (:140-176), fitness 1/tour_length (exact-order sum, as
+ * tl_tour_lengths) taken before the optional reversal mutation; returns best() (:264-269) and its
+ * exact-order length.  Every random draw is Philox4x32-10(seed; ...), so a run is reproducible.
+ * Option defaults and validation follow GAOptions (src/tsp/mod.rs:816-846).  init_tour (nullable):
+ * seeds max(n/5, 1) individuals (the tour itself and 2..=4-times mutated copies, :207-222), the rest
+ * are shuffles.  Coordinate (F32_EXACT) and EXPLICIT problems; n up to what one CTA's shared memory
+ * holds (about 7000 cities), TL_ERR_UNSUPPORTED beyond. */
+typedef struct {
+    float mutation_probability; /* in [0, 1], default 0.001 */
+    uint32_t n_elite;           /* default 3                */
+    uint32_t epochs;            /* default 10000            */
+    uint32_t pad;
+    uint64_t seed;
+} tl_ga_options;
+tl_status tl_ga(tl_problem *p, const tl_ga_options *opts, const uint32_t *init_tour, uint32_t *best_tour_out,
+                float *best_cost_out, tl_stats *stats);
+
 /* ---- local search, device-resident session (benchmarks, pipelines) ---------------- */
 
 tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uint32_t *tour,

@@ -9,6 +9,7 @@ CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -36,6 +37,9 @@ class Context:
             capi.check(self._lib.tl_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h)))
         self.h = h
         self.device = device
+        # handles created from this context; close() destroys them first (the C handles point back
+        # at the tl_ctx, so a Problem collected after its Context would touch freed memory)
+        self._children = weakref.WeakSet()
 
     def sync(self):
         capi.check(self._lib.tl_ctx_sync(self.h))
@@ -66,6 +70,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(self._children):
+                child.close()
             self._lib.tl_ctx_destroy(self.h)
             self.h = None
 
@@ -82,6 +88,8 @@ class Problem:
     def __init__(self, ctx: Context, h, n: int, kind: str):
         self.ctx, self.h, self.n, self.kind = ctx, h, n, kind
         self._lib = ctx._lib
+        self._children = weakref.WeakSet()  # sessions: destroyed before the problem they point at
+        ctx._children.add(self)
 
     @classmethod
     def euc2d(cls, ctx: Context, x, y, dist_kind: int = DIST_F32_EXACT) -> "Problem":
@@ -172,11 +180,23 @@ class Problem:
                                     C.byref(cost), C.byref(st)))
         return best, float(cost.value), st
 
+    def ga(self, seed: int, init_tour=None, mutation_probability: float = 0.001, n_elite: int = 3, epochs: int = 10000):
+        """tl_ga with the reference's GAOptions defaults: returns (best_tour, best_length, Stats)."""
+        o = capi.GaOptions(mutation_probability, n_elite, epochs, 0, seed)
+        best = np.empty(self.n, dtype=np.uint32)
+        cost, st = C.c_float(), Stats()
+        it = _u32(init_tour) if init_tour is not None else None
+        capi.check(self._lib.tl_ga(self.h, C.byref(o), capi.ptr(it) if it is not None else None, capi.ptr(best),
+                                   C.byref(cost), C.byref(st)))
+        return best, float(cost.value), st
+
     def session(self, algo: int, tour, path: int = PATH_AUTO) -> "Session":
         return Session(self, algo, path, tour)
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(self._children):
+                child.close()
             self._lib.tl_problem_destroy(self.h)
             self.h = None
 
@@ -198,6 +218,7 @@ class Session:
         h = C.c_void_p()
         capi.check(self._lib.tl_session_create(problem.h, algo, path, capi.ptr(t), C.byref(h)))
         self.h = h
+        problem._children.add(self)
 
     def set_shard(self, index: int, count: int):
         capi.check(self._lib.tl_session_set_shard(self.h, index, count))

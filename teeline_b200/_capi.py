@@ -32,7 +32,7 @@ EXPORTS = [
     "tl_session_destroy", "tl_session_set_shard", "tl_session_scan", "tl_session_time_scans",
     "tl_session_enqueue",
     "tl_session_run", "tl_session_tour", "tl_session_stats", "tl_session_log", "tl_selftest_sqrt",
-    "tl_microbench_fp32", "tl_aco",
+    "tl_microbench_fp32", "tl_aco", "tl_ga",
 ]
 
 
@@ -60,6 +60,11 @@ class Stats(C.Structure):
 class AcoOptions(C.Structure):
     _fields_ = [("alpha", C.c_float), ("beta", C.c_float), ("evaporation_rate", C.c_float),
                 ("num_ants", C.c_uint32), ("epochs", C.c_uint32), ("pad", C.c_uint32), ("seed", C.c_uint64)]
+
+
+class GaOptions(C.Structure):
+    _fields_ = [("mutation_probability", C.c_float), ("n_elite", C.c_uint32), ("epochs", C.c_uint32),
+                ("pad", C.c_uint32), ("seed", C.c_uint64)]
 
 
 class TeelineError(RuntimeError):
@@ -121,6 +126,8 @@ def load():
     L.tl_microbench_fp32.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tl_aco.argtypes = [C.c_void_p, C.POINTER(AcoOptions), C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
                          C.POINTER(Stats)]
+    L.tl_ga.argtypes = [C.c_void_p, C.POINTER(GaOptions), C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
+                        C.POINTER(Stats)]
     _lib = L
     return L
 

@@ -297,6 +297,17 @@ cudaError_t launch_aco_construct(const float *w, const float *eta, uint32_t n, u
 void launch_aco_update(float *ph, uint32_t n, const uint32_t *tours, const float *costs, uint32_t ants,
                        uint32_t *best_tour, float *best_cost, unsigned long long *improvements, cudaStream_t st);
 
+// K8: GA population step (k8_ga.cu)
+size_t ga_breed_smem_bytes(uint32_t n, uint32_t L);
+cudaError_t launch_ga_init(const float2 *xy, const float *tri, uint32_t n, bool fast, const uint32_t *init,
+                           uint32_t n_seeded, uint64_t seed, uint32_t *pop, float *fit, cudaStream_t st);
+cudaError_t launch_ga_rank(const float *fit, uint32_t L, int *order, float *sfit, cudaStream_t st);
+cudaError_t launch_ga_breed(const float2 *xy, const float *tri, uint32_t n, bool fast, uint32_t L, uint32_t ne,
+                            uint32_t pairs, uint32_t epoch, uint64_t seed, float mutation_probability,
+                            const uint32_t *pop, const int *order, const float *sfit, uint32_t *nxt, float *nfit,
+                            unsigned long long *mutations, cudaStream_t st);
+void launch_ga_best(const uint32_t *pop, const float *fit, uint32_t n, uint32_t L, uint32_t *best, cudaStream_t st);
+
 // K4
 void launch_tour_lengths_f32(const float2 *xy, const float *tri, uint32_t n, const uint32_t *tours,
                              uint64_t batch, bool fast_sqrt, bool fast_mode, float *out, int sm_count,

@@ -22,7 +22,9 @@ struct Args {
     std::string cmd, solver, input, output, config, output_format = "text", distance_type, mode, path;
     std::vector<std::string> steps;
     bool no_seed = false, verbose = false;
-    std::optional<size_t> epochs, platoo_epochs, n_nearest;
+    std::optional<size_t> epochs, platoo_epochs, n_nearest, n_elite, num_ants;
+    std::optional<float> mutation_probability, alpha, beta, evaporation_rate;
+    uint64_t seed = 0; // extension: Philox key of the population solvers
 };
 
 [[noreturn]] void die(const std::string &msg, int code = 1)
@@ -63,6 +65,13 @@ Args parse_args(int argc, char **argv)
         else if (s == "--epochs") a.epochs = std::strtoull(next("--epochs").c_str(), nullptr, 10);
         else if (s == "--platoo_epochs") a.platoo_epochs = std::strtoull(next("--platoo_epochs").c_str(), nullptr, 10);
         else if (s == "--n_nearest") a.n_nearest = std::strtoull(next("--n_nearest").c_str(), nullptr, 10);
+        else if (s == "--n_elite") a.n_elite = std::strtoull(next("--n_elite").c_str(), nullptr, 10);
+        else if (s == "--mutation_probability") a.mutation_probability = std::strtof(next("--mutation_probability").c_str(), nullptr);
+        else if (s == "--alpha") a.alpha = std::strtof(next("--alpha").c_str(), nullptr);
+        else if (s == "--beta") a.beta = std::strtof(next("--beta").c_str(), nullptr);
+        else if (s == "--evaporation-rate") a.evaporation_rate = std::strtof(next("--evaporation-rate").c_str(), nullptr);
+        else if (s == "--num-ants") a.num_ants = std::strtoull(next("--num-ants").c_str(), nullptr, 10);
+        else if (s == "--seed") a.seed = std::strtoull(next("--seed").c_str(), nullptr, 10);
         else if (s == "--mode") a.mode = next("--mode");  // extension: ref | best | best_cyclic
         else if (s == "--path") a.path = next("--path");  // extension: auto | matrix | recompute
         else if (!s.empty() && s[0] != '-' && a.cmd == "solve" && a.solver.empty()) a.solver = s;
@@ -82,6 +91,26 @@ AppOptions options_from_args(const Args &a)
     auto v = h.validate();
     if (v.is_err()) die(v.error);
     o.heuristic = h;
+    // AcoOptions::from_cli / GAOptions::from_cli (mod.rs:1198-1240, 892-905): the solver's own defaults
+    // (ACO: 150 epochs) unless a flag is given
+    AcoOptions aco;
+    if (a.epochs) aco.heuristic.epochs = *a.epochs;
+    if (a.platoo_epochs) aco.heuristic.platoo_epochs = *a.platoo_epochs;
+    if (a.alpha) aco.alpha = *a.alpha;
+    if (a.beta) aco.beta = *a.beta;
+    if (a.evaporation_rate) aco.evaporation_rate = *a.evaporation_rate;
+    if (a.num_ants) aco.num_ants = *a.num_ants;
+    auto av = aco.validate();
+    if (av.is_err()) die(av.error);
+    o.aco = aco;
+    GAOptions ga;
+    ga.heuristic = h;
+    if (a.mutation_probability) ga.mutation_probability = *a.mutation_probability;
+    if (a.n_elite) ga.n_elite = *a.n_elite;
+    auto gv = ga.validate();
+    if (gv.is_err()) die(gv.error);
+    o.ga = ga;
+    o.cuda_seed = a.seed;
     o.cuda_mode = a.mode;
     o.cuda_path = a.path;
     return o;

@@ -143,7 +143,8 @@ bool auto_expand_with_shuffle(Solvers s)
 bool is_accelerated(Solvers s)
 {
     return s == Solvers::NearestNeighbor || s == Solvers::TwoOpt || s == Solvers::OrOpt || s == Solvers::TwoOptBest ||
-           s == Solvers::ThreeOpt;
+           s == Solvers::ThreeOpt || s == Solvers::AntColony || s == Solvers::GeneticAlgorithm ||
+           s == Solvers::RandomShuffle;
 }
 
 // ---- DistanceMatrix ----------------------------------------------------------------------------------
@@ -584,6 +585,79 @@ Solution solve(const TspProblem &problem, const HeuristicOptions &opts, const Pr
 
 } // namespace nearest_neighbor
 
+namespace {
+
+// PathUpdate(best) + Done, what the population solvers send at the end (ant_colony.rs:241-247,
+// genetic_algorithm.rs:33-41); per-epoch updates are not replayed
+void send_final(const ProgressSender *tx, const std::vector<size_t> &route, float total)
+{
+    if (!tx) return;
+    ProgressMessage m;
+    m.kind = ProgressMessage::PathUpdate;
+    m.route = route;
+    m.total = total;
+    (*tx)(m);
+    ProgressMessage done;
+    done.kind = ProgressMessage::Done;
+    (*tx)(done);
+}
+
+} // namespace
+
+namespace ant_colony {
+
+Solution solve(const TspProblem &problem, const AcoOptions &o, const ProgressSender *tx, const std::vector<size_t> *init_tour,
+               uint64_t seed)
+{
+    const DistanceMatrix &dm = problem.distances;
+    std::vector<uint32_t> init, best(dm.num_cities());
+    if (init_tour) init = to_positions(*init_tour, dm, "ant_colony");
+    tl_aco_options co{o.alpha, o.beta, o.evaporation_rate, (uint32_t)o.num_ants, (uint32_t)o.heuristic.epochs, 0u, seed};
+    float cost = 0.0f;
+    check(tl_aco(dm.impl->prob, &co, init_tour ? init.data() : nullptr, best.data(), &cost, nullptr), "ant_colony");
+    const std::vector<size_t> route = to_ids(best, dm);
+    send_final(tx, route, cost);
+    return Solution::from_parts(route, problem.cities, dm);
+}
+
+} // namespace ant_colony
+
+namespace genetic_algorithm {
+
+Solution solve(const TspProblem &problem, const GAOptions &o, const ProgressSender *tx, const std::vector<size_t> *init_tour,
+               uint64_t seed)
+{
+    const DistanceMatrix &dm = problem.distances;
+    std::vector<uint32_t> init, best(dm.num_cities());
+    if (init_tour) init = to_positions(*init_tour, dm, "genetic_algorithm");
+    tl_ga_options go{o.mutation_probability, (uint32_t)o.n_elite, (uint32_t)o.heuristic.epochs, 0u, seed};
+    float cost = 0.0f;
+    check(tl_ga(dm.impl->prob, &go, init_tour ? init.data() : nullptr, best.data(), &cost, nullptr), "genetic_algorithm");
+    const std::vector<size_t> route = to_ids(best, dm);
+    send_final(tx, route, cost);
+    return Solution::from_parts(route, problem.cities, dm);
+}
+
+} // namespace genetic_algorithm
+
+namespace random_shuffle {
+
+Solution solve(const TspProblem &problem, uint64_t seed)
+{
+    std::vector<size_t> ids = ids_of(problem.cities);
+    uint64_t state = seed ^ 0x9E3779B97F4A7C15ull;
+    auto next = [&state]() { // splitmix64
+        uint64_t z = (state += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    for (size_t i = ids.size(); i > 1; --i) std::swap(ids[i - 1], ids[(size_t)(next() % i)]);
+    return Solution::from_parts(ids, problem.cities, problem.distances);
+}
+
+} // namespace random_shuffle
+
 Result<bool> validate_tour(const std::vector<size_t> &tour, const std::vector<KDPoint> &cities)
 {
     if (tour.size() != cities.size())
@@ -611,10 +685,24 @@ Result<Solution> solve_with_context(Solvers solver, const TspProblem &problem, c
         return Result<Solution>::ok(two_opt::solve_with(problem, opts.cuda_mode, opts.cuda_path, tx, init_tour));
     case Solvers::TwoOptBest:
         return Result<Solution>::ok(two_opt::solve_with(problem, "best", opts.cuda_path, tx, init_tour));
+    case Solvers::AntColony: { // mod.rs:1706-1711: options validated, then ant_colony::solve
+        const AcoOptions o = opts.aco.value_or(AcoOptions{});
+        auto av = o.validate();
+        if (av.is_err()) return Result<Solution>::err(av.error);
+        return Result<Solution>::ok(ant_colony::solve(problem, o, tx, init_tour, opts.cuda_seed));
+    }
+    case Solvers::GeneticAlgorithm: {
+        GAOptions o = opts.ga.value_or(GAOptions{});
+        if (!opts.ga && opts.heuristic) o.heuristic = *opts.heuristic; // CLI --epochs reaches the GA this way
+        auto gv = o.validate();
+        if (gv.is_err()) return Result<Solution>::err(gv.error);
+        return Result<Solution>::ok(genetic_algorithm::solve(problem, o, tx, init_tour, opts.cuda_seed));
+    }
+    case Solvers::RandomShuffle: return Result<Solution>::ok(random_shuffle::solve(problem, opts.cuda_seed));
     case Solvers::Unspecified: return Result<Solution>::err("solver not specified");
     default:
         return Result<Solution>::err(std::string("solver ") + solver_name(solver) +
-                                     " is outside the accelerated local-search path of this build (nn, 2opt, or_opt, 3opt)");
+                                     " is outside the accelerated path of this build (nn, 2opt, or_opt, 3opt, aco, ga)");
     }
 }
 
@@ -677,6 +765,119 @@ Result<bool> HeuristicOptions::validate() const
 {
     if (n_nearest == 0) return Result<bool>::err("n_nearest must be >= 1");
     return Result<bool>::ok(true);
+}
+
+namespace {
+
+// `{}` of an f32 in the reference's messages: shortest round-trip decimal; %g is enough for the values users type
+std::string fmt_f32(float v)
+{
+    char b[64];
+    std::snprintf(b, sizeof b, "%g", v);
+    return b;
+}
+
+// parse_f32 (mod.rs:1602-1607): a float, or an integer widened
+bool toml_f32(const TomlValue &v, float &out)
+{
+    if (const double *d = v.as_float()) { out = (float)*d; return true; }
+    if (const int64_t *i = v.as_integer()) { out = (float)*i; return true; }
+    return false;
+}
+
+// the four HeuristicOptions keys every population table accepts; returns 0 = not one of them, 1 = ok, -1 = error
+int heuristic_key(const std::string &k, const TomlValue &v, HeuristicOptions &h, std::string &err)
+{
+    if (k == "epochs" || k == "platoo_epochs" || k == "n_nearest") {
+        const int64_t *i = v.as_integer();
+        if (!i || *i < 0) { err = "config: `" + k + "` must be a non-negative integer, got " + v.display(); return -1; }
+        (k == "epochs" ? h.epochs : k == "platoo_epochs" ? h.platoo_epochs : h.n_nearest) = (size_t)*i;
+        return 1;
+    }
+    if (k == "verbose") {
+        const bool *b = v.as_bool();
+        if (!b) { err = "config: `verbose` must be a bool, got " + v.display(); return -1; }
+        h.verbose = *b;
+        return 1;
+    }
+    return 0;
+}
+
+} // namespace
+
+Result<bool> AcoOptions::validate() const // mod.rs:1114-1153
+{
+    if (!std::isfinite(alpha) || alpha < 0.0f) return Result<bool>::err("alpha must be >= 0 (got " + fmt_f32(alpha) + ")");
+    if (!(beta >= 0.0f && beta <= 6.0f)) return Result<bool>::err("beta must be in [0, 6] (got " + fmt_f32(beta) + ")");
+    if (!std::isfinite(evaporation_rate) || evaporation_rate <= 0.0f || evaporation_rate >= 1.0f)
+        return Result<bool>::err("evaporation_rate must be in (0, 1) (got " + fmt_f32(evaporation_rate) + ")");
+    if (num_ants == 0) return Result<bool>::err("num_ants must be >= 1");
+    return Result<bool>::ok(true);
+}
+
+Result<AcoOptions> AcoOptions::from_toml(const TomlTable &table) // mod.rs:1155-1196
+{
+    AcoOptions a;
+    for (const auto &kv : table) {
+        const std::string &k = kv.first;
+        std::string err;
+        const int hk = heuristic_key(k, kv.second, a.heuristic, err);
+        if (hk < 0) return Result<AcoOptions>::err(err);
+        if (hk > 0) continue;
+        if (k == "alpha" || k == "beta" || k == "evaporation_rate") {
+            float f;
+            if (!toml_f32(kv.second, f))
+                return Result<AcoOptions>::err("config: `aco." + k + "` must be a float, got " + kv.second.display());
+            (k == "alpha" ? a.alpha : k == "beta" ? a.beta : a.evaporation_rate) = f;
+        } else if (k == "num_ants") {
+            const int64_t *i = kv.second.as_integer();
+            if (!i || *i < 0)
+                return Result<AcoOptions>::err("config: `aco.num_ants` must be a non-negative integer, got " + kv.second.display());
+            a.num_ants = (size_t)*i;
+        } else {
+            return Result<AcoOptions>::err("config: unknown field `" + k +
+                                           "` in [aco] — valid: epochs, platoo_epochs, n_nearest, verbose, alpha, beta, "
+                                           "evaporation_rate, num_ants");
+        }
+    }
+    auto v = a.validate();
+    if (v.is_err()) return Result<AcoOptions>::err(v.error);
+    return Result<AcoOptions>::ok(a);
+}
+
+Result<bool> GAOptions::validate() const // mod.rs:832-845
+{
+    auto h = heuristic.validate();
+    if (h.is_err()) return h;
+    if (!std::isfinite(mutation_probability) || mutation_probability < 0.0f || mutation_probability > 1.0f)
+        return Result<bool>::err("mutation_probability must be in [0, 1] (got " + fmt_f32(mutation_probability) + ")");
+    return Result<bool>::ok(true);
+}
+
+Result<GAOptions> GAOptions::from_toml(const TomlTable &table) // mod.rs:847-890
+{
+    GAOptions g;
+    for (const auto &kv : table) {
+        const std::string &k = kv.first;
+        std::string err;
+        const int hk = heuristic_key(k, kv.second, g.heuristic, err);
+        if (hk < 0) return Result<GAOptions>::err(err);
+        if (hk > 0) continue;
+        if (k == "mutation_probability") {
+            if (!toml_f32(kv.second, g.mutation_probability))
+                return Result<GAOptions>::err("config: `ga.mutation_probability` must be a float, got " + kv.second.display());
+        } else if (k == "n_elite") {
+            const int64_t *i = kv.second.as_integer();
+            if (!i) return Result<GAOptions>::err("config: `ga.n_elite` must be an integer, got " + kv.second.display());
+            g.n_elite = (size_t)*i;
+        } else {
+            return Result<GAOptions>::err("config: unknown field `" + k +
+                                          "` in [ga] — valid: epochs, platoo_epochs, n_nearest, verbose, mutation_probability, n_elite");
+        }
+    }
+    auto v = g.validate();
+    if (v.is_err()) return Result<GAOptions>::err(v.error);
+    return Result<GAOptions>::ok(g);
 }
 
 // ---- pipeline ---------------------------------------------------------------------------------------------
@@ -1229,7 +1430,19 @@ Result<AppOptions> provide(const TomlTable &table, AppOptions base)
         if (key == "solver") continue;
         bool known_sub = false;
         for (const char *s : kSub) known_sub = known_sub || key == s;
-        if (known_sub) { // validated as tables; their solvers are outside this build's path
+        if (key == "aco" || key == "ga") {
+            const TomlTable *t = kv.second.as_table();
+            if (!t) return Result<AppOptions>::err("config: `" + key + "` must be a table");
+            if (key == "aco") {
+                auto a = tsp::AcoOptions::from_toml(*t);
+                if (a.is_err()) return Result<AppOptions>::err(a.error);
+                base.aco = a.unwrap();
+            } else {
+                auto g = tsp::GAOptions::from_toml(*t);
+                if (g.is_err()) return Result<AppOptions>::err(g.error);
+                base.ga = g.unwrap();
+            }
+        } else if (known_sub) { // validated as tables; their solvers are outside this build's path
             if (!kv.second.as_table()) return Result<AppOptions>::err("config: `" + key + "` must be a table");
         } else if (key == "heuristic") {
             const TomlTable *t = kv.second.as_table();
@@ -1242,9 +1455,11 @@ Result<AppOptions> provide(const TomlTable &table, AppOptions base)
             if (!t) return Result<AppOptions>::err("config: `cuda` must be a table");
             for (const auto &ckv : *t) {
                 const std::string *s = ckv.second.as_str();
+                const int64_t *iv = ckv.second.as_integer();
                 if (ckv.first == "mode" && s) base.cuda_mode = *s;
                 else if (ckv.first == "path" && s) base.cuda_path = *s;
-                else return Result<AppOptions>::err("config: unknown field `" + ckv.first + "` in [cuda] — valid: mode, path (strings)");
+                else if (ckv.first == "seed" && iv) base.cuda_seed = (uint64_t)*iv;
+                else return Result<AppOptions>::err("config: unknown field `" + ckv.first + "` in [cuda] — valid: mode, path (strings), seed (integer)");
             }
         } else {
             return Result<AppOptions>::err("config: unknown field `" + key +

@@ -189,10 +189,30 @@ struct HeuristicOptions { // mod.rs:597-683
     Result<bool> validate() const; // "n_nearest must be >= 1"
 };
 
-struct AppOptions { // mod.rs:1586-1596; only the sub-table this path consumes is modelled
+struct AcoOptions { // mod.rs:1083-1200; its own epochs = 150, platoo_epochs = 20 defaults
+    HeuristicOptions heuristic{150, 20, 3, false};
+    float alpha = 1.0f, beta = 2.0f, evaporation_rate = 0.5f;
+    size_t num_ants = 25;
+    static Result<AcoOptions> from_toml(const TomlTable &table);
+    Result<bool> validate() const;
+};
+
+struct GAOptions { // mod.rs:816-905
+    HeuristicOptions heuristic;
+    float mutation_probability = 0.001f;
+    size_t n_elite = 3;
+    static Result<GAOptions> from_toml(const TomlTable &table);
+    Result<bool> validate() const;
+};
+
+struct AppOptions { // mod.rs:1586-1596; only the sub-tables this path consumes are modelled
     std::optional<HeuristicOptions> heuristic;
-    // extension table [stage.cuda] (never required): mode = "ref"|"best", path = "auto"|"matrix"|"recompute"
+    std::optional<AcoOptions> aco;
+    std::optional<GAOptions> ga;
+    // extension table [stage.cuda] (never required): mode = "ref"|"best", path = "auto"|"matrix"|"recompute",
+    // seed = <integer> (the population solvers' Philox key; the reference's RNG is unseeded)
     std::string cuda_mode, cuda_path;
+    uint64_t cuda_seed = 0;
 };
 
 // ---- solvers (same free-function convention as the reference) ------------------------------------
@@ -214,6 +234,17 @@ Solution solve(const TspProblem &problem, const HeuristicOptions &opts, const Pr
 namespace nearest_neighbor {
 Solution solve(const TspProblem &problem, const HeuristicOptions &opts, const ProgressSender *progress_tx,
                const std::vector<size_t> *init_tour);
+}
+namespace ant_colony { // src/tsp/ant_colony.rs:92-239; `seed` keys the Philox stream (extension)
+Solution solve(const TspProblem &problem, const AcoOptions &opts, const ProgressSender *progress_tx,
+               const std::vector<size_t> *init_tour, uint64_t seed = 0);
+}
+namespace genetic_algorithm { // src/tsp/genetic_algorithm.rs:16-44
+Solution solve(const TspProblem &problem, const GAOptions &opts, const ProgressSender *progress_tx,
+               const std::vector<size_t> *init_tour, uint64_t seed = 0);
+}
+namespace random_shuffle { // src/tsp/random_shuffle.rs: a shuffled order of the city ids (splitmix64-seeded here)
+Solution solve(const TspProblem &problem, uint64_t seed = 0);
 }
 
 Result<bool> validate_tour(const std::vector<size_t> &tour, const std::vector<KDPoint> &cities); // mod.rs:1620-1634

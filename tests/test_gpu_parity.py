@@ -1099,6 +1099,83 @@ def test_aco_reference_edge_cases_and_option_validation(T, ctx):
         p5.aco(1, init_tour=[0, 1, 2, 3, 3])
 
 
+# ---- K8 GA population step (genetic_algorithm.rs) ---------------------------
+#
+# Same parity notion as K7: the reference's RNG is unseeded, so the CUDA path is compared bit for bit
+# (best tour, best length, mutation count) with the oracle port that shares its Philox stream and its
+# blocked roulette sums; the crossover operator itself is pinned by the reference's unit vectors
+# (tests/test_oracle_goldens.py) and the result spread by docs/benchmarks.md:39,139-141.
+
+def check_ga(T, prob, P, seed, init=None, **kw):
+    want_t, want_c, want_st = O.ga(P, seed, init_tour=init, **kw)
+    got_t, got_c, st = prob.ga(seed, init_tour=init, **kw)
+    assert sorted(got_t.tolist()) == list(range(P.n))
+    assert (got_t.astype(np.int64) == want_t).all(), (seed, kw)
+    assert np.float32(got_c) == np.float32(want_c) == np.float32(O.tour_length(P, got_t)), (seed, kw)
+    assert int(st.moves) == int(want_st.moves) and int(st.evals) == int(want_st.evals)
+    assert int(st.passes) == int(want_st.passes)
+    return got_t, got_c, st
+
+
+def test_ga_berlin52_equals_the_oracle_port(T, ctx, berlin52):
+    _, x, y = berlin52
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    nn = O.nn_tour(P, 3)
+    for seed in range(8):
+        check_ga(T, prob, P, seed, init=nn, epochs=400)
+        check_ga(T, prob, P, seed, init=None, epochs=200, mutation_probability=0.05)
+    _, c, st = check_ga(T, prob, P, 11, init=O.shuffle_tour(52, 12))  # GAOptions::default(): 10 000 epochs
+    assert int(st.passes) == 10000 and 7542.0 <= c <= 7542.0 * 1.25
+
+
+def test_ga_distribution_over_200_seeds(T, ctx, berlin52):
+    """200 seeded runs (300 epochs, shuffled warm start as `teeline solve ga` supplies): every run equals
+    the oracle port; all valid; the mean improves on the mean start by a wide margin."""
+    _, x, y = berlin52
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    costs, starts = [], []
+    for seed in range(200):
+        init = O.shuffle_tour(52, 2000 + seed)
+        _, c, _ = check_ga(T, prob, P, seed, init=init, epochs=300, mutation_probability=0.01)
+        costs.append(c)
+        starts.append(O.tour_length(P, init))
+    assert np.mean(costs) < 0.6 * np.mean(starts) and min(costs) >= 7544.36
+
+
+@pytest.mark.parametrize("n,epochs", [(2, 5), (3, 5), (4, 20), (5, 20), (7, 30), (8, 30), (255, 12), (257, 12),
+                                      (1000, 4)])
+def test_ga_synthetic_sizes(T, ctx, n, epochs):
+    x, y = O.gen_uniform(n, 700 + n)
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    check_ga(T, prob, P, 7, init=O.shuffle_tour(n, 3), epochs=epochs, mutation_probability=0.2)
+    check_ga(T, prob, P, 8, init=None, epochs=epochs, n_elite=0 if n >= 4 else 1)
+    check_ga(T, prob, P, 9, init=None, epochs=epochs, n_elite=n, mutation_probability=1.0)  # elites only
+
+
+def test_ga_explicit_duplicates_and_option_validation(T, ctx, golden_dir):
+    n, tri = read_explicit(os.path.join(golden_dir, "gr17.tsp"))
+    check_ga(T, T.Problem.explicit(ctx, tri, n), O.Problem(tri=tri, n=n), 5, init=np.arange(n), epochs=200)
+    # coincident cities (zero-length edges; equal fitnesses exercise the stable sort's tie order)
+    x, y = O.gen_uniform(60, 5)
+    x[:20], y[:20] = x[0], y[0]
+    check_ga(T, T.Problem.euc2d(ctx, x, y), O.Problem(x, y), 4, init=O.shuffle_tour(60, 1), epochs=150,
+             mutation_probability=0.1)
+    # all cities coincide: every length is 0 and every fitness is 0 (build_evaluator :117-121)
+    z = np.zeros(12, dtype=np.float32)
+    check_ga(T, T.Problem.euc2d(ctx, z, z), O.Problem(z, z), 4, init=None, epochs=10)
+    p5 = T.Problem.euc2d(ctx, [0.0, 0.0, 0.0, 1.0, 1.0], [0.0, 0.5, 1.0, 1.0, 0.0])
+    t, c, _ = p5.ga(1, init_tour=[0, 1, 2, 3, 4], epochs=0)  # test_ga_respects_initial_tour (:353-369)
+    assert t.tolist() == [0, 1, 2, 3, 4] and c == 4.0
+    for mp in (-0.1, 1.5, float("nan")):
+        with pytest.raises(T.TeelineError) as ei:
+            p5.ga(1, mutation_probability=mp)
+        assert "mutation_probability must be in [0, 1]" in str(ei.value)
+    with pytest.raises(T.TeelineError):
+        p5.ga(1, init_tour=[0, 1, 2, 3, 3])
+    with pytest.raises(T.TeelineError):
+        T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32).ga(1)
+
+
 def test_batch_beyond_one_cta_takes_the_population_engine(T, ctx):
     """n = 13 000 does not fit one CTA's shared memory: tl_two_opt_batch switches to K2-pop (tour
     records in global memory, work items scheduled over the whole GPU); same moves as the oracle."""

@@ -87,6 +87,36 @@ def test_cli_config_errors_match_reference_messages(bins, tmp_path):
         assert rc == 1 and want in err, (src, err)
 
 
+def test_cli_population_option_errors_match_reference_messages(bins, tmp_path):
+    """[stage.aco] / [stage.ga] tables and the matching CLI flags: AcoOptions / GAOptions from_toml and
+    validate (src/tsp/mod.rs:1114-1196, 832-890), same messages."""
+    cli = bins[0]
+    inp = os.path.join(GOLDEN, "berlin52.tsp")
+    cases = {
+        "[[stage]]\nsolver = \"aco\"\n[stage.aco]\nalpha = -1.0\n": "alpha must be >= 0 (got -1)",
+        "[[stage]]\nsolver = \"aco\"\n[stage.aco]\nbeta = 7\n": "beta must be in [0, 6] (got 7)",
+        "[[stage]]\nsolver = \"aco\"\n[stage.aco]\nevaporation_rate = 1.0\n": "evaporation_rate must be in (0, 1) (got 1)",
+        "[[stage]]\nsolver = \"aco\"\n[stage.aco]\nnum_ants = 0\n": "num_ants must be >= 1",
+        "[[stage]]\nsolver = \"aco\"\n[stage.aco]\nants = 3\n":
+            "config: unknown field `ants` in [aco] — valid: epochs, platoo_epochs, n_nearest, verbose, alpha, beta, evaporation_rate, num_ants",
+        "[[stage]]\nsolver = \"aco\"\n[stage.aco]\nalpha = \"x\"\n": "config: `aco.alpha` must be a float, got \"x\"",
+        "[[stage]]\nsolver = \"ga\"\n[stage.ga]\nmutation_probability = 1.5\n": "mutation_probability must be in [0, 1] (got 1.5)",
+        "[[stage]]\nsolver = \"ga\"\n[stage.ga]\nn_elite = \"many\"\n": "config: `ga.n_elite` must be an integer, got \"many\"",
+        "[[stage]]\nsolver = \"ga\"\n[stage.ga]\nelite = 1\n":
+            "config: unknown field `elite` in [ga] — valid: epochs, platoo_epochs, n_nearest, verbose, mutation_probability, n_elite",
+        "[[stage]]\nsolver = \"ga\"\n[stage.aco]\nalpha = 1.0\n": "config: stage 0 (ga): `[stage.aco]` is not valid for this solver",
+    }
+    for k, (src, want) in enumerate(cases.items()):
+        f = tmp_path / f"p{k}.toml"
+        f.write_text(src)
+        rc, _, err = run([cli, "pipeline", "--config", str(f), "-i", inp])
+        assert rc == 1 and want in err, (src, err)
+    rc, _, err = run([cli, "solve", "aco", "--beta", "9", "-i", inp])
+    assert rc == 1 and "beta must be in [0, 6] (got 9)" in err
+    rc, _, err = run([cli, "solve", "ga", "--mutation_probability", "2", "-i", inp])
+    assert rc == 1 and "mutation_probability must be in [0, 1] (got 2)" in err
+
+
 def test_cli_argument_errors(bins):
     cli = bins[0]
     inp = os.path.join(GOLDEN, "berlin52.tsp")
@@ -161,6 +191,41 @@ def test_cli_goldens_berlin52(bins):
     rc, out, _ = run([cli, "solve", "2opt_best", "-i", inp])
     tb = O.two_opt_best(P, nn)[0]
     assert rc == 0 and parse_cli(out) == ("%.5f" % O.tour_length(P, tb), 0, [int(ids[p]) for p in tb])
+
+
+@pytest.mark.gpu
+def test_cli_population_solvers(bins, tmp_path):
+    """`teeline solve aco|ga` (= shuffle -> solver, main.rs:387-397) and a [[stage]] pipeline with
+    [stage.aco] / [stage.ga] tables: a valid tour whose printed cost is its exact-order length; the
+    same seed gives the same run; nn -> aco never ends worse than its warm start (ant_colony.rs:358-381)."""
+    cli = bins[0]
+    inp = os.path.join(GOLDEN, "berlin52.tsp")
+    ids, P = ids_and_problem("berlin52.tsp")
+    pos = {int(c): k for k, c in enumerate(ids)}
+
+    def check(argv):
+        rc, out, err = run([cli] + argv + ["-i", inp])
+        assert rc == 0, err
+        total, flag, route = parse_cli(out)
+        assert sorted(route) == sorted(int(c) for c in ids) and flag == 0
+        assert total == "%.5f" % O.tour_length(P, [pos[c] for c in route])
+        return float(total), route
+
+    a1 = check(["solve", "aco", "--seed", "3"])
+    assert a1 == check(["solve", "aco", "--seed", "3"]) and a1[0] < 7542 * 1.25
+    g1 = check(["solve", "ga", "--seed", "3", "--epochs", "2000"])
+    assert g1 == check(["solve", "ga", "--seed", "3", "--epochs", "2000"]) and g1[0] < 7542 * 1.6
+    assert g1 != check(["solve", "ga", "--seed", "4", "--epochs", "2000"])
+    cfg = tmp_path / "pop.toml"
+    cfg.write_text("[[stage]]\nsolver = \"nn\"\n[[stage]]\nsolver = \"aco\"\n[stage.aco]\nepochs = 40\nnum_ants = 10\n"
+                   "[stage.cuda]\nseed = 5\n[[stage]]\nsolver = \"ga\"\n[stage.ga]\nepochs = 300\nn_elite = 2\n")
+    total, _ = check(["pipeline", "--config", str(cfg)])
+    assert total <= 8980.91797  # nn's G1 length: aco keeps its warm start as the incumbent, ga seeds it as an elite
+    # the same stages against the oracle port, stage by stage
+    nn = O.nn_tour(P, 3)
+    t_aco, _, _ = O.aco(P, 5, init_tour=nn, epochs=40, num_ants=10)
+    t_ga, c_ga, _ = O.ga(P, 0, init_tour=t_aco, epochs=300, n_elite=2)
+    assert total == float("%.5f" % c_ga)
 
 
 @pytest.mark.gpu
