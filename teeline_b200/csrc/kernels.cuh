@@ -246,6 +246,12 @@ void launch_two_opt_batch(int cfg, const float2 *xy, uint32_t *tours, uint32_t n
                           long long max_moves, float screen_margin, void *counters, int grid, bool fast,
                           cudaStream_t st);
 
+// cluster per tour (small batches): returns the cluster size (1 = use the CTA-per-tour kernel) and its configuration
+int two_opt_batch_cluster_plan(uint32_t n, uint64_t batch, int sm_count, int *cfg_out);
+cudaError_t launch_two_opt_batch_cluster(int cfg, int cl, const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch,
+                                         int cyclic, long long max_moves, float screen_margin, void *counters, bool fast,
+                                         cudaStream_t st);
+
 // K2-pop: population 2-opt scheduled at work-item granularity over the whole GPU (k2_two_opt_pop.cu)
 constexpr int kPopR = 5;        // diagonals per lane (odd => conflict-free LDS.128)
 constexpr int kPopTI = 96;      // rows per work item (default; TL_POP_CHUNK overrides up to kPopMaxTI)

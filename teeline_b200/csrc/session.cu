@@ -976,7 +976,7 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
         set_error("tl_two_opt_batch: device allocation failed");
         return TL_ERR_NOMEM;
     }
-    struct { unsigned long long moves, scans; unsigned int next_tour, unconverged; } h{};
+    struct { unsigned long long moves, scans; unsigned int next_tour, unconverged; unsigned long long phase[5]; } h{};
     cudaEvent_t e0, e1;
     TL_CUDA_TRY(cudaEventCreate(&e0));
     TL_CUDA_TRY(cudaEventCreate(&e1));
@@ -1016,9 +1016,16 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
             launch_pop_extract(d_recs.p, n, npad, batch, d_t.p, c->sm_count, st);
             c->launches += 3;
         } else {
-            const int cfg = two_opt_batch_config(n, batch, c->sm_count);
-            const int grid = two_opt_batch_grid(cfg, n, batch, c->sm_count, p->fast_sqrt, margin >= 0.0f);
-            launch_two_opt_batch(cfg, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p, grid, p->fast_sqrt, st);
+            int ccfg = 0;
+            const int cl = two_opt_batch_cluster_plan(n, batch, c->sm_count, &ccfg);
+            if (cl > 1) { // fewer tours than CTA slots: a thread-block cluster per tour
+                e = launch_two_opt_batch_cluster(ccfg, cl, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p,
+                                                 p->fast_sqrt, st);
+            } else {
+                const int cfg = two_opt_batch_config(n, batch, c->sm_count);
+                const int grid = two_opt_batch_grid(cfg, n, batch, c->sm_count, p->fast_sqrt, margin >= 0.0f);
+                launch_two_opt_batch(cfg, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p, grid, p->fast_sqrt, st);
+            }
             c->launches++;
         }
         if (e == cudaSuccess) e = cudaGetLastError();
@@ -1041,6 +1048,10 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
     cudaEventDestroy(e1);
     if (e != cudaSuccess) { set_error("tl_two_opt_batch: %s", cudaGetErrorString(e)); return TL_ERR_CUDA; }
     if (hp.error) { set_error("tl_two_opt_batch: work queue overrun (a worker stalled)"); return TL_ERR_CUDA; }
+    if (!use_pop && h.phase[4] && getenv("TL_BATCH_PHASES")) // -DTL_TIMELINE builds only
+        fprintf(stderr, "[tl] batch phases per CTA step (kcycles): scan %.2f  wait-cta %.2f  exchange %.2f  apply %.2f  (%llu CTA steps)\n",
+                h.phase[0] / 1e3 / h.phase[4], h.phase[1] / 1e3 / h.phase[4], h.phase[2] / 1e3 / h.phase[4],
+                h.phase[3] / 1e3 / h.phase[4], h.phase[4]);
     if (stats) {
         const uint64_t nn = n;
         const uint64_t pairs = n < 4 ? 0 : (cyclic ? nn * (nn - 3) / 2 : (nn - 3) * (nn - 2) / 2);

@@ -593,9 +593,10 @@ def test_matrix_scan_only_10k_f32_and_i32(T, ctx):
 
 # ---- K2-batch: one CTA per tour, whole search in one launch (multi-start / GA population) ------------
 
-def check_batch(T, ctx, x, y, tours, cyclic=False, max_moves=-1):
-    """Both batched engines -- K2-pop (work items of single scans scheduled over the whole GPU) and the
-    CTA-per-tour kernel -- against the oracle's complete searches, tour by tour."""
+def check_batch(T, ctx, x, y, tours, cyclic=False, max_moves=-1, engines=None):
+    """The batched engines -- K2-pop (work items of single scans scheduled over the whole GPU), the
+    CTA-per-tour kernel and the cluster-per-tour kernel at every cluster size -- against the oracle's
+    complete searches, tour by tour."""
     P = O.Problem(x, y)
     p = T.Problem.euc2d(ctx, x, y)
     algo = T.ALGO_TWO_OPT_BEST_CYCLIC if cyclic else T.ALGO_TWO_OPT_BEST
@@ -603,11 +604,17 @@ def check_batch(T, ctx, x, y, tours, cyclic=False, max_moves=-1):
     moves = sum(w[1].moves for w in want)
     passes = sum(w[1].passes for w in want)
     evals = sum(w[1].evals for w in want)
-    saved = os.environ.get("TL_BATCH_ENGINE")
-    forced = [saved] if saved else ["pop", "cta"]
+    saved = {k: os.environ.get(k) for k in ("TL_BATCH_ENGINE", "TL_BATCH_CLUSTER")}
+    forced = engines or ([saved["TL_BATCH_ENGINE"]] if saved["TL_BATCH_ENGINE"] else
+                         ["pop", "cta", "cluster2", "cluster4", "cluster8", "auto"])
     try:
         for engine in forced:
-            os.environ["TL_BATCH_ENGINE"] = engine
+            os.environ.pop("TL_BATCH_CLUSTER", None)
+            os.environ["TL_BATCH_ENGINE"] = "pop" if engine == "pop" else "cta"
+            if engine == "cta":
+                os.environ["TL_BATCH_CLUSTER"] = "1"
+            elif engine.startswith("cluster"):
+                os.environ["TL_BATCH_CLUSTER"] = engine[len("cluster"):]
             got, st, lengths = p.two_opt_batch(tours, algo, max_moves=max_moves)
             for b, (want_t, _, _) in enumerate(want):
                 assert (got[b].astype(np.int64) == want_t).all(), f"{engine}: tour {b} differs"
@@ -616,10 +623,11 @@ def check_batch(T, ctx, x, y, tours, cyclic=False, max_moves=-1):
             # the whole batch is ONE search launch (+ record set-up/extraction for K2-pop) + ONE length launch
             assert int(st.launches) == (4 if engine == "pop" and len(x) >= 4 and max_moves != 0 else 2), engine
     finally:
-        if saved is None:
-            os.environ.pop("TL_BATCH_ENGINE", None)
-        else:
-            os.environ["TL_BATCH_ENGINE"] = saved
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     return got, st
 
 
@@ -639,8 +647,27 @@ def test_batch_every_launch_configuration(T, ctx, monkeypatch, cfg):
     n = 700
     x, y = O.gen_uniform(n, 4242)
     tours = np.stack([O.nn_tour(O.Problem(x, y), 3)] + [O.shuffle_tour(n, s) for s in range(1, 6)])
-    check_batch(T, ctx, x, y, tours, max_moves=40)
-    check_batch(T, ctx, x, y, tours[:2], cyclic=True, max_moves=25)
+    check_batch(T, ctx, x, y, tours, max_moves=40, engines=["cta"])
+    check_batch(T, ctx, x, y, tours[:2], cyclic=True, max_moves=25, engines=["cta"])
+
+
+@pytest.mark.parametrize("cl", [2, 4, 8])
+def test_batch_cluster_per_tour(T, ctx, monkeypatch, cl):
+    """A thread-block cluster per tour (DSMEM ticket, candidates exchanged with one cluster barrier per
+    step): more tours than resident clusters (every cluster walks several tours), coordinates outside
+    the fast-sqrt domain (the IEEE instantiation), a converging run, and a size whose records make
+    the kernel fall back to bigger CTAs."""
+    engine = [f"cluster{cl}"]
+    x, y = O.gen_uniform(300, 77)
+    tours = np.stack([O.shuffle_tour(300, s) for s in range(1, 700 // cl)])
+    check_batch(T, ctx, x, y, tours, max_moves=6, engines=engine)
+    check_batch(T, ctx, x, y, tours[:5], engines=engine)  # to the local optimum
+    check_batch(T, ctx, x * np.float32(1e-9), y * np.float32(1e-9), tours[:4], max_moves=30, engines=engine)  # some |c| < 2^-27
+    n = 4000  # 65 KB of records: 256 x 4 no longer fits an SM, the plan takes 512 x 2
+    x, y = O.gen_uniform(n, 4000)
+    tours = np.stack([O.shuffle_tour(n, s) for s in (1, 2, 3)])
+    check_batch(T, ctx, x, y, tours, max_moves=8, engines=engine)
+    check_batch(T, ctx, x, y, tours[:2], cyclic=True, max_moves=5, engines=engine)
 
 
 def test_batch_berlin52_population(T, ctx, berlin52):
