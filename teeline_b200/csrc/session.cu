@@ -255,6 +255,22 @@ void build_matrix(tl_session *s, const uint32_t *d_tour)
     } else {
         launch_gather_slots(p->d_xy, d_tour, s->cs.p, s->n, s->sxy.p, nullptr, st);
         launch_k1_square(s->sxy.p, s->n, s->ld, p->fast_sqrt, p->nint_mode(), s->M.p, st);
+        if (getenv("TL_K1_TIMING")) { // tuning aid: warm kernel time (CUDA events, 20 back-to-back launches) on stderr
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, st);
+            for (int r = 0; r < 20; ++r) launch_k1_square(s->sxy.p, s->n, s->ld, p->fast_sqrt, p->nint_mode(), s->M.p, st);
+            cudaEventRecord(e1, st);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "[tl] k1_square n=%u %s: %.2f us per launch, %.1f GB/s written\n", s->n,
+                    p->kind == PK_EUC_NINT ? (p->grid_nint ? "nint-int32" : "nint-f64") : "f32", ms / 20 * 1e3,
+                    (double)s->n * s->ld * 4.0 / (ms / 20 * 1e-3) / 1e9);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
     }
     s->c->launches += 2;
 }
