@@ -67,7 +67,7 @@ enum {
 
 /* where distances come from during the scan */
 enum {
-    TL_PATH_AUTO = 0,     /* recompute for coordinate problems, matrix for EXPLICIT ones */
+    TL_PATH_AUTO = 0,     /* matrix for EXPLICIT and NINT_I32 problems, recompute for F32_EXACT coordinates */
     TL_PATH_MATRIX = 1,   /* n x n matrix in HBM, tour-ordered, re-permuted as the tour fragments */
     TL_PATH_RECOMPUTE = 2 /* distances recomputed from tour-ordered coordinates (bit-identical)   */
 };
