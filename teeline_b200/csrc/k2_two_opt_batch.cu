@@ -44,7 +44,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
+#include <vector>
 
 namespace tl {
 
@@ -80,24 +82,27 @@ __device__ __forceinline__ unsigned long long gtime_b() { return (unsigned long 
 
 namespace cg = cooperative_groups;
 
-constexpr int kMaxBands = 96; // bands of 32*R diagonals: enough for every n whose records fit shared memory
+// One work item of a scan (built on the host, batch_items below): four quarter-warp pieces that walk
+// `cnt` rows together.  Quarter q (lanes 8q .. 8q+7) starts at row r0[q] on the diagonals k0[q] + 5*(lane & 7) + r.
+// A full-width item has r0[q] equal and k0[q] = K0 + 40 q; the TAIL of a band -- the rows on which only a
+// prefix of its 160 diagonals still lies inside the triangle -- is tiled with 40-row x 40-diagonal pieces
+// instead, four pieces (of any bands) per item, so that a band costs ~3 k cells beyond the triangle
+// instead of 12.8 k (18 % of a 1000-city scan with full-width rows).
+struct __align__(16) BatchItem {
+    int32_t k0[4];
+    int32_t r0[4];
+    int32_t cnt, pad[3];
+};
+constexpr int QD = 8 * R; // diagonals (and rows) of a quarter-warp piece
 
-// first work item of every band (+ the total at [nbands]); rows of band b: jmax - (2 + b*BW) + 1
-__device__ __forceinline__ int fill_band_table(int *s_band_first, int n, int cyclic, int chunk, int &nbands_out)
+__device__ __forceinline__ void load_item(const BatchItem *__restrict__ items, int item, int lane, int &k0, int &r0, int &cnt)
 {
-    const int jmax = cyclic ? n - 1 : n - 2;
-    const int nbands = (n - 3 + BW - 1) / BW; // diagonals k = 2 .. n-2 in bands of BW
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < nbands; ++b) {
-            s_band_first[b] = acc;
-            acc += (jmax - (2 + b * BW) + 1 + chunk - 1) / chunk;
-        }
-        s_band_first[nbands] = acc;
-    }
-    __syncthreads();
-    nbands_out = nbands;
-    return s_band_first[nbands];
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(items + item));
+    const int4 b = __ldg(reinterpret_cast<const int4 *>(items + item) + 1);
+    const int q = lane >> 3;
+    k0 = (q == 0 ? a.x : q == 1 ? a.y : q == 2 ? a.z : a.w) + (lane & 7) * R;
+    r0 = q == 0 ? b.x : q == 1 ? b.y : q == 2 ? b.z : b.w;
+    cnt = __ldg(&items[item].cnt);
 }
 
 // tour-ordered records of one tour in shared memory (same layout and padding rules as build_pts_kernel)
@@ -125,7 +130,7 @@ __device__ __forceinline__ void stage_tour(Pt *pts, const float2 *__restrict__ x
     }
 }
 
-// One work item (band `bnd`, rows [r_begin, r_end) of it) walked by one warp.
+// One work item walked by one warp.
 // SCREEN: as in k2_two_opt.cu -- the walk evaluates deltas with the screening distance and
 // re-evaluates exactly (from the shared-memory records) whenever a candidate comes within the
 // rigorous margin of the best known delta.  `shared_best` is the best exact delta any thread of the
@@ -136,11 +141,11 @@ __device__ __forceinline__ void stage_tour(Pt *pts, const float2 *__restrict__ x
 // it -- so the result does not depend on when a thread sees an update.  publish(bits) is called with
 // every new thread-best.
 template <bool FAST, bool SCREEN, class Publish>
-__device__ __forceinline__ void scan_item(const Pt *pts, uint32_t n, int cyclic, int K0, int r_begin, int r_end, int lane,
+__device__ __forceinline__ void scan_item(const Pt *pts, uint32_t n, int cyclic, int k0, int r_begin, int cnt,
                                           float screen_margin, const volatile unsigned int *shared_best, Publish &&publish,
                                           float &best, uint32_t &bi, uint32_t &bj, float &thr)
 {
-    const int k0 = K0 + lane * R; // first diagonal of this lane
+    // k0: first diagonal of this lane; r_begin: its first row (equal across the warp for a full-width item)
     const Pt *srow = pts + r_begin;
     const Pt *scol = pts + r_begin + k0;
 
@@ -163,7 +168,7 @@ __device__ __forceinline__ void scan_item(const Pt *pts, uint32_t n, int cyclic,
     };
     auto step = [&](auto Uc, int tau) {
         constexpr int U = decltype(Uc)::value;
-        const Pt rp = srow[tau + 1];     // (x,y) of i+1 and s_i: same address in every lane
+        const Pt rp = srow[tau + 1];     // (x,y) of i+1 and s_i: one address per warp (per quarter in a tail item)
         const Pt nx = scol[tau + R + 1]; // next window point
         float dl[R];
 #pragma unroll
@@ -208,7 +213,6 @@ __device__ __forceinline__ void scan_item(const Pt *pts, uint32_t n, int cyclic,
         wy[U] = nx.y;
         ws[U] = nx.sp;
     };
-    const int cnt = r_end - r_begin;
     int t = 0;
     refresh();
 #pragma unroll 1
@@ -245,20 +249,16 @@ __device__ __forceinline__ unsigned long long warp_min_key(float best, uint32_t 
 template <bool FAST, bool SCREEN, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     two_opt_batch_kernel(const float2 *__restrict__ xy, uint32_t *__restrict__ tours, uint32_t n, uint32_t batch,
-                         int cyclic, long long max_moves, float screen_margin, int chunk,
-                         BatchCounters *__restrict__ ctr)
+                         int cyclic, long long max_moves, float screen_margin, const BatchItem *__restrict__ items,
+                         int nitems, BatchCounters *__restrict__ ctr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Pt *pts = reinterpret_cast<Pt *>(smem_raw);
     __shared__ unsigned long long s_key[2];
     __shared__ unsigned int s_tour, s_item, s_shared_best[2];
-    __shared__ int s_band_first[kMaxBands + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, nthreads = blockDim.x;
     const int nwarps = nthreads >> 5;
-    const int jmax = cyclic ? (int)n - 1 : (int)n - 2;
-    int nbands;
-    const int nitems = fill_band_table(s_band_first, (int)n, cyclic, chunk, nbands);
     const uint32_t npad = n + BW + 2;
     const unsigned int per_scan = (unsigned int)(nitems + nwarps); // tickets one scan consumes
 
@@ -301,12 +301,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 if (lane == 0) raw = atomicAdd(&s_item, 1u);
                 int item = (int)(__shfl_sync(0xffffffffu, raw, 0) - base);
                 if (item >= nitems) break;
-                int bnd = 0;
-                while (item >= s_band_first[bnd + 1]) ++bnd;
-                item -= s_band_first[bnd];
-                const int K0 = 2 + bnd * BW;
-                const int r_begin = item * chunk, r_end = min(r_begin + chunk, jmax - K0 + 1);
-                scan_item<FAST, SCREEN>(pts, n, cyclic, K0, r_begin, r_end, lane, screen_margin, &s_shared_best[par],
+                int k0, r0, cnt;
+                load_item(items, item, lane, k0, r0, cnt);
+                scan_item<FAST, SCREEN>(pts, n, cyclic, k0, r0, cnt, screen_margin, &s_shared_best[par],
                                         [&](unsigned int bits) { atomicMax(&s_shared_best[par], bits); }, best, bi, bj,
                                         thr);
             }
@@ -363,8 +360,8 @@ constexpr int kMaxCluster = 8;
 template <bool FAST, bool SCREEN, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     two_opt_batch_cluster_kernel(const float2 *__restrict__ xy, uint32_t *__restrict__ tours, uint32_t n, uint32_t batch,
-                                 int cyclic, long long max_moves, float screen_margin, int chunk,
-                                 BatchCounters *__restrict__ ctr)
+                                 int cyclic, long long max_moves, float screen_margin,
+                                 const BatchItem *__restrict__ items, int nitems, BatchCounters *__restrict__ ctr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Pt *pts = reinterpret_cast<Pt *>(smem_raw);
@@ -372,15 +369,11 @@ __global__ void __launch_bounds__(MAXT, MINB)
     __shared__ unsigned long long s_ckey[2][kMaxCluster]; // [scan parity][rank]: every CTA's key of a step
     __shared__ unsigned int s_tour, s_ticket;
     __shared__ unsigned int s_shared_best[2]; // [scan parity]
-    __shared__ int s_band_first[kMaxBands + 1];
 
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int rank = cluster.block_rank(), csize = cluster.num_blocks();
     const int tid = threadIdx.x, lane = tid & 31, nthreads = blockDim.x;
     const int nwarps = nthreads >> 5;
-    const int jmax = cyclic ? (int)n - 1 : (int)n - 2;
-    int nbands;
-    const int nitems = fill_band_table(s_band_first, (int)n, cyclic, chunk, nbands);
     const uint32_t npad = n + BW + 2;
     const unsigned int per_scan = (unsigned int)nitems + csize * (unsigned int)nwarps; // tickets one scan consumes
     unsigned int *ticket0 = cluster.map_shared_rank(&s_ticket, 0);
@@ -433,13 +426,10 @@ __global__ void __launch_bounds__(MAXT, MINB)
             int item = as_item(fetch_raw());
             while (item < nitems) {
                 const unsigned int next_raw = fetch_raw();
-                int bnd = 0;
-                while (item >= s_band_first[bnd + 1]) ++bnd;
-                item -= s_band_first[bnd];
-                const int K0 = 2 + bnd * BW;
-                const int r_begin = item * chunk, r_end = min(r_begin + chunk, jmax - K0 + 1);
-                scan_item<FAST, SCREEN>(pts, n, cyclic, K0, r_begin, r_end, lane, screen_margin, &s_shared_best[par],
-                                        publish, best, bi, bj, thr);
+                int k0, r0, cnt;
+                load_item(items, item, lane, k0, r0, cnt);
+                scan_item<FAST, SCREEN>(pts, n, cyclic, k0, r0, cnt, screen_margin, &s_shared_best[par], publish, best,
+                                        bi, bj, thr);
                 item = as_item(next_raw);
             }
 
@@ -513,22 +503,68 @@ constexpr size_t kSmemPerSM = 200 * 1024; // shared memory the resident CTAs of 
 
 bool cfg_fits(int c, uint32_t n) { return two_opt_batch_smem_bytes(n) * kCfgs[c].minb <= kSmemPerSM; }
 
-// rows per work item: 16 (small CTAs) .. 2 (1024 threads) items per warp and scan (measured:
-// profiles/r01n_batch_scaling.txt), at least 8 rows:
-// an item costs a fixed prologue, so big CTAs on a short scan take longer items
-int chunk_rows(uint32_t n, int cyclic, int threads)
+// The work items of one scan for `threads` threads working on a tour (all CTAs of a cluster together):
+// ~16 (small CTAs) .. 2 (1024 threads) full-width items per warp (measured: profiles/r01n_batch_scaling.txt;
+// an item costs a fixed prologue, so big CTAs on a short scan take longer items; at least 8 rows), then the
+// bands' tails as quarter-warp pieces, four to an item (BatchItem above).
+std::vector<BatchItem> batch_items(uint32_t n, int cyclic, int threads)
 {
     const int jmax = cyclic ? (int)n - 1 : (int)n - 2;
-    const int nbands = ((int)n - 3 + BW - 1) / BW;
-    long long rows = 0;
-    for (int b = 0; b < nbands; ++b) rows += jmax - (2 + b * BW) + 1;
+    const int nbands = ((int)n - 3 + BW - 1) / BW; // diagonals k = 2 .. n-2 in bands of BW
+    struct Piece { int k0, r0, cnt; };
+    std::vector<Piece> pieces;
     long long per_warp = threads <= 128 ? 16 : threads <= 256 ? 8 : threads <= 512 ? 4 : threads <= 1024 ? 2 : 3;
     if (const char *ev = getenv("TL_BATCH_IPW")) per_warp = std::max(1, atoi(ev));
-    const long long want = per_warp * (threads / 32);
-    return (int)std::max<long long>(8, (rows + want - 1) / want);
+    const long long target = per_warp * (threads / 32); // items per scan to aim for
+    long long full_rows = 0, all_rows = 0;
+    for (int b = 0; b < nbands; ++b) all_rows += jmax - (2 + b * BW) + 1;
+    // rows of a tail piece: no longer than a full-width item is going to be (many threads on a short scan)
+    const int prow = (int)std::min<long long>(QD, std::max<long long>(8, (all_rows + target - 1) / target));
+    for (int b = 0; b < nbands; ++b) {
+        const int K0 = 2 + b * BW, H = jmax - K0 + 1; // H rows on the band's first diagonal, H - d on diagonal K0 + d
+        const int Hf = std::max(0, H - (BW - 1));     // rows on which all BW diagonals are inside the triangle
+        full_rows += Hf;
+        for (int row0 = Hf; row0 < H; row0 += prow)
+            for (int q = 0; q < 4; ++q)
+                if (row0 + q * QD <= H - 1) pieces.push_back({K0 + q * QD, row0, std::min(prow, H - row0)});
+    }
+    const int tail_items = (int)(pieces.size() + 3) / 4;
+    const long long want = std::max<long long>(1, target - tail_items);
+    const int chunk = (int)std::max<long long>(8, (full_rows + want - 1) / want);
+    std::vector<BatchItem> items;
+    for (int b = 0; b < nbands; ++b) {
+        const int K0 = 2 + b * BW, H = jmax - K0 + 1, Hf = std::max(0, H - (BW - 1));
+        for (int r = 0; r < Hf; r += chunk) {
+            BatchItem it{};
+            for (int q = 0; q < 4; ++q) {
+                it.k0[q] = K0 + q * QD;
+                it.r0[q] = r;
+            }
+            it.cnt = std::min(chunk, Hf - r);
+            items.push_back(it);
+        }
+    }
+    for (size_t p0 = 0; p0 < pieces.size(); p0 += 4) {
+        BatchItem it{};
+        for (int q = 0; q < 4; ++q) {
+            if (p0 + q < pieces.size()) {
+                it.k0[q] = pieces[p0 + q].k0;
+                it.r0[q] = pieces[p0 + q].r0;
+                it.cnt = std::max(it.cnt, pieces[p0 + q].cnt);
+            } else { // an empty quarter: every cell beyond the triangle (padding records, delta = +inf)
+                it.k0[q] = jmax + 1;
+                it.r0[q] = 0;
+            }
+        }
+        items.push_back(it);
+    }
+    // longest items first: the ticket hands the short ones out last, which evens out the end of a scan
+    std::stable_sort(items.begin(), items.end(), [](const BatchItem &a, const BatchItem &b) { return a.cnt > b.cnt; });
+    return items;
 }
 
-using BatchKernel = void (*)(const float2 *, uint32_t *, uint32_t, uint32_t, int, long long, float, int, BatchCounters *);
+using BatchKernel = void (*)(const float2 *, uint32_t *, uint32_t, uint32_t, int, long long, float, const BatchItem *, int,
+                             BatchCounters *);
 
 template <int T, int MINB>
 BatchKernel pick_variant(bool fast, bool screen)
@@ -652,9 +688,19 @@ int two_opt_batch_cluster_plan(uint32_t n, uint64_t batch, int sm_count, int *cf
     return cl;
 }
 
+// host copy of the work-item table of one scan for configuration `cfg` and clusters of `cl` CTAs
+std::vector<unsigned char> two_opt_batch_item_table(uint32_t n, int cyclic, int cfg, int cl, int *nitems)
+{
+    const std::vector<BatchItem> items = batch_items(n, cyclic, kCfgs[cfg].threads * cl);
+    *nitems = (int)items.size();
+    std::vector<unsigned char> raw(items.size() * sizeof(BatchItem));
+    memcpy(raw.data(), items.data(), raw.size());
+    return raw;
+}
+
 cudaError_t launch_two_opt_batch_cluster(int cfg, int cl, const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch,
-                                         int cyclic, long long max_moves, float screen_margin, void *counters, bool fast,
-                                         cudaStream_t st)
+                                         int cyclic, long long max_moves, float screen_margin, const void *items,
+                                         int nitems, void *counters, bool fast, cudaStream_t st)
 {
     const bool screen = fast && screen_margin >= 0.0f;
     const int threads = kCfgs[cfg].threads;
@@ -677,21 +723,19 @@ cudaError_t launch_two_opt_batch_cluster(int cfg, int cl, const float2 *xy, uint
     if (max_clusters < 1) max_clusters = 1;
     const uint64_t nclusters = batch < (uint64_t)max_clusters ? batch : (uint64_t)max_clusters;
     lc.gridDim = dim3((unsigned)(nclusters * cl));
-    // work items per scan: the cluster's warps together take ~4 each, so that a CTA sharing its SM
-    // with other tours can fall behind without stalling the step
-    const int chunk = chunk_rows(n, cyclic, threads * cl);
-    return cudaLaunchKernelEx(&lc, k, xy, tours, n, (uint32_t)batch, cyclic, max_moves, screen_margin, chunk,
+    return cudaLaunchKernelEx(&lc, k, xy, tours, n, (uint32_t)batch, cyclic, max_moves, screen_margin,
+                              reinterpret_cast<const BatchItem *>(items), nitems,
                               reinterpret_cast<BatchCounters *>(counters));
 }
 
 void launch_two_opt_batch(int cfg, const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
-                          long long max_moves, float screen_margin, void *counters, int grid, bool fast,
-                          cudaStream_t st)
+                          long long max_moves, float screen_margin, const void *items, int nitems, void *counters,
+                          int grid, bool fast, cudaStream_t st)
 {
     const bool screen = fast && screen_margin >= 0.0f;
     const int threads = kCfgs[cfg].threads;
     pick_kernel(cfg, fast, screen)<<<grid, threads, two_opt_batch_smem_bytes(n), st>>>(
-        xy, tours, n, (uint32_t)batch, cyclic, max_moves, screen_margin, chunk_rows(n, cyclic, threads),
+        xy, tours, n, (uint32_t)batch, cyclic, max_moves, screen_margin, reinterpret_cast<const BatchItem *>(items), nitems,
         reinterpret_cast<BatchCounters *>(counters));
 }
 

@@ -1,5 +1,6 @@
 // kernels.cuh -- kernel-side types and host launcher prototypes (internal).
 #pragma once
+#include <vector>
 
 #include "common.cuh"
 #include "shard_exchange.cuh"
@@ -242,15 +243,17 @@ int two_opt_batch_config(uint32_t n, uint64_t batch, int sm_count);
 int two_opt_batch_grid(int cfg, uint32_t n, uint64_t batch, int sm_count, bool fast, bool screen);
 // counters: {u64 moves, u64 scans, u32 next_tour, u32 unconverged}, zeroed by the caller;
 // screen_margin < 0 disables screening (common.cuh: kScreenMarginScale)
+// work items of one scan (full-width row chunks + the bands' tails as quarter-warp pieces), host copy
+std::vector<unsigned char> two_opt_batch_item_table(uint32_t n, int cyclic, int cfg, int cl, int *nitems);
 void launch_two_opt_batch(int cfg, const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch, int cyclic,
-                          long long max_moves, float screen_margin, void *counters, int grid, bool fast,
-                          cudaStream_t st);
+                          long long max_moves, float screen_margin, const void *items, int nitems, void *counters,
+                          int grid, bool fast, cudaStream_t st);
 
 // cluster per tour (small batches): returns the cluster size (1 = use the CTA-per-tour kernel) and its configuration
 int two_opt_batch_cluster_plan(uint32_t n, uint64_t batch, int sm_count, int *cfg_out);
 cudaError_t launch_two_opt_batch_cluster(int cfg, int cl, const float2 *xy, uint32_t *tours, uint32_t n, uint64_t batch,
-                                         int cyclic, long long max_moves, float screen_margin, void *counters, bool fast,
-                                         cudaStream_t st);
+                                         int cyclic, long long max_moves, float screen_margin, const void *items,
+                                         int nitems, void *counters, bool fast, cudaStream_t st);
 
 // K2-pop: population 2-opt scheduled at work-item granularity over the whole GPU (k2_two_opt_pop.cu)
 constexpr int kPopR = 5;        // diagonals per lane (odd => conflict-free LDS.128)

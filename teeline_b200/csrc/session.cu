@@ -1001,6 +1001,7 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
     if (e == cudaSuccess) e = cudaMemsetAsync(d_ctr.p, 0, ctr_bytes, st);
     if (e == cudaSuccess) e = cudaEventRecord(e0, st);
     DevBuf<Pt> d_recs;
+    DevBuf<unsigned char> d_items;
     DevBuf<PopTourCtl> d_ctl;
     DevBuf<int32_t> d_bands;
     DevBuf<unsigned long long> d_queue;
@@ -1034,13 +1035,27 @@ tl_status tl_two_opt_batch(tl_problem *p, int32_t algo, uint32_t *tours_inout, s
         } else {
             int ccfg = 0;
             const int cl = two_opt_batch_cluster_plan(n, batch, c->sm_count, &ccfg);
-            if (cl > 1) { // fewer tours than CTA slots: a thread-block cluster per tour
-                e = launch_two_opt_batch_cluster(ccfg, cl, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p,
-                                                 p->fast_sqrt, st);
+            const int cfg = cl > 1 ? ccfg : two_opt_batch_config(n, batch, c->sm_count);
+            int nitems = 0;
+            const std::vector<unsigned char> items = two_opt_batch_item_table(n, cyclic, cfg, cl, &nitems);
+            if (d_items.alloc(items.size()) != cudaSuccess) {
+                cudaGetLastError();
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+                set_error("tl_two_opt_batch: device allocation failed");
+                return TL_ERR_NOMEM;
+            }
+            e = cudaMemcpyAsync(d_items.p, items.data(), items.size(), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st); // `items` is a local
+            if (e != cudaSuccess) {
+                // reported below
+            } else if (cl > 1) { // fewer tours than CTA slots: a thread-block cluster per tour
+                e = launch_two_opt_batch_cluster(cfg, cl, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_items.p,
+                                                 nitems, d_ctr.p, p->fast_sqrt, st);
             } else {
-                const int cfg = two_opt_batch_config(n, batch, c->sm_count);
                 const int grid = two_opt_batch_grid(cfg, n, batch, c->sm_count, p->fast_sqrt, margin >= 0.0f);
-                launch_two_opt_batch(cfg, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_ctr.p, grid, p->fast_sqrt, st);
+                launch_two_opt_batch(cfg, p->d_xy, d_t.p, n, batch, cyclic, max_moves, margin, d_items.p, nitems, d_ctr.p,
+                                     grid, p->fast_sqrt, st);
             }
             c->launches++;
         }
