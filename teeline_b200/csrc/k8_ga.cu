@@ -9,8 +9,8 @@
 //   best() = the LAST individual of maximal fitness (Iterator::max_by, :264-269).
 //
 // Work decomposition (one launch of each per epoch):
-//   ga_rank_kernel   thread per individual: rank = #better + #equal-before (the stable sort as a
-//                    counting rank over the fitnesses in shared memory), scatter order[] and sfit[].
+//   ga_rank_kernel   warp per individual: rank = #better + #equal-before (the stable sort as a
+//                    counting rank, the lanes split the comparisons), scatter order[] and sfit[].
 //   ga_breed_kernel  CTA per pair of children (+ one CTA per elite): blocked roulette (roulette.cuh,
 //                    the same f32 addition order as the oracle port) for the two parents; ordered
 //                    crossover as a STREAM COMPACTION -- the reference walks the parent cyclically
@@ -143,23 +143,25 @@ __global__ void __launch_bounds__(T)
     for (int k = tid; k < n; k += T) pop[(size_t)b * n + k] = g[k];
 }
 
-// stable descending sort as a counting rank (:68, :277-280)
+// stable descending sort as a counting rank (:68, :277-280): one WARP per individual, the lanes split
+// the comparisons (L = 1000: 125 CTAs of 8 warps instead of 4 CTAs whose threads each walk all L)
 __global__ void __launch_bounds__(T)
     ga_rank_kernel(const float *__restrict__ fit, int L, int *__restrict__ order, float *__restrict__ sfit)
 {
-    extern __shared__ float s_fit[];
-    for (int k = threadIdx.x; k < L; k += T) s_fit[k] = fit[k];
-    __syncthreads();
-    const int a = blockIdx.x * T + threadIdx.x;
-    if (a >= L) return;
-    const float fa = s_fit[a];
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * (T / 32) + (threadIdx.x >> 5);
+    if (a >= L) return; // warp-uniform
+    const float fa = __ldg(&fit[a]);
     int r = 0;
-    for (int b = 0; b < L; ++b) {
-        const float fb = s_fit[b];
+    for (int b = lane; b < L; b += 32) {
+        const float fb = __ldg(&fit[b]);
         r += (fb > fa) || (fb == fa && b < a);
     }
-    order[r] = a;
-    sfit[r] = fa;
+    r = __reduce_add_sync(0xffffffffu, r);
+    if (lane == 0) {
+        order[r] = a;
+        sfit[r] = fa;
+    }
 }
 
 template <int KIND>
@@ -346,10 +348,8 @@ cudaError_t launch_ga_init(const float2 *xy, const float *tri, uint32_t n, bool 
 
 cudaError_t launch_ga_rank(const float *fit, uint32_t L, int *order, float *sfit, cudaStream_t st)
 {
-    const size_t smem = (size_t)4 * L;
-    cudaError_t e = allow_smem(ga_rank_kernel, smem);
-    if (e != cudaSuccess) return e;
-    ga_rank_kernel<<<(L + T - 1) / T, T, smem, st>>>(fit, (int)L, order, sfit);
+    constexpr unsigned per_cta = T / 32; // individuals (warps) per CTA
+    ga_rank_kernel<<<(L + per_cta - 1) / per_cta, T, 0, st>>>(fit, (int)L, order, sfit);
     return cudaSuccess;
 }
 
