@@ -640,12 +640,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # over ranks (every call does identical work; a single slow call -- first touch of a pool block, a
     # host hiccup -- would otherwise decide the headline).  The total over all calls is kept beside it.
     dt = float(np.median(call_s))
+    evals_per_call = evals / e2e_steps
+    evals_all_ranks = evals_per_call
     if dist is not None:
+        # every rank solves its own instance (seed + rank), which takes its own number of moves: the
+        # job's rate is the evaluations of ALL ranks over the slowest rank's time
         tdt = torch.tensor([dt, dt_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
         dt, dt_total = float(tdt[0].item()), float(tdt[1].item())
-    evals_per_call = evals / e2e_steps
-    e2e_value = world * evals_per_call / dt
+        tev = torch.tensor([evals_per_call], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tev, op=dist.ReduceOp.SUM)
+        evals_all_ranks = float(tev.item())
+    e2e_value = evals_all_ranks / dt
     h2d = 2 * 4 * n + 4 * n  # x, y; the NN tour goes back up as the 2-opt stage's seed
     d2h = 4 * n + 4 * n + 64  # NN tour, final tour, stats
 
@@ -724,7 +730,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                         ("to the 2-opt local optimum" if args.e2e_moves < 0 else f"max_moves={args.e2e_moves}") +
                         f") + tour read-back, pinned host buffers; median of {e2e_steps} calls",
                 "seconds": dt_total, "wall_ms_per_call": 1e3 * dt, "wall_ms_per_call_all": [1e3 * c for c in call_s],
-                "value_from_total_time": world * evals / dt_total,
+                "value_from_total_time": evals_all_ranks * e2e_steps / dt_total,
                 "moves_applied_per_call": e2e_applied / e2e_steps,
                 "nn_tour_ms_per_call": 1e3 * nn_s / e2e_steps,
                 "metric_note": "moves evaluated by the 2-opt stage / wall time of the WHOLE call (NN start tour "
