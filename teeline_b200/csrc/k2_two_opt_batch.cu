@@ -11,16 +11,18 @@
 // touches no global memory at all; CTAs pull tours from a global ticket counter (tours converge
 // after different move counts, so a static split would leave SMs idle at the tail).
 // Scan: diagonals k = j - i again (one new distance per move), cut like the single-tour kernel
-// into bands of 32*R diagonals x chunks of rows.  The work items of one scan are handed to the
-// CTA's warps through a shared-memory ticket (an item is ~60 rows, so a warp's last item costs a
-// few percent of a scan, whatever n is).  A lane owns R consecutive diagonals and walks its rows
-// with the (R+1)-point register window of k2_two_opt.cu, reading the records straight from
-// shared memory: the lanes of a warp sit on the same row i (warp-broadcast LDS.128 of the row
-// point) and on windows R records apart (odd R => conflict-free LDS.128).
-// Argmin: (delta, i, j) lexicographic through warp shuffles and shared memory -- independent of
-// which thread saw a candidate first.  Apply: the in-place reversal of two_opt_apply.cuh on the
-// shared-memory records.
-//
+// into bands of 32*R diagonals x chunks of rows; the tail of a band (rows on which only a prefix of
+// its diagonals is still inside the triangle) is tiled with quarter-warp pieces instead (BatchItem).
+// The work items of one scan -- a table built on the host -- are handed to the CTA's warps through a
+// shared-memory ticket (an item is ~60 rows, so a warp's last item costs a few percent of a scan,
+// whatever n is).  A lane owns R consecutive diagonals and walks its rows with the (R+1)-point
+// register window of k2_two_opt.cu, reading the records straight from shared memory: the lanes of a
+// warp (of a quarter-warp in a tail item) sit on the same row i (broadcast LDS.128 of the row point)
+// and on windows R records apart (odd R => conflict-free LDS.128).  The threshold below which a
+// screened delta is re-evaluated exactly is shared by all threads working on the tour.
+// Argmin: (delta, i, j) lexicographic as ONE 64-bit key, two REDUX and one shared-memory atomicMin per
+// warp -- independent of which thread saw a candidate first.  Apply: the in-place reversal of
+// two_opt_apply.cuh on the shared-memory records.
 //
 // CLUSTER PER TOUR (two_opt_batch_cluster_kernel): when the batch has fewer tours than the GPU has
 // CTA slots -- BASELINE config 5 sharded over 8 GPUs leaves 128 tours for 148 SMs -- a tour is a
