@@ -476,7 +476,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     seed = seed0 + rank  # one independent instance per rank
     P = pairs_per_scan(n)
     kinds = {"nint": T.DIST_NINT_I32, "f32": T.DIST_F32_EXACT}
-    paths = {"recompute": T.PATH_RECOMPUTE, "matrix": T.PATH_MATRIX}
+    paths = {"recompute": T.PATH_RECOMPUTE, "matrix": T.PATH_MATRIX, "auto": T.PATH_AUTO}
     x, y = instance(n, seed, args.dist)
     stream = torch.cuda.current_stream().cuda_stream
     ctx = T.Context(local_rank, stream=stream)
@@ -585,6 +585,55 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                       ("recompute_f32", "recompute", "f32")):
             if (p_path, p_dist) != (args.path, args.dist):
                 other_paths[label] = probe(label, p_path, p_dist)
+
+    # --- the metric's second half, "wall time to 2-opt local optimum", per mode:
+    #     host buffers in, NN start tour, the whole search through the C ABI, tour back; median of 3 calls.
+    #     Mode R is the reference's own first-improvement loop (the local optimum the Rust two_opt::solve
+    #     reaches, bit for bit); Mode B is the best-improvement scan the headline counts.
+    def to_optimum(algo, p_dist, p_path):
+        gx, gy = instance(n, seed, p_dist)
+        walls, st3 = [], None
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            p3 = T.Problem.euc2d(ctx, gx, gy, kinds[p_dist])
+            t3, st3, _ = p3.local_search(algo, p3.nn_tour(3), path=paths[p_path])
+            p3.close()
+            walls.append(time.perf_counter() - t0)
+        return {"dist": p_dist, "path": "matrix" if st3.path_used == T.PATH_MATRIX else "recompute",
+                "wall_ms": 1e3 * float(np.median(walls[1:])), "device_ms": float(st3.device_ms),
+                "moves": int(st3.moves), "passes_or_scans": int(st3.passes), "evals": int(st3.evals),
+                "launches": int(st3.launches)}
+
+    def or_opt_after_two_opt(p_dist, p_path):
+        """BASELINE config 3's second stage: Or-opt (the reference's or_opt::solve, bit-exact) from the
+        Mode B local optimum, to its own local optimum."""
+        gx, gy = instance(n, seed, p_dist)
+        p3 = T.Problem.euc2d(ctx, gx, gy, kinds[p_dist])
+        t2, _, _ = p3.local_search(T.ALGO_TWO_OPT_BEST, p3.nn_tour(3), path=paths[p_path])
+        walls, st3 = [], None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _t, st3, _ = p3.local_search(T.ALGO_OR_OPT, t2, path=paths[p_path])
+            walls.append(time.perf_counter() - t0)
+        p3.close()
+        return {"dist": p_dist, "path": "matrix" if st3.path_used == T.PATH_MATRIX else "recompute",
+                "wall_ms": 1e3 * float(np.median(walls[1:])), "device_ms": float(st3.device_ms), "moves": int(st3.moves),
+                "scans": int(st3.passes), "evals": int(st3.evals),
+                "candidates_per_s": int(st3.evals) / (1e-3 * float(st3.device_ms))}
+
+    wall_to_optimum = None
+    if rank == 0 and args.workload != "n100k":
+        wall_to_optimum = {
+            "note": f"n={n}: tl_problem_create_euc2d + tl_nn_tour + tl_local_search to the local optimum + tour read-back, "
+                    "wall clock, median of 3 calls after one warm-up",
+            "mode_r_reference_exact_f32": to_optimum(T.ALGO_TWO_OPT_REF, "f32", "auto"),
+            "mode_r_reference_exact_nint": to_optimum(T.ALGO_TWO_OPT_REF, "nint", "auto"),
+            "mode_b_best_improvement_nint_matrix": to_optimum(T.ALGO_TWO_OPT_BEST, "nint", "matrix"),
+            "mode_b_best_improvement_f32_recompute": to_optimum(T.ALGO_TWO_OPT_BEST, "f32", "recompute"),
+            "or_opt_from_the_mode_b_optimum_nint_matrix": or_opt_after_two_opt("nint", "matrix"),
+        }
 
     # --- the partitioned cases (configs 4 and 5): sharded across the ranks, measured against this
     #     run's own single-GPU baseline
@@ -740,6 +789,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "other_paths": other_paths,
+        "wall_to_local_optimum": wall_to_optimum,
         "moves_applied": moves_applied,
         "partitioned": partitioned,
     }
