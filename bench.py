@@ -612,7 +612,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         p3 = T.Problem.euc2d(ctx, gx, gy, kinds[p_dist])
         t2, _, _ = p3.local_search(T.ALGO_TWO_OPT_BEST, p3.nn_tour(3), path=paths[p_path])
         walls, st3 = [], None
-        for _ in range(3):
+        for _ in range(4):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             _t, st3, _ = p3.local_search(T.ALGO_OR_OPT, t2, path=paths[p_path])
