@@ -670,6 +670,23 @@ def test_batch_cluster_per_tour(T, ctx, monkeypatch, cl):
     check_batch(T, ctx, x, y, tours[:2], cyclic=True, max_moves=5, engines=engine)
 
 
+@pytest.mark.parametrize("B", [37, 74, 75, 148, 149, 296, 297, 600])
+def test_batch_sizes_around_the_engine_policy(T, ctx, B):
+    """Batch sizes on both sides of every threshold of the engine policy (clusters of 8/4/2 1024-thread
+    CTAs below S/2 tours, one CTA per tour up to 2 S, clusters of 2 x 256 as the queueing engine above):
+    whatever kernel runs, every tour equals the oracle's."""
+    n = 200
+    x, y = O.gen_uniform(n, 77)
+    P, p = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    tours = np.stack([O.shuffle_tour(n, s) for s in range(1, B + 1)])
+    got, st, lengths = p.two_opt_batch(tours, max_moves=5)
+    assert int(st.moves) == 5 * B and int(st.launches) == 2
+    for b in range(B):
+        want_t, _, _ = O.two_opt_best(P, tours[b], max_moves=5)
+        assert (got[b].astype(np.int64) == want_t).all(), b
+    assert (bits(lengths) == bits(p.tour_lengths(got))).all()
+
+
 def test_batch_berlin52_population(T, ctx, berlin52):
     _, x, y = berlin52
     P = O.Problem(x, y)
