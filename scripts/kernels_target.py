@@ -40,7 +40,15 @@ big = np.tile(tours, (16, 1))                       # 65 536 tours x 1000 = 262 
 p1.tour_lengths(big, T.LEN_EXACT)                   # K4 exact
 p1.tour_lengths(big, T.LEN_FAST)                    # K4 fast
 p1.tour_lengths(tours[:1024], T.LEN_EXACT)          # config 5 / GA population shape
-p1.two_opt_batch(tours[:1024], max_moves=50)        # K2-batch, 1024 x 50 scans
+p1.two_opt_batch(tours[:1024], max_moves=50)        # K2-batch, 1024 x 50 scans (clusters of 2 x 256)
+p1.two_opt_batch(tours[:128], max_moves=50)         # K2-batch, 128 tours, one 1024-thread CTA each
+p1.two_opt_batch(tours[:16], max_moves=50)          # K2-batch, 16 tours, clusters of 8 x 1024
+p1.aco(1, init_tour=tours[0], epochs=2, num_ants=148)  # K7: 2 epochs x 148 ants
+p1.ga(1, init_tour=tours[0], epochs=3)              # K8: 3 epochs, population 1000
+si = pi.session(T.ALGO_TWO_OPT_BEST, pi.nn_tour(3), T.PATH_MATRIX)  # k1_square (nint) + headline scan
+si.enqueue(3)
+ctx.sync()
+si.close()
 
 n3 = 100000
 x3, y3 = bench.gen_uniform(n3, n3)

@@ -12,3 +12,10 @@ for n in (1000, 10000, 20000, 50000):
         t = p.nn_tour(3)
     dt = (time.perf_counter() - t0) / 3
     print(f"nn_tour n={n}: {dt * 1e3:.2f} ms wall per call" + (" [TL_NN_NO_HEADS]" if os.environ.get("TL_NN_NO_HEADS") else ""), flush=True)
+gx, gy = bench.gen_grid(10000, 10000)
+pn = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32)
+pn.nn_tour(3)
+t0 = time.perf_counter()
+for _ in range(3):
+    pn.nn_tour(3)
+print(f"nn_tour n=10000 nint (integer grid): {(time.perf_counter() - t0) / 3 * 1e3:.2f} ms wall per call", flush=True)

@@ -356,7 +356,11 @@ tl_status tl_dist_matrix_packed_i32(tl_problem *p, int32_t *out)
 
 // ---- k-NN and the nearest-neighbour constructor ----------------------------------------
 
-static int metric_id(const tl_problem *p) { return p->kind == PK_EUC_NINT ? 2 : (p->fast_sqrt ? 0 : 1); }
+static int metric_id(const tl_problem *p)
+{
+    if (p->kind == PK_EUC_NINT) return p->grid_nint ? 3 : 2; // 3: integer coordinates, nint without FP64
+    return p->fast_sqrt ? 0 : 1;
+}
 
 tl_status tl_knn(tl_problem *p, uint32_t k, uint32_t *out)
 {

@@ -16,6 +16,8 @@
 // in the reference; see oracle/algos.inc.)
 #include "kernels.cuh"
 
+#include <algorithm>
+
 #include <math_constants.h>
 
 namespace tl {
@@ -25,10 +27,12 @@ namespace {
 constexpr int kTile = 1024;
 
 // METRIC: 0 = f32 metric with the guarded fast sqrt, 1 = f32 metric with the IEEE-safe sqrt,
-// 2 = TSPLIB nint metric (converted to f32: exact while distances stay below 2^24).
+// 2 = TSPLIB nint metric (converted to f32: exact while distances stay below 2^24), 3 = the same
+// integers from dist_nint_grid (integer coordinates, no FP64: common.cuh).
 template <int METRIC>
 __device__ __forceinline__ float metric(float x1, float y1, float x2, float y2)
 {
+    if (METRIC == 3) return (float)dist_nint_grid(x1, y1, x2, y2);
     if (METRIC == 2) return (float)dist_nint(x1, y1, x2, y2);
     return dist_f32<METRIC == 0>(x1, y1, x2, y2);
 }
@@ -284,6 +288,8 @@ void launch_knn(const float2 *xy, const float *tri, uint32_t n, uint32_t k, int 
         launch_knn_k<0>(xy, n, k, out, st);
     } else if (metric_id == 1) {
         launch_knn_k<1>(xy, n, k, out, st);
+    } else if (metric_id == 3) {
+        launch_knn_k<3>(xy, n, k, out, st);
     } else {
         launch_knn_k<2>(xy, n, k, out, st);
     }
@@ -291,13 +297,15 @@ void launch_knn(const float2 *xy, const float *tri, uint32_t n, uint32_t k, int 
 
 size_t nn_tour_smem_bytes(uint32_t n) { return (size_t)((n + 31) / 32) * 4; }
 
-// list heads kept in shared memory beside the visited bitmap: 8, 4 or 0 entries per city
+// list heads kept in shared memory beside the visited bitmap: as many entries per city as fit (at most
+// 16, at least 4, else none) -- every entry kept there is one global-memory round trip saved whenever
+// the nearer ones are all visited (10 entries at n = 10 000, 16 up to n = 6 300)
 static uint32_t nn_tour_heads(uint32_t n, uint32_t kk)
 {
     if (n > 65535) return 0;
-    for (uint32_t ks : {8u, 4u})
-        if (ks <= kk && nn_tour_smem_bytes(n) + (size_t)n * ks * 2 <= 200 * 1024) return ks;
-    return 0;
+    const size_t room = (size_t)200 * 1024 - std::min<size_t>((size_t)200 * 1024, nn_tour_smem_bytes(n));
+    const uint32_t ks = (uint32_t)std::min<size_t>(std::min<uint32_t>(16u, kk), room / ((size_t)n * 2));
+    return ks >= 4 ? ks : 0;
 }
 
 cudaError_t nn_tour_configure()
@@ -305,6 +313,7 @@ cudaError_t nn_tour_configure()
     cudaError_t e = cudaFuncSetAttribute(nn_tour_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_tour_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_tour_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_tour_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     return e;
 }
 
@@ -317,6 +326,8 @@ void launch_nn_tour(const float2 *xy, const float *tri, uint32_t n, const uint32
         nn_tour_kernel<0><<<1, 1024, smem, st>>>(xy, tri, n, knn, kk, ks, tour);
     else if (metric_id == 1)
         nn_tour_kernel<1><<<1, 1024, smem, st>>>(xy, tri, n, knn, kk, ks, tour);
+    else if (metric_id == 3)
+        nn_tour_kernel<3><<<1, 1024, smem, st>>>(xy, tri, n, knn, kk, ks, tour);
     else
         nn_tour_kernel<2><<<1, 1024, smem, st>>>(xy, tri, n, knn, kk, ks, tour);
 }
