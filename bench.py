@@ -632,6 +632,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "mode_r_reference_exact_nint": to_optimum(T.ALGO_TWO_OPT_REF, "nint", "auto"),
             "mode_b_best_improvement_nint_matrix": to_optimum(T.ALGO_TWO_OPT_BEST, "nint", "matrix"),
             "mode_b_best_improvement_f32_recompute": to_optimum(T.ALGO_TWO_OPT_BEST, "f32", "recompute"),
+            # the same moves and the same tour as Mode B, from cached row minima: a step re-evaluates only the
+            # pairs the previous move changed (`evals` = pair deltas actually computed)
+            "mode_b_cached_nint_matrix": to_optimum(T.ALGO_TWO_OPT_BEST_CACHED, "nint", "matrix"),
+            "mode_b_cached_f32_recompute": to_optimum(T.ALGO_TWO_OPT_BEST_CACHED, "f32", "recompute"),
             "or_opt_from_the_mode_b_optimum_nint_matrix": or_opt_after_two_opt("nint", "matrix"),
         }
 

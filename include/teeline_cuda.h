@@ -62,7 +62,11 @@ enum {
     TL_ALGO_TWO_OPT_BEST = 1,        /* "Mode B": best-improvement, same neighbourhood            */
     TL_ALGO_TWO_OPT_BEST_CYCLIC = 2, /* Mode B incl. closing edge (two-opt-algo.ts:71-99)         */
     TL_ALGO_OR_OPT = 3,              /* or_opt.rs:80-184 (best-improvement, bit-exact)            */
-    TL_ALGO_THREE_OPT = 4            /* three_opt.rs:16-218 (best-improvement over triples, bit-exact) */
+    TL_ALGO_THREE_OPT = 4,           /* three_opt.rs:16-218 (best-improvement over triples, bit-exact) */
+    TL_ALGO_TWO_OPT_BEST_CACHED = 5  /* Mode B, the same moves and tour as TL_ALGO_TWO_OPT_BEST, but a step only
+                                        re-evaluates the pairs the previous move changed (cached row minima):
+                                        the fast way to the local optimum; stats.evals counts the pairs actually
+                                        computed.  Not shardable, no tl_session_scan / time_scans. */
 };
 
 /* where distances come from during the scan */

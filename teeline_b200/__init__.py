@@ -14,7 +14,8 @@ import weakref
 import numpy as np
 
 from . import _capi as capi
-from ._capi import (ALGO_OR_OPT, ALGO_THREE_OPT, ALGO_TWO_OPT_BEST, ALGO_TWO_OPT_BEST_CYCLIC, ALGO_TWO_OPT_REF,
+from ._capi import (ALGO_OR_OPT, ALGO_THREE_OPT, ALGO_TWO_OPT_BEST, ALGO_TWO_OPT_BEST_CACHED, ALGO_TWO_OPT_BEST_CYCLIC,
+                    ALGO_TWO_OPT_REF,
                     DIST_F32_EXACT, DIST_NINT_I32, LEN_EXACT, LEN_FAST, PATH_AUTO, PATH_MATRIX,
                     PATH_RECOMPUTE, Move, Stats, TeelineError)
 

@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("TL_LIB") or os.path.join(_HERE, "libteeline_cuda.so")
 TL_OK = 0
 DIST_F32_EXACT, DIST_NINT_I32 = 0, 1
 ALGO_TWO_OPT_REF, ALGO_TWO_OPT_BEST, ALGO_TWO_OPT_BEST_CYCLIC, ALGO_OR_OPT, ALGO_THREE_OPT = 0, 1, 2, 3, 4
+ALGO_TWO_OPT_BEST_CACHED = 5
 PATH_AUTO, PATH_MATRIX, PATH_RECOMPUTE = 0, 1, 2
 LEN_EXACT, LEN_FAST = 0, 1
 NCCL_ID_BYTES = 128

@@ -51,6 +51,15 @@ struct DevState {
     unsigned long long found_key; // Mode R: (i << 32 | j) of the first improving pair, ~0 if none
     float last_delta;
     int32_t error; // 1: a sharded step timed out waiting for a peer's record (shard_exchange.cuh)
+    unsigned long long computed; // cached Mode B (k2_two_opt_cached.cu): pairs whose delta was computed
+};
+
+// cached Mode B: what the next step has to re-evaluate (written by the previous step's tail)
+struct CachedDesc {
+    int32_t nfull;      // rows to rescan from scratch, listed in `fullrows`; -1: every row
+    int32_t I, J;       // the move just applied: columns I .. J of the rows above changed
+    int32_t npart_rows; // rows 0 .. npart_rows-1 re-evaluate those columns only
+    int32_t active;     // CTAs of the launch that take part in the step
 };
 
 
@@ -231,6 +240,12 @@ void launch_build_cs(const Src &src, const uint32_t *tour, uint32_t n, uint32_t 
 void launch_gather_slots(const float2 *xy, const uint32_t *tour, const Cs *cs, uint32_t n, float2 *sxy,
                          int32_t *slot_city, cudaStream_t st);
 void launch_reset_slots(const Src &src, uint32_t n, uint32_t npad, int cyclic, cudaStream_t st);
+
+// K2 cached Mode B (k2_two_opt_cached.cu): one step = re-evaluate what the last move changed, reduce the
+// row keys, apply
+void launch_two_opt_cached_step(const Src &src, uint32_t n, int cyclic, unsigned long long *rowkey, CachedDesc *desc,
+                                int *fullrows, DevState *state, unsigned int *ticket, tl_move *log, uint64_t log_cap,
+                                int grid, cudaStream_t st);
 
 // K2-batch: one CTA per tour, tour records in shared memory
 constexpr int kBatchR = 5;              // diagonals per thread group (odd => conflict-free LDS.128)

@@ -72,6 +72,12 @@ struct tl_session {
     bool use_mailbox = false; // sharded 2-opt: per-rank minima exchanged inside the scan kernel (shard_exchange.cuh)
     ShardComm comm{};
 
+    // cached Mode B (TL_ALGO_TWO_OPT_BEST_CACHED is run as TL_ALGO_TWO_OPT_BEST with `cached` set)
+    bool cached = false;
+    DevBuf<unsigned long long> rowkey; // per-row minimum: order-preserving delta bits << 32 | j
+    DevBuf<CachedDesc> cdesc;
+    DevBuf<int> fullrows;
+
     DevBuf<BestF> cand; // shard_count * grid records (BestF and BestI have the same layout)
     DevBuf<DevState> state;
     DevBuf<unsigned int> ticket;
@@ -384,6 +390,18 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
         TL_CUDA_TRY(cudaGetLastError());
         return TL_OK;
     }
+    if (s->cached) {
+        // a full grid for the steps that rescan many rows; a step's tail decides how many of these CTAs
+        // the next step uses (the others leave at once)
+        const int cgrid = s->c->sm_count * 8;
+        for (uint32_t k = 0; k < steps; ++k) {
+            launch_two_opt_cached_step(s->src, s->n, s->cyclic, s->rowkey.p, s->cdesc.p, s->fullrows.p, s->state.p,
+                                       s->ticket.p, s->log.p, s->log_cap, cgrid, st);
+            s->c->launches += 1;
+        }
+        TL_CUDA_TRY(cudaGetLastError());
+        return TL_OK;
+    }
     for (uint32_t k = 0; k < steps; ++k) {
         if (s->matrix() && s->algo != TL_ALGO_OR_OPT && s->algo != TL_ALGO_THREE_OPT && s->repermute_every > 0 &&
             s->steps_since_permute >= (uint32_t)s->repermute_every)
@@ -478,6 +496,8 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     return tl::guarded([&]() -> tl_status {
     if (!p || !tour || !out) { set_error("tl_session_create: null argument"); return TL_ERR_INVALID; }
     *out = nullptr;
+    const bool cached = algo == TL_ALGO_TWO_OPT_BEST_CACHED; // Mode B with cached row minima: runs as Mode B
+    if (cached) algo = TL_ALGO_TWO_OPT_BEST;
     if (algo != TL_ALGO_TWO_OPT_BEST && algo != TL_ALGO_TWO_OPT_BEST_CYCLIC && algo != TL_ALGO_TWO_OPT_REF &&
         algo != TL_ALGO_OR_OPT && algo != TL_ALGO_THREE_OPT) {
         set_error("tl_session_create: unknown algo %d", algo);
@@ -505,6 +525,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     s->p = p;
     s->c = c;
     s->algo = algo;
+    s->cached = cached;
     s->path_used = want_matrix ? TL_PATH_MATRIX : TL_PATH_RECOMPUTE;
     s->n = p->n;
     s->cyclic = algo == TL_ALGO_TWO_OPT_BEST_CYCLIC || algo == TL_ALGO_OR_OPT || algo == TL_ALGO_THREE_OPT;
@@ -570,6 +591,18 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         set_error("tl_session_create: device allocation failed");
         return fail(TL_ERR_NOMEM);
     }
+    if (cached && !s->trivial) {
+        if (s->rowkey.alloc(p->n) != cudaSuccess || s->cdesc.alloc(1) != cudaSuccess || s->fullrows.alloc(p->n) != cudaSuccess) {
+            set_error("tl_session_create: device allocation failed");
+            return fail(TL_ERR_NOMEM);
+        }
+        // every row key "none", first step: rescan every row
+        const CachedDesc d0{-1, 0, 0, 0, p->ctx->sm_count * 8};
+        cudaError_t ce = cudaMemsetAsync(s->rowkey.p, 0xff, (size_t)p->n * 8, c->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->cdesc.p, &d0, sizeof d0, cudaMemcpyHostToDevice, c->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream); // d0 is a local
+        if (ce != cudaSuccess) { set_error("tl_session_create: %s", cudaGetErrorString(ce)); return fail(TL_ERR_CUDA); }
+    }
     // or_opt::solve and three_opt::solve ignore the seed and return identity order when n < 4
     // (or_opt.rs:31-34, three_opt.rs:25-28)
     std::vector<uint32_t> ident;
@@ -600,6 +633,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         const size_t bytes = (size_t)p->n * s->ld * 4;
         s->repermute_every = bytes > ((size_t)96 << 20) ? 256 : 0;
         if (const char *ev = getenv("TL_REPERMUTE_EVERY")) s->repermute_every = atoi(ev);
+        if (cached) s->repermute_every = 0; // a cached step reads a few rows, not the triangle
         configure_matrix_pin(s, bytes);
     } else {
         if (s->pts.alloc(s->npad) != cudaSuccess) { set_error("tl_session_create: device allocation failed"); return fail(TL_ERR_NOMEM); }
@@ -655,6 +689,10 @@ tl_status tl_session_set_shard(tl_session *s, int32_t index, int32_t count)
         if (count > 1) { set_error("Mode R does not shard (replicas only)"); return TL_ERR_UNSUPPORTED; }
         return TL_OK;
     }
+    if (s->cached) {
+        if (count > 1) { set_error("cached Mode B does not shard (a step touches a few rows)"); return TL_ERR_UNSUPPORTED; }
+        return TL_OK;
+    }
     DeviceGuard g(s->c);
     s->shard_index = index;
     s->shard_count = count;
@@ -694,6 +732,7 @@ tl_status tl_session_scan(tl_session *s, tl_move *best, int32_t *found)
     if (!s || !found) { set_error("tl_session_scan: null argument"); return TL_ERR_INVALID; }
     *found = 0;
     if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_scan: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
+    if (s->cached) { set_error("tl_session_scan: cached Mode B has no whole-triangle scan (use TL_ALGO_TWO_OPT_BEST)"); return TL_ERR_UNSUPPORTED; }
     if (s->trivial) return TL_OK;
     DeviceGuard g(s->c);
     tl_status rc = pull_state(s);
@@ -727,6 +766,7 @@ tl_status tl_session_time_scans(tl_session *s, uint32_t reps, double *avg_ms)
     return tl::guarded([&]() -> tl_status {
     if (!s || !avg_ms || reps == 0) { set_error("tl_session_time_scans: bad arguments"); return TL_ERR_INVALID; }
     if (s->algo == TL_ALGO_TWO_OPT_REF) { set_error("tl_session_time_scans: Mode R has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
+    if (s->cached) { set_error("tl_session_time_scans: cached Mode B has no whole-triangle scan"); return TL_ERR_UNSUPPORTED; }
     *avg_ms = 0.0;
     if (s->trivial) return TL_OK;
     DeviceGuard g(s->c);
@@ -862,7 +902,7 @@ tl_status tl_session_stats(tl_session *s, tl_stats *stats)
     memset(stats, 0, sizeof *stats);
     stats->passes = s->algo == TL_ALGO_TWO_OPT_REF ? s->h.passes : s->h.scans;
     stats->moves = s->h.moves;
-    stats->evals = stats->passes * s->pairs_per_scan;
+    stats->evals = s->cached ? s->h.computed : stats->passes * s->pairs_per_scan;
     stats->launches = s->c->launches - s->launches0;
     stats->repermutes = s->repermutes;
     stats->device_ms = s->device_ms;

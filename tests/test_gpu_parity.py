@@ -591,6 +591,96 @@ def test_matrix_scan_only_10k_f32_and_i32(T, ctx):
     s.close()
 
 
+# ---- K2 cached Mode B: the same moves as Mode B from cached row minima (k2_two_opt_cached.cu) ------------
+
+def check_cached(T, prob, P, start, path, max_moves=-1):
+    """TL_ALGO_TWO_OPT_BEST_CACHED against the oracle's full-scan Mode B: the same move log (positions
+    and exact deltas), the same tour, the same move and scan counts; it must have computed fewer pair
+    deltas than full scans would."""
+    want_t, want_st, want_mv = O.two_opt_best(P, start, max_moves=max_moves, nthreads=4, log_cap=1 << 16)
+    got_t, st, mv = prob.local_search(T.ALGO_TWO_OPT_BEST_CACHED, start, path=path, max_moves=max_moves, log_cap=1 << 16)
+    assert [(m[1], m[2]) for m in mv] == [(m[1], m[2]) for m in want_mv]
+    assert [np.float32(m[0]) for m in mv] == [np.float32(m[0]) for m in want_mv]
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes)) == (want_st.moves, want_st.passes)
+    assert bool(st.converged) == (max_moves < 0 or want_st.moves < max_moves)
+    assert 0 < int(st.evals) <= want_st.evals * 2 + 8  # row-oriented: never more than two full rescans' worth per scan
+    return got_t, st
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 13, 33, 257, 600, 1025, 1300])
+def test_cached_mode_b_synthetic(T, ctx, n):
+    """Shuffled starts: long segments (every row rescanned), short ones, rows whose cached minimum sat on
+    a changed column -- on the recompute path and on the f32 matrix."""
+    x, y = O.gen_uniform(n, 300 + n)
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    start = O.shuffle_tour(n, n + 1)
+    mm = -1 if n <= 600 else 120
+    check_cached(T, prob, P, start, T.PATH_RECOMPUTE, max_moves=mm)
+    check_cached(T, prob, P, start, T.PATH_MATRIX, max_moves=mm)
+
+
+def test_cached_mode_b_goldens_ties_and_metrics(T, ctx, berlin52, golden_dir):
+    _, x, y = berlin52
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    for start in (O.nn_tour(P, 3), np.arange(52)):
+        check_cached(T, prob, P, start, T.PATH_RECOMPUTE)
+        check_cached(T, prob, P, start, T.PATH_MATRIX)
+    rng = np.random.default_rng(3)
+    lx = rng.integers(0, 12, 400).astype(np.float32)
+    ly = rng.integers(0, 12, 400).astype(np.float32)  # lattice: many exactly equal deltas
+    check_cached(T, T.Problem.euc2d(ctx, lx, ly), O.Problem(lx, ly), O.shuffle_tour(400, 2), T.PATH_RECOMPUTE)
+    n = 600  # TSPLIB nint: integer deltas, ties everywhere
+    gx, gy = O.gen_grid(n, 77)
+    Pn = O.Problem(tri=O.matrix_packed_nint(gx, gy), n=n)
+    _, st = check_cached(T, T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32), Pn, O.shuffle_tour(n, 5), T.PATH_AUTO)
+    assert st.path_used == T.PATH_MATRIX
+    ne, tri = read_explicit(os.path.join(golden_dir, "gr17.tsp"))
+    check_cached(T, T.Problem.explicit(ctx, tri, ne), O.Problem(tri=tri, n=ne), np.arange(ne), T.PATH_AUTO)
+
+
+def test_cached_mode_b_1k_and_budgets(T, ctx):
+    x, y = O.gen_uniform(1000, 1000)
+    P, prob = O.Problem(x, y), T.Problem.euc2d(ctx, x, y)
+    nn = O.nn_tour(P, 3)
+    t, st = check_cached(T, prob, P, nn, T.PATH_RECOMPUTE)
+    assert f5(O.tour_length(P, t)) == "25282.04297" and int(st.moves) == 170
+    assert int(st.evals) < 0.2 * 171 * 498501  # the point of the cache
+    check_cached(T, prob, P, nn, T.PATH_MATRIX, max_moves=37)
+    check_cached(T, prob, P, O.shuffle_tour(1000, 11), T.PATH_RECOMPUTE, max_moves=60)
+    for tiny in (2, 3):
+        xs, ys = O.gen_uniform(tiny, tiny)
+        tt, stt, _ = T.Problem.euc2d(ctx, xs, ys).local_search(T.ALGO_TWO_OPT_BEST_CACHED, np.arange(tiny)[::-1].copy())
+        assert tt.tolist() == list(range(tiny))[::-1] and int(stt.moves) == 0 and stt.converged == 1
+    s = prob.session(T.ALGO_TWO_OPT_BEST_CACHED, nn)
+    with pytest.raises(T.TeelineError):
+        s.scan()
+    with pytest.raises(T.TeelineError):
+        s.set_shard(0, 2)
+    s.close()
+
+
+def test_cached_mode_b_10k_equals_the_full_scan_path(T, ctx):
+    """BASELINE config 3 (n = 10 000, nint matrix): the cached search applies the 1508 moves of the
+    full-scan search, move for move (the full-scan path itself is checked against the oracle above),
+    with a few percent of its pair evaluations."""
+    n = 10000
+    gx, gy = O.gen_grid(n, n)
+    prob = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32)
+    nn = prob.nn_tour(3)
+    full_t, full_st, full_mv = prob.local_search(T.ALGO_TWO_OPT_BEST, nn, path=T.PATH_MATRIX, log_cap=1 << 16)
+    got_t, st, mv = prob.local_search(T.ALGO_TWO_OPT_BEST_CACHED, nn, path=T.PATH_MATRIX, log_cap=1 << 16)
+    assert mv == full_mv and (got_t == full_t).all()
+    assert (int(st.moves), int(st.passes)) == (int(full_st.moves), int(full_st.passes)) == (1508, 1509)
+    assert int(st.evals) < 0.1 * int(full_st.evals)
+    x, y = O.gen_uniform(n, n)
+    pf = T.Problem.euc2d(ctx, x, y)
+    nnf = pf.nn_tour(3)
+    a_t, a_st, a_mv = pf.local_search(T.ALGO_TWO_OPT_BEST, nnf, path=T.PATH_RECOMPUTE, log_cap=1 << 16)
+    b_t, b_st, b_mv = pf.local_search(T.ALGO_TWO_OPT_BEST_CACHED, nnf, path=T.PATH_RECOMPUTE, log_cap=1 << 16)
+    assert a_mv == b_mv and (a_t == b_t).all() and int(a_st.moves) == int(b_st.moves)
+
+
 # ---- K2-batch: one CTA per tour, whole search in one launch (multi-start / GA population) ------------
 
 def check_batch(T, ctx, x, y, tours, cyclic=False, max_moves=-1, engines=None):
