@@ -601,7 +601,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             p3.close()
             walls.append(time.perf_counter() - t0)
         return {"dist": p_dist, "path": "matrix" if st3.path_used == T.PATH_MATRIX else "recompute",
-                "wall_ms": 1e3 * float(np.median(walls[1:])), "device_ms": float(st3.device_ms),
+                "wall_ms": 1e3 * float(np.median(walls[1:])), "wall_ms_all": [1e3 * w for w in walls],
+                "device_ms": float(st3.device_ms),
                 "moves": int(st3.moves), "passes_or_scans": int(st3.passes), "evals": int(st3.evals),
                 "launches": int(st3.launches)}
 

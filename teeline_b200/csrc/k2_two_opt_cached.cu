@@ -79,14 +79,17 @@ __device__ __forceinline__ typename Pol::V pair_delta(const Pol &P, const typena
     return Val<V>::sub(Val<V>::add(e1, e2), Val<V>::add(Pol::sp(pi1), Pol::sp(pj1)));
 }
 
+// Every record load of this kernel goes to L2 (L2Pol, policy.cuh): consecutive steps overlap through
+// programmatic dependent launch, and an L1 hit on a record the previous step's tail rewrote would be stale.
 template <class Pol>
 __global__ void __launch_bounds__(256)
-    two_opt_cached_step_kernel(Pol P, int n, int cyclic, unsigned long long *__restrict__ rowkey, CachedDesc *desc,
+    two_opt_cached_step_kernel(Pol P0, int n, int cyclic, unsigned long long *__restrict__ rowkey, CachedDesc *desc,
                                int *__restrict__ fullrows, DevState *state, unsigned int *ticket,
                                tl_move *__restrict__ log, uint64_t log_cap)
 {
     using V = typename Pol::V;
     using Rec = typename Pol::Rec;
+    const L2Pol<Pol> P(P0);
     griddep_launch_dependents();
     griddep_wait(); // the previous step's move is applied and its description written
     if (*reinterpret_cast<const volatile int *>(&state->done)) return;

@@ -34,6 +34,12 @@ struct EucPol {
         }
     }
     __device__ __forceinline__ const Rec *base() const { return pts; }
+    // the record as L2 holds it (ld.global.cg), whatever this SM's L1 still has
+    __device__ __forceinline__ Rec load_l2(uint32_t q) const
+    {
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(pts + q));
+        return Pt{v.x, v.y, __float_as_int(v.z), v.w};
+    }
     static __device__ __forceinline__ Col col(const Rec &r) { return Col{r.x, r.y}; }
     static __device__ __forceinline__ V sp(const Rec &r) { return r.sp; }
     static __device__ __forceinline__ void set_sp(Rec &r, V v) { r.sp = v; }
@@ -70,6 +76,16 @@ struct MatPol {
 
     __device__ __forceinline__ Rec load(uint32_t q) const { return cs[q]; }
     __device__ __forceinline__ const Rec *base() const { return cs; }
+    __device__ __forceinline__ Rec load_l2(uint32_t q) const
+    {
+        const int4 v = __ldcg(reinterpret_cast<const int4 *>(cs + q));
+        Cs r;
+        r.slot = v.x;
+        r.sp_bits = v.y;
+        r.city = v.z;
+        r.pad = v.w;
+        return r;
+    }
     static __device__ __forceinline__ Col col(const Rec &r) { return Col{r.slot}; }
     static __device__ __forceinline__ V sp(const Rec &r) { return Val<V>::from_bits(r.sp_bits); }
     static __device__ __forceinline__ void set_sp(Rec &r, V v) { r.sp_bits = Val<V>::bits(v); }
@@ -89,6 +105,20 @@ struct MatPol {
     }
     __device__ __forceinline__ void store_sp(uint32_t q, V v) const { cs[q].sp_bits = Val<V>::bits(v); }
     __device__ __forceinline__ void store(uint32_t q, const Rec &r) const { cs[q] = r; }
+};
+
+// A policy whose record loads go to L2 (ld.global.cg), whatever this SM's L1 still holds.  Needed by every
+// kernel that is chained to its predecessor with programmatic dependent launch and reads records the
+// predecessor's tail rewrites: the CTAs of step k+1 are resident on an SM while step k's CTAs on the same
+// SM still load records into its L1; the L1 invalidation of the new grid has then already happened, step
+// k's tail (on another SM) rewrites the records, and an L1 hit in step k+1 is stale.  Seen with the cached
+// Mode B kernel at n = 1000 (all 16 KB of records stay in L1): a wrong move or a wild segment once in ~6
+// runs, none in 30 with L2 loads (scripts/cached_stress2.py).  The scan kernels stage records with bulk
+// copies (recompute) or through L2 loads (matrix), and their tails and Mode R use this wrapper.
+template <class Pol>
+struct L2Pol : Pol {
+    __device__ __forceinline__ explicit L2Pol(const Pol &p) : Pol(p) {}
+    __device__ __forceinline__ typename Pol::Rec load(uint32_t q) const { return Pol::load_l2(q); }
 };
 
 } // namespace tl
