@@ -31,6 +31,8 @@
 #include "policy.cuh"
 #include "two_opt_apply.cuh"
 
+#include <cstdlib>
+
 namespace tl {
 
 namespace {
@@ -89,7 +91,11 @@ __global__ void __launch_bounds__(256)
 {
     using V = typename Pol::V;
     using Rec = typename Pol::Rec;
+#ifdef TL_CACHED_PLAIN
+    const Pol &P = P0; // experiment: plain (L1-cached) record loads
+#else
     const L2Pol<Pol> P(P0);
+#endif
     griddep_launch_dependents();
     griddep_wait(); // the previous step's move is applied and its description written
     if (*reinterpret_cast<const volatile int *>(&state->done)) return;
@@ -333,7 +339,7 @@ void launch_two_opt_cached_step(const Src &src, uint32_t n, int cyclic, unsigned
     cfg.blockDim = dim3(256);
     cfg.stream = st;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = getenv("TL_CACHED_NO_PDL") ? 0 : 1; // experiment: plain stream order between steps
     TL_DISPATCH_POL(src, (cudaLaunchKernelEx(&cfg, two_opt_cached_step_kernel<decltype(P)>, P, (int)n, cyclic, rowkey, desc,
                                              fullrows, state, ticket, log, (uint64_t)log_cap)));
 }
