@@ -110,8 +110,7 @@ __device__ __noinline__ void fused_apply_tail(Pt *__restrict__ pts, const BestF 
         }
     }
     const bool found = v.i != 0xffffffffu;
-    // L2 loads: this SM's L1 may hold records from an earlier step's tail (L2Pol, policy.cuh)
-    if (found) reverse_segment_inplace(L2Pol<EucPol<FAST>>(EucPol<FAST>{pts}), v.i, v.j, nullptr, threadIdx.x, blockDim.x);
+    if (found) reverse_segment_inplace(EucPol<FAST>{pts}, v.i, v.j, nullptr, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0) {
         *ticket = 0u;
         finish_best_step(state, hdr, found, v.delta, v.i, v.j, log, log_cap);

@@ -81,8 +81,6 @@ __device__ __forceinline__ typename Pol::V pair_delta(const Pol &P, const typena
     return Val<V>::sub(Val<V>::add(e1, e2), Val<V>::add(Pol::sp(pi1), Pol::sp(pj1)));
 }
 
-// Every record load of this kernel goes to L2 (L2Pol, policy.cuh): consecutive steps overlap through
-// programmatic dependent launch, and an L1 hit on a record the previous step's tail rewrote would be stale.
 template <class Pol>
 __global__ void __launch_bounds__(256)
     two_opt_cached_step_kernel(Pol P0, int n, int cyclic, unsigned long long *__restrict__ rowkey, CachedDesc *desc,
@@ -108,6 +106,13 @@ __global__ void __launch_bounds__(256)
     // only the first `active` CTAs work on this step (a small step would otherwise pay for a thousand
     // CTAs queueing on the last-CTA ticket); the others leave at once
     const int active = *reinterpret_cast<const volatile int *>(&desc->active);
+    // Every CTA reports that it has read the description (fire-and-forget).  The tail rewrites the
+    // description for the next step and must not do so while a CTA of THIS grid has yet to read it: a
+    // grid of 1184 CTAs is not resident at once (2 CTAs per SM for the 102-register instantiation),
+    // and a CTA that starts after a short step's tail would take the next step's description for its
+    // own -- work on it, take a ticket, and let the next step's tail start early (seen as a wrong move
+    // or an illegal address once in ~10 runs at n = 1000 before this counter existed).
+    if (tid == 0) atomicAdd(ticket + 1, 1u);
     if ((int)blockIdx.x >= active) return;
     const bool all_rows = nfull_raw < 0;
     const int nfull = all_rows ? nrows : nfull_raw;
@@ -267,6 +272,10 @@ __global__ void __launch_bounds__(256)
     const int mi = br, mj = (int)(unsigned int)bk;
     if (found) {
         reverse_segment_inplace(P, (uint32_t)mi, (uint32_t)mj, nullptr, (uint32_t)tid, 256u);
+        // every CTA of this grid has read the description before it is rewritten (see above)
+        if (tid == 0)
+            while (*reinterpret_cast<volatile unsigned int *>(ticket + 1) < gridDim.x) {}
+        __syncthreads();
         // which rows the move invalidates (see the header); more than a third of the rows: rescan them all
         const int seg_rows = min(mj, nrows - 1) - mi + 1;
         if (tid == 0) s_nfull = 0;
@@ -319,7 +328,10 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     if (tid == 0) {
-        *ticket = 0u;
+        if (!found) // the search ends here: nothing is rewritten, but the counter must not outlive the grid
+            while (*reinterpret_cast<volatile unsigned int *>(ticket + 1) < gridDim.x) {}
+        ticket[0] = 0u;
+        ticket[1] = 0u;
         finish_best_step(state, hdr, found, found ? (float)ord_value<V>((unsigned int)(bk >> 32)) : 0.0f, (uint32_t)mi,
                          (uint32_t)mj, log, log_cap);
     }

@@ -180,7 +180,7 @@ __device__ __noinline__ void fused_apply_tail_matrix(const V *__restrict__ M, ui
 #endif
     // integer metric: the record carries d(p_i, p_j), so the reversal needs no matrix loads
     if (found)
-        reverse_segment_inplace(L2Pol<MatPol<V>>(MatPol<V>{cs, M, ld}), v.i, v.j, nullptr, threadIdx.x, blockDim.x,
+        reverse_segment_inplace(MatPol<V>{cs, M, ld}, v.i, v.j, nullptr, threadIdx.x, blockDim.x,
                                 std::is_same<V, int32_t>::value, Val<V>::from_bits((int32_t)v.aux), v.delta);
 #ifdef TL_TIMELINE
     __syncthreads();
@@ -323,14 +323,14 @@ __global__ void __launch_bounds__(WARPS * 32, kMatMinBlocks)
             const int cnt = min(tile_rows, r_end - i0);
             __syncwarp();
             for (int t = lane; t < cnt + 1; t += 32) {
-                const int4 c = __ldcg(reinterpret_cast<const int4 *>(cs + i0 + t)); // L2: see L2Pol (policy.cuh)
-                srow_slot[t] = c.x;
-                srow_sp[t] = c.y;
+                const Cs c = cs[i0 + t];
+                srow_slot[t] = c.slot;
+                srow_sp[t] = c.sp_bits;
             }
             for (int t = lane; t < cnt + BW + 1; t += 32) {
-                const int4 c = __ldcg(reinterpret_cast<const int4 *>(cs + i0 + K0 + t));
-                scol_slot[t] = c.x;
-                scol_sp[t] = c.y;
+                const Cs c = cs[i0 + K0 + t];
+                scol_slot[t] = c.slot;
+                scol_sp[t] = c.sp_bits;
             }
             if (done_flag) return;
             __syncwarp();

@@ -35,12 +35,11 @@ constexpr unsigned long long kNoKey = ~0ull;
 // skipped as soon as a lexicographically smaller hit is known.
 template <class Pol>
 __global__ void __launch_bounds__(256)
-    ref_step_kernel(Pol P0, uint32_t n, DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
+    ref_step_kernel(Pol P, uint32_t n, DevState *state, unsigned int *ticket, tl_move *__restrict__ log,
                     uint64_t log_cap)
 {
     using V = typename Pol::V;
     using Rec = typename Pol::Rec;
-    const L2Pol<Pol> P(P0); // record loads from L2: steps overlap through PDL (policy.cuh)
     griddep_launch_dependents();
     griddep_wait();
     if (*reinterpret_cast<const volatile int *>(&state->done)) return;

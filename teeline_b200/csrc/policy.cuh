@@ -107,14 +107,8 @@ struct MatPol {
     __device__ __forceinline__ void store(uint32_t q, const Rec &r) const { cs[q] = r; }
 };
 
-// A policy whose record loads go to L2 (ld.global.cg), whatever this SM's L1 still holds.  Needed by every
-// kernel that is chained to its predecessor with programmatic dependent launch and reads records the
-// predecessor's tail rewrites: the CTAs of step k+1 are resident on an SM while step k's CTAs on the same
-// SM still load records into its L1; the L1 invalidation of the new grid has then already happened, step
-// k's tail (on another SM) rewrites the records, and an L1 hit in step k+1 is stale.  Seen with the cached
-// Mode B kernel at n = 1000 (all 16 KB of records stay in L1): a wrong move or a wild segment once in ~6
-// runs, none in 30 with L2 loads (scripts/cached_stress2.py).  The scan kernels stage records with bulk
-// copies (recompute) or through L2 loads (matrix), and their tails and Mode R use this wrapper.
+// A policy whose record loads go to L2 (ld.global.cg), whatever this SM's L1 holds.  Used by the cached
+// Mode B kernel, whose steps are a few microseconds long and read the same 16-byte records from many CTAs.
 template <class Pol>
 struct L2Pol : Pol {
     __device__ __forceinline__ explicit L2Pol(const Pol &p) : Pol(p) {}
