@@ -1,0 +1,15 @@
+#!/bin/bash
+# final 1-GPU validation of the round
+out=gpurun_out/r03p
+mkdir -p $out
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee $out/smoke.txt
+echo "== full pytest"; timeout 1800 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.txt 2>&1; tail -4 $out/pytest_gpu.txt
+echo "== bench --steps 20"; timeout 600 python bench.py --steps 20 --warmup 3 > $out/bench_steps20.json 2> $out/bench_steps20.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r03p/bench_steps20.json').read().strip().splitlines()[-1])
+print('value',d['value'],'ms/step',d['ms_per_step'],'frac',d['roofline']['frac'],'kernel_ms',d['roofline']['kernel_ms'],'e2e',d['e2e']['value'],'cpu',d['cpu_baseline']['value'])
+for k,v in d['wall_to_local_optimum'].items():
+    if isinstance(v,dict): print(k, round(v['wall_ms'],2), round(v['device_ms'],2), v['moves'], v.get('evals'), [round(x,1) for x in v.get('wall_ms_all',[])])
+print('config5', d['partitioned']['config5_1024_tours']['single_gpu'])
+PY
+echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $out/bench_reference.json 2> $out/bench_reference.err; cut -c1-200 $out/bench_reference.json

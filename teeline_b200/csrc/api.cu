@@ -155,6 +155,8 @@ void tl_ctx_destroy(tl_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     release_peer_mailboxes(ctx);
     if (ctx->nccl_comm) nccl_comm_destroy(ctx->nccl_comm);
+    if (ctx->mat_block) cudaFreeAsync(ctx->mat_block, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     for (void *chunk : ctx->pin_chunks) cudaFreeHost(chunk);

@@ -26,6 +26,14 @@ struct tl_ctx {
     // cudaMallocAsync in the process share
     cudaMemPool_t pool = nullptr;
     uint64_t launches = 0;
+    // One distance-matrix block kept across sessions (the largest seen): a matrix session needs n^2 * 4
+    // bytes (400 MB at 10k), and whether the stream-ordered pool can hand back the block the previous
+    // session returned depends on what has been carved out of it since -- when it cannot, the pool
+    // grows by another n^2 block, 40-80 ms on the call's critical path (seen as end-to-end calls of
+    // 75-130 ms instead of 65 once sessions of different kinds had run in the process).  Freed with
+    // the context.  Sessions of one context run on one stream, so handing the block over is ordered.
+    void *mat_block = nullptr;
+    size_t mat_bytes = 0;
     // NCCL (resolved at run time with dlopen, see nccl_shim.cu)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -138,6 +146,21 @@ struct DevBuf {
         if (p) dev_free(p, st);
         p = nullptr;
         count = 0;
+    }
+    // hand the block to / take it from a cache (the context's matrix block): no allocator call
+    T *detach()
+    {
+        T *q = p;
+        p = nullptr;
+        count = 0;
+        return q;
+    }
+    void adopt(T *q, size_t c)
+    {
+        release();
+        p = q;
+        count = c;
+        st = g_alloc_stream;
     }
     ~DevBuf() { release(); }
     DevBuf() = default;

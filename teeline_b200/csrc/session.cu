@@ -551,33 +551,54 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         tl_session_destroy(s);
         return rc;
     };
+    // TL_DEBUG_TIMING: host wall time of the phases of this call on stderr
+    const bool trace = getenv("TL_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tc0 = trace ? now() : 0.0;
+    double tc1 = tc0, tc2 = tc0, tc3 = tc0;
     if (want_matrix) {
         // The matrix is allocated FIRST: the pool usually holds the previous session's matrix block, and
         // the small buffers below would otherwise be carved out of it, so that the matrix no longer fits
         // and the pool has to grow by another n^2 block (8-30 ms per call in the end-to-end path).
         s->ld = (p->n + 31u) & ~31u;
         const size_t bytes = (size_t)p->n * s->ld * 4;
-        // what a new block can come from: the driver's free memory plus what this context's pool
-        // holds cached from earlier sessions (reserved but not in use)
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        if (c->pool) {
-            uint64_t reserved = 0, used = 0;
-            if (cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-                cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
-                free_b += (size_t)(reserved - used);
+        void *cached = nullptr;
+        size_t cached_bytes = 0;
+        {   // take the block a previous session of this context left behind (host.hpp: mat_block)
+            std::lock_guard<std::mutex> lk(c->pin_mu);
+            cached = c->mat_block;
+            cached_bytes = c->mat_bytes;
+            c->mat_block = nullptr;
+            c->mat_bytes = 0;
         }
-        if (bytes > free_b - std::min<size_t>(free_b, (size_t)1 << 30)) {
-            set_error("the %u x %u distance matrix (%.1f GB) does not fit device memory (%.1f GB free); "
-                      "use TL_PATH_RECOMPUTE", p->n, s->ld, bytes / 1e9, free_b / 1e9);
-            return fail(TL_ERR_NOMEM);
-        }
-        if (s->M.alloc((size_t)p->n * s->ld) != cudaSuccess) {
-            cudaGetLastError();
-            set_error("tl_session_create: matrix allocation failed");
-            return fail(TL_ERR_NOMEM);
+        if (cached && cached_bytes >= bytes) {
+            s->M.adopt(static_cast<uint32_t *>(cached), cached_bytes / 4);
+        } else {
+            if (cached) cudaFreeAsync(cached, c->stream); // too small: given back first
+            // what a new block can come from: the driver's free memory plus what this context's pool
+            // holds cached from earlier sessions (reserved but not in use)
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            if (c->pool) {
+                uint64_t reserved = 0, used = 0;
+                if (cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                    cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+                    free_b += (size_t)(reserved - used);
+            }
+            free_b += cached_bytes;
+            if (bytes > free_b - std::min<size_t>(free_b, (size_t)1 << 30)) {
+                set_error("the %u x %u distance matrix (%.1f GB) does not fit device memory (%.1f GB free); "
+                          "use TL_PATH_RECOMPUTE", p->n, s->ld, bytes / 1e9, free_b / 1e9);
+                return fail(TL_ERR_NOMEM);
+            }
+            if (s->M.alloc((size_t)p->n * s->ld) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("tl_session_create: matrix allocation failed");
+                return fail(TL_ERR_NOMEM);
+            }
         }
     }
+    if (trace) tc1 = now();
     DevBuf<uint32_t> d_tour;
     if (d_tour.alloc(p->n) != cudaSuccess || s->state.alloc(1) != cudaSuccess || s->ticket.alloc(2) != cudaSuccess ||
         s->log.alloc(s->log_cap) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
@@ -611,6 +632,7 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
         for (uint32_t k = 0; k < p->n; ++k) ident[k] = k;
         tour = ident.data();
     }
+    if (trace) tc2 = now();
     cudaError_t e = cudaMemcpyAsync(d_tour.p, tour, (size_t)p->n * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->ticket.p, 0, 8, c->stream);
     if (e != cudaSuccess) { set_error("tl_session_create: %s", cudaGetErrorString(e)); return fail(TL_ERR_CUDA); }
@@ -658,10 +680,14 @@ tl_status tl_session_create(tl_problem *p, int32_t algo, int32_t path, const uin
     }
     tl_status rc = push_state(s); // also waits for d_tour's consumers
     if (rc != TL_OK) return fail(rc);
+    if (trace) tc3 = now();
     if (!s->trivial && algo != TL_ALGO_TWO_OPT_REF) {
         rc = upload_geometry(s);
         if (rc != TL_OK) return fail(rc);
     }
+    if (trace)
+        fprintf(stderr, "[tl] session_create: matrix block %.2f ms, buffers %.2f ms, build + state %.2f ms, geometry %.2f ms\n",
+                tc1 - tc0, tc2 - tc1, tc3 - tc2, now() - tc3);
     if (cudaGetLastError() != cudaSuccess) { set_error("tl_session_create: kernel launch failed"); return fail(TL_ERR_CUDA); }
     *out = s;
     return TL_OK;
@@ -678,6 +704,20 @@ void tl_session_destroy(tl_session *s)
     for (cudaEvent_t e : s->ev_snap)
         if (e) cudaEventDestroy(e);
     if (s->h_snap) s->c->return_pinned(s->h_snap);
+    if (s->M.p) { // keep the matrix block for the next session of this context (the larger one wins)
+        tl_ctx *c = s->c;
+        const size_t bytes = s->M.count * 4;
+        void *drop = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(c->pin_mu);
+            if (!c->mat_block || bytes > c->mat_bytes) {
+                drop = c->mat_block;
+                c->mat_bytes = bytes;
+                c->mat_block = s->M.detach();
+            }
+        }
+        if (drop) cudaFreeAsync(drop, c->stream);
+    }
     delete s;
 }
 
