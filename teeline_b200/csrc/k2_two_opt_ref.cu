@@ -17,11 +17,27 @@
 // the device; the host enqueues batches of steps and only looks at the done flag between batches.  The chain is serial by nature (every move
 // changes the path the next comparison sees), so this path is latency- not throughput-bound;
 // it exists for exact parity with the reference, not for the Tmove/s metric.
+//
+// PERSISTENT FORM (ref_persistent_kernel, coordinate problems whose tour records fit one SM's
+// shared memory: n <= kRefPersistMaxN).  A step of the cursor is a few thousand pair evaluations
+// followed by a serial decision, so the per-step kernel above is bound by launch + grid hand-off
+// latency (about 7 us per step, 3842 steps at n = 10k).  Here ONE thread-block cluster of 16 (8)
+// CTAs runs the whole chain in a single launch: every CTA holds a replica of the tour-ordered
+// records in shared memory, the window's pairs are dealt to the cluster's warps, each CTA's first
+// hit goes to every peer with one remote shared-memory store (DSMEM), ONE cluster barrier per
+// step, and every CTA then applies the same reversal to its own replica.  Cursor, window and pass
+// bookkeeping are replicated registers and go back to DevState when the launch ends (a move budget
+// or a later tl_session_run resumes from there); only the window sizes differ from the per-step
+// kernel's, which changes what is evaluated speculatively, never which move comes next.
 #include "kernels.cuh"
 #include "policy.cuh"
 #include "two_opt_apply.cuh"
 
+#include <cooperative_groups.h>
+
 namespace tl {
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -131,6 +147,220 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+
+// ---- persistent form ------------------------------------------------------------------------
+#ifndef TL_REFP_THREADS
+#define TL_REFP_THREADS 512
+#endif
+#ifndef TL_REFP_RB
+#define TL_REFP_RB 4
+#endif
+#ifdef TL_REFP_PROF
+// tuning builds only (-DTL_REFP_PROF): cycles of rank 0 / thread 0 per phase, summed over the launch
+// [0] steps, [1] hits, [2] units this warp evaluated, [3] eval cycles, [4] barrier cycles, [5] apply cycles,
+// [6] whole-kernel cycles, [7] rows of all windows
+__device__ unsigned long long tl_refp_prof[8];
+#define REFP_CLK() clock64()
+#define REFP_ADD(k, v) do { if (rank == 0 && tid == 0) tl_refp_prof[k] += (unsigned long long)(v); } while (0)
+#else
+#define REFP_CLK() 0ll
+#define REFP_ADD(k, v) do { (void)(v); } while (0)
+#endif
+constexpr int kRefPThreads = TL_REFP_THREADS;
+constexpr unsigned int kNoHit = 0xffffffffu;
+constexpr int RB = TL_REFP_RB; // rows per unit: the 32 column records a warp loads serve RB pairs per lane
+static_assert(kRefPersistMaxN <= (1 << 14), "keys are (row in window) << 14 | column");
+
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// max_steps cursor steps (or until done).  Window unit = (block of RB rows, 32 consecutive columns):
+// a warp loads the 32 column records once (the shared-memory pipe is the limit: 8 wavefronts for the
+// two 16-byte column records of a warp against 1 for a broadcast row record) and evaluates RB pairs
+// per lane.  key = (row in window) << 14 | column orders the window's pairs lexicographically; the
+// cluster-wide minimum key is the reference's next move.
+template <bool FAST, bool SCREEN>
+__global__ void __launch_bounds__(kRefPThreads, 1)
+    ref_persistent_kernel(Pt *__restrict__ pts, uint32_t n, DevState *state, tl_move *__restrict__ log,
+                          uint64_t log_cap, uint32_t max_steps, float margin)
+{
+    extern __shared__ __align__(16) unsigned char ref_smem[];
+    Pt *rec = reinterpret_cast<Pt *>(ref_smem);
+    // [step parity]: the smallest hit key of the step known so far, CLUSTER-wide -- a warp that finds a
+    // hit pushes it into every CTA's copy with a remote atomicMin (DSMEM), so every warp of the cluster
+    // stops evaluating pairs behind it, and after the step's cluster barrier every copy holds the move
+    __shared__ unsigned int s_min[2];
+    __shared__ float s_delta;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int rank = cluster.block_rank(), csize = cluster.num_blocks();
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t gwarp = warp * csize + rank, nwarps = (kRefPThreads / 32) * csize; // early units spread over the CTAs
+
+    if (*reinterpret_cast<const volatile int *>(&state->done)) return; // cluster-uniform
+    for (uint32_t q = tid; q < n; q += kRefPThreads)
+        reinterpret_cast<float4 *>(rec)[q] = __ldcg(reinterpret_cast<const float4 *>(pts) + q);
+    if (tid == 0) s_min[0] = s_min[1] = kNoHit;
+    // replicated loop state
+    uint32_t ci = (uint32_t)state->cur_i, cj = (uint32_t)state->cur_j, W = (uint32_t)state->window_rows;
+    int improved = state->improved_in_pass;
+    unsigned long long moves = state->moves, passes = state->passes;
+    const long long max_moves = state->max_moves;
+    int done = 0, converged = 0;
+    const uint32_t last_row = n - 4, last_col = n - 2;
+    const EucPol<FAST> P{rec};
+    // The window right after a hit (or at the start of a pass): as many row blocks as keep every warp
+    // of the cluster busy for about two rounds -- a step costs its synchronisation, not its pairs.
+    auto first_window = [&](uint32_t row) {
+        const uint32_t chunks = (last_col - (min(row, last_row) + 2) + 1 + 31) / 32;
+        return (uint32_t)RB * max(1u, min(64u, 2u * nwarps / chunks));
+    };
+    if (W == (uint32_t)kRefWindow0) W = first_window(ci); // a state the per-step kernel (or session create) left
+    __syncthreads();
+    cluster_barrier(); // nobody pushes a hit into a peer's copy before that peer has armed it
+
+    const long long tk0 = REFP_CLK();
+    for (uint32_t step = 0; step < max_steps && !done; ++step) {
+        const long long tp0 = REFP_CLK();
+        const uint32_t par = step & 1u;
+        // re-arm the other copy for the next step: peers push into it only after this step's barrier,
+        // and this CTA's reads of it (the previous step's move) ended at that step's last __syncthreads
+        if (tid == 0) s_min[par ^ 1u] = kNoHit;
+        const uint32_t rows = min(W, last_row - ci + 1);
+        const uint32_t cpr = (last_col - (ci + 2) + 1 + 31) / 32; // 32-column chunks of the window's longest row
+        const uint32_t nblk = (rows + RB - 1) / RB;
+        const uint32_t units = nblk * cpr;
+        unsigned int mine = kNoHit;
+        const uint32_t dq = nwarps / cpr, dr = nwarps - dq * cpr; // unit stride in (block, chunk) form
+        uint32_t b = gwarp / cpr, c = gwarp - b * cpr;            // one division per step
+        for (uint32_t u = gwarp; u < units; u += nwarps) {
+            // every key of this and of the warp's later units is at least (first row of the block) << 14:
+            // stop once a smaller hit is known (this warp's, or any in this CTA -- one read per warp)
+            unsigned int known = 0;
+            if (lane == 0) known = *reinterpret_cast<volatile unsigned int *>(&s_min[par]);
+            known = min(mine, __shfl_sync(0xffffffffu, known, 0));
+            const uint32_t w0 = b * RB;
+            if ((w0 << 14) > known) break;
+            const uint32_t i0 = ci + w0;
+            const uint32_t j = i0 + 2 + c * 32 + lane;
+            const bool jin = j <= last_col;
+            Pt pj{}, pj1{};
+            if (jin) {
+                pj = rec[j];
+                pj1 = rec[j + 1];
+            }
+            const uint32_t nr = min((uint32_t)RB, rows - w0); // rows of this block inside the window
+            Pt pi[RB + 1];
+#pragma unroll
+            for (int r = 0; r <= RB; ++r)
+                if ((uint32_t)r <= nr) pi[r] = rec[i0 + r]; // i0 + nr <= last_row + 1
+            bool cand[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                cand[r] = false;
+                // row i0 + r starts at column i + 2, the cursor's own row at cur_j
+                const uint32_t jfirst = (w0 + r == 0) ? cj : i0 + r + 2;
+                if ((uint32_t)r < nr && jin && j >= jfirst) {
+                    const float cur = __fadd_rn(pi[r + 1].sp, pj1.sp);
+                    if (SCREEN) { // cheap distances; anything within the error margin is re-checked exactly
+                        const float nws = __fadd_rn(dist_f32_screen(pi[r].x, pi[r].y, pj.x, pj.y),
+                                                    dist_f32_screen(pi[r + 1].x, pi[r + 1].y, pj1.x, pj1.y));
+                        cand[r] = nws < __fadd_rn(cur, margin);
+                    } else {
+                        // two separately rounded sums, compared directly (two_opt.rs:35-49)
+                        cand[r] = __fadd_rn(P.dist(pi[r], pj), P.dist(pi[r + 1], pj1)) < cur;
+                    }
+                }
+            }
+            bool hit_here = false;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                unsigned int bal = __ballot_sync(0xffffffffu, cand[r]);
+                if (SCREEN && bal && !hit_here) { // warp-uniform: the exact comparison for this row's candidates
+                    bool hit = false;
+                    if (cand[r])
+                        hit = __fadd_rn(P.dist(pi[r], pj), P.dist(pi[r + 1], pj1)) < __fadd_rn(pi[r + 1].sp, pj1.sp);
+                    bal = __ballot_sync(0xffffffffu, hit);
+                }
+                if (bal && !hit_here) { // the block's rows in order: the first row with a hit holds its smallest key
+                    hit_here = true;
+                    mine = min(mine, ((w0 + r) << 14) | (j - lane + (uint32_t)(__ffs(bal) - 1)));
+                }
+            }
+            if (hit_here && lane < csize) atomicMin(cluster.map_shared_rank(&s_min[par], lane), mine);
+            c += dr;
+            b += dq;
+            if (c >= cpr) { c -= cpr; b += 1; }
+            REFP_ADD(2, 1);
+        }
+        const long long tp1 = REFP_CLK();
+        cluster_barrier(); // release/acquire: every hit of the step has landed in every copy
+        const long long tp2 = REFP_CLK();
+        const unsigned int key = s_min[par];
+        const bool found = key != kNoHit;
+        uint32_t ni, nj, nw_rows;
+        if (found) {
+            const uint32_t mi = ci + (key >> 14), mj = key & 16383u;
+            reverse_segment_inplace(P, mi, mj, &s_delta, tid, kRefPThreads);
+            __syncthreads();
+            if (rank == 0 && tid == 0 && log && moves < log_cap) log[moves] = tl_move{s_delta, mi, mj, 0, 0, 0};
+            moves += 1;
+            improved = 1;
+            ni = mi;
+            nj = mj + 1;
+            if (nj > last_col) { ni += 1; nj = ni + 2; }
+            nw_rows = 0; // the first window of the new cursor, sized below
+            if (max_moves >= 0 && (long long)moves >= max_moves) done = 1;
+        } else {
+            ni = ci + W;
+            nj = ni + 2;
+            nw_rows = min(W * 4u, n);
+            __syncthreads(); // (the found branch's barrier: the steps stay symmetric)
+        }
+        if (ni > last_row) { // end of a pass over the triangle
+            passes += 1;
+            if (improved) {
+                improved = 0;
+                ni = 0;
+                nj = 2;
+                nw_rows = 0;
+            } else {
+                done = 1;
+                converged = 1;
+            }
+        }
+        ci = ni;
+        cj = nj;
+        W = nw_rows ? nw_rows : first_window(ci);
+        REFP_ADD(0, 1);
+        REFP_ADD(1, found ? 1 : 0);
+        REFP_ADD(3, tp1 - tp0);
+        REFP_ADD(4, tp2 - tp1);
+        REFP_ADD(5, REFP_CLK() - tp2);
+        REFP_ADD(7, rows);
+    }
+    REFP_ADD(6, REFP_CLK() - tk0);
+
+    if (rank == 0) {
+        for (uint32_t q = tid; q < n; q += kRefPThreads)
+            reinterpret_cast<float4 *>(pts)[q] = reinterpret_cast<const float4 *>(rec)[q];
+        if (tid == 0) {
+            state->moves = moves;
+            state->passes = passes;
+            state->improved_in_pass = improved;
+            state->cur_i = (int32_t)ci;
+            state->cur_j = (int32_t)cj;
+            state->window_rows = (int32_t)W;
+            state->found_key = kNoKey;
+            if (done) state->done = 1;
+            if (converged) state->converged = 1;
+        }
+    }
+    cluster_barrier(); // no CTA leaves while a peer may still push into its shared memory
+}
+
 template <class Pol>
 __global__ void extract_tour_kernel(Pol P, uint32_t n, uint32_t *__restrict__ tour)
 {
@@ -154,6 +384,93 @@ void launch_ref_step(const Src &src, uint32_t n, DevState *state, unsigned int *
     cfg.numAttrs = 1;
     TL_DISPATCH_POL(src, (cudaLaunchKernelEx(&cfg, ref_step_kernel<decltype(P)>, P, n, state, ticket, log,
                                              (uint64_t)log_cap)));
+}
+
+#ifdef TL_REFP_PROF
+} // namespace tl
+extern "C" int tl_debug_refp(double *out8, int reset)
+{
+    unsigned long long h[8];
+    if (cudaMemcpyFromSymbol(h, tl::tl_refp_prof, sizeof h) != cudaSuccess) return 1;
+    for (int k = 0; k < 8; ++k) out8[k] = (double)h[k];
+    if (reset) {
+        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyToSymbol(tl::tl_refp_prof, z, sizeof z);
+    }
+    return 0;
+}
+namespace tl {
+#endif
+
+// The persistent form: one cluster of `csize` CTAs (16 needs the non-portable opt-in; 8 otherwise).
+// Returns the cluster size this device can run for n records, 0 if the form does not apply.
+int ref_persistent_cluster_size(const Src &src, uint32_t n)
+{
+    if (src.kind > SRC_EUC_SAFE || n < 4 || n > (uint32_t)kRefPersistMaxN) return 0;
+    static int cached_size[2] = {-1, -1}; // by FAST; the answer for the largest n holds for every n
+    const int fast = src.kind == SRC_EUC_FAST ? 1 : 0;
+    if (cached_size[fast] >= 0) return cached_size[fast];
+    const void *fn = fast ? (const void *)ref_persistent_kernel<true, false> : (const void *)ref_persistent_kernel<false, false>;
+    const size_t smem = (size_t)kRefPersistMaxN * sizeof(Pt);
+    int best = 0;
+    bool ok = true;
+    for (const void *f : {(const void *)ref_persistent_kernel<true, true>, (const void *)ref_persistent_kernel<true, false>,
+                          (const void *)ref_persistent_kernel<false, false>})
+        ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+             cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (ok) {
+        for (int cs : {16, 8, 4, 2}) {
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cs;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)cs);
+            cfg.blockDim = dim3(kRefPThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) == cudaSuccess && nclusters >= 1) {
+                best = cs;
+                break;
+            }
+            cudaGetLastError();
+        }
+    }
+    cudaGetLastError();
+    if (const char *ev = getenv("TL_REF_CLUSTER")) { // tuning: 0 = per-step kernel, 2/4/8/16 = at most this size
+        const int want = atoi(ev);
+        if (want <= 0) best = 0;
+        else if (want < best) best = want;
+    }
+    cached_size[fast] = best;
+    return best;
+}
+
+void launch_ref_persistent(const Src &src, uint32_t n, DevState *state, tl_move *log, uint64_t log_cap,
+                           uint32_t max_steps, int csize, float screen_margin, cudaStream_t st)
+{
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)csize);
+    cfg.blockDim = dim3(kRefPThreads);
+    cfg.dynamicSmemBytes = (size_t)n * sizeof(Pt);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // screen_margin >= 0 (fast-sqrt domain only, common.cuh: kScreenMarginScale): screened distances first
+    if (src.kind == SRC_EUC_FAST && screen_margin >= 0.0f)
+        cudaLaunchKernelEx(&cfg, ref_persistent_kernel<true, true>, src.pts, n, state, log, (uint64_t)log_cap, max_steps, screen_margin);
+    else if (src.kind == SRC_EUC_FAST)
+        cudaLaunchKernelEx(&cfg, ref_persistent_kernel<true, false>, src.pts, n, state, log, (uint64_t)log_cap, max_steps, -1.0f);
+    else
+        cudaLaunchKernelEx(&cfg, ref_persistent_kernel<false, false>, src.pts, n, state, log, (uint64_t)log_cap, max_steps, -1.0f);
 }
 
 void launch_apply_two_opt(const Src &src, const void *cand, int ncand, DevState *state, unsigned int *ticket,

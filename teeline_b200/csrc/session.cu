@@ -380,6 +380,16 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
     const int apply_grid =
         (int)std::max<uint32_t>(1, std::min<uint32_t>((s->n / 2 + 255) / 256, (uint32_t)s->c->sm_count));
     if (s->algo == TL_ALGO_TWO_OPT_REF) {
+        // coordinate problems whose records fit one SM's shared memory: the whole chain of `steps`
+        // cursor steps in ONE launch of a thread-block cluster (k2_two_opt_ref.cu, persistent form)
+        if (const int csize = ref_persistent_cluster_size(s->src, s->n)) {
+            const float m = s->p->dmax * kScreenMarginScale;
+            const float margin = (s->p->fast_sqrt && std::isfinite(m) && s->p->dmax >= kScreenMinDmax && !getenv("TL_NO_SCREEN")) ? m : -1.0f;
+            launch_ref_persistent(s->src, s->n, s->state.p, s->log.p, s->log_cap, steps, csize, margin, st);
+            s->c->launches += 1;
+            TL_CUDA_TRY(cudaGetLastError());
+            return TL_OK;
+        }
         // one unit (row x 256 columns) per CTA: the first window (8 rows) is covered in one shot
         const int units0 = kRefWindow0 * (int)((s->n + 255) / 256);
         const int ref_grid = std::max(1, std::min(units0, s->c->sm_count * 4));
@@ -875,6 +885,9 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
     int64_t budget = budgeted ? max_moves - (int64_t)s->h.moves : 0;
     auto issue = [&](int slot) -> tl_status {
         uint32_t batch = s->algo == TL_ALGO_TWO_OPT_REF ? 64 : 32;
+        // Mode R, persistent form: a batch is one launch, so make it long (the kernel stops by itself
+        // at convergence or at the move budget)
+        if (s->algo == TL_ALGO_TWO_OPT_REF && ref_persistent_cluster_size(s->src, s->n)) batch = 1u << 20;
         if (budgeted) {
             batch = (uint32_t)std::min<int64_t>(256, budget);
             budget -= batch;
