@@ -155,6 +155,12 @@ __global__ void __launch_bounds__(256)
 #ifndef TL_REFP_RB
 #define TL_REFP_RB 4
 #endif
+#ifndef TL_REFP_ROUNDS
+#define TL_REFP_ROUNDS 1 // first window after a hit: this many rounds of the cluster's warps
+#endif
+#ifndef TL_REFP_GROW
+#define TL_REFP_GROW 4 // window growth after a miss
+#endif
 #ifdef TL_REFP_PROF
 // tuning builds only (-DTL_REFP_PROF): cycles of rank 0 / thread 0 per phase, summed over the launch
 // [0] steps, [1] hits, [2] units this warp evaluated, [3] eval cycles, [4] barrier cycles, [5] apply cycles,
@@ -176,10 +182,30 @@ __device__ __forceinline__ void cluster_barrier()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Tour records in shared memory as four arrays (x, y, city, entering-edge length): a warp's column
+// loads and the reversal's stores touch consecutive words (conflict-free; 16-byte records would
+// put the 4-byte field stores of consecutive lanes 4 ways onto the same banks), and a load that needs
+// only some fields costs only those.  Same interface as EucPol (policy.cuh).
+template <bool FAST>
+struct SmemSoaPol {
+    using V = float;
+    using Rec = Pt;
+    float *x, *y, *spl;
+    int32_t *cty;
+    __device__ __forceinline__ Rec load(uint32_t q) const { return Pt{x[q], y[q], cty[q], spl[q]}; }
+    static __device__ __forceinline__ V sp(const Rec &r) { return r.sp; }
+    __device__ __forceinline__ V dist(const Rec &a, const Rec &b) const { return dist_f32<FAST>(a.x, a.y, b.x, b.y); }
+    __device__ __forceinline__ void store_id(uint32_t q, const Rec &from) const
+    {
+        x[q] = from.x;
+        y[q] = from.y;
+        cty[q] = from.city;
+    }
+    __device__ __forceinline__ void store_sp(uint32_t q, V v) const { spl[q] = v; }
+};
+
 // max_steps cursor steps (or until done).  Window unit = (block of RB rows, 32 consecutive columns):
-// a warp loads the 32 column records once (the shared-memory pipe is the limit: 8 wavefronts for the
-// two 16-byte column records of a warp against 1 for a broadcast row record) and evaluates RB pairs
-// per lane.  key = (row in window) << 14 | column orders the window's pairs lexicographically; the
+// a warp loads the 32 column records once and evaluates RB pairs per lane.  key = (row in window) << 14 | column orders the window's pairs lexicographically; the
 // cluster-wide minimum key is the reference's next move.
 template <bool FAST, bool SCREEN>
 __global__ void __launch_bounds__(kRefPThreads, 1)
@@ -187,7 +213,10 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
                           uint64_t log_cap, uint32_t max_steps, float margin)
 {
     extern __shared__ __align__(16) unsigned char ref_smem[];
-    Pt *rec = reinterpret_cast<Pt *>(ref_smem);
+    const uint32_t na = (n + 3u) & ~3u; // array pitch (words)
+    const SmemSoaPol<FAST> P{reinterpret_cast<float *>(ref_smem), reinterpret_cast<float *>(ref_smem) + na,
+                             reinterpret_cast<float *>(ref_smem) + 3 * (size_t)na,
+                             reinterpret_cast<int32_t *>(ref_smem) + 2 * (size_t)na};
     // [step parity]: the smallest hit key of the step known so far, CLUSTER-wide -- a warp that finds a
     // hit pushes it into every CTA's copy with a remote atomicMin (DSMEM), so every warp of the cluster
     // stops evaluating pairs behind it, and after the step's cluster barrier every copy holds the move
@@ -200,8 +229,13 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
     const uint32_t gwarp = warp * csize + rank, nwarps = (kRefPThreads / 32) * csize; // early units spread over the CTAs
 
     if (*reinterpret_cast<const volatile int *>(&state->done)) return; // cluster-uniform
-    for (uint32_t q = tid; q < n; q += kRefPThreads)
-        reinterpret_cast<float4 *>(rec)[q] = __ldcg(reinterpret_cast<const float4 *>(pts) + q);
+    for (uint32_t q = tid; q < n; q += kRefPThreads) {
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(pts) + q); // Pt = {x, y, city, sp}
+        P.x[q] = v.x;
+        P.y[q] = v.y;
+        P.cty[q] = __float_as_int(v.z);
+        P.spl[q] = v.w;
+    }
     if (tid == 0) s_min[0] = s_min[1] = kNoHit;
     // replicated loop state
     uint32_t ci = (uint32_t)state->cur_i, cj = (uint32_t)state->cur_j, W = (uint32_t)state->window_rows;
@@ -210,12 +244,13 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
     const long long max_moves = state->max_moves;
     int done = 0, converged = 0;
     const uint32_t last_row = n - 4, last_col = n - 2;
-    const EucPol<FAST> P{rec};
-    // The window right after a hit (or at the start of a pass): as many row blocks as keep every warp
-    // of the cluster busy for about two rounds -- a step costs its synchronisation, not its pairs.
+    // The window right after a hit (or at the start of a pass): as many row blocks as give every warp
+    // of the cluster one unit -- a step costs its synchronisation, not its pairs (1, 2 or 3 rounds and
+    // growth factors 2 / 4 / 8 after a miss all end within 2 % of each other at n = 10k; one round is
+    // 18 % faster at n = 1000, profiles/r03u_mode_r_persistent_soa_and_window_policy.txt).
     auto first_window = [&](uint32_t row) {
         const uint32_t chunks = (last_col - (min(row, last_row) + 2) + 1 + 31) / 32;
-        return (uint32_t)RB * max(1u, min(64u, 2u * nwarps / chunks));
+        return (uint32_t)RB * max(1u, min(64u, (uint32_t)TL_REFP_ROUNDS * nwarps / chunks));
     };
     if (W == (uint32_t)kRefWindow0) W = first_window(ci); // a state the per-step kernel (or session create) left
     __syncthreads();
@@ -248,14 +283,14 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
             const bool jin = j <= last_col;
             Pt pj{}, pj1{};
             if (jin) {
-                pj = rec[j];
-                pj1 = rec[j + 1];
+                pj = P.load(j);
+                pj1 = P.load(j + 1);
             }
             const uint32_t nr = min((uint32_t)RB, rows - w0); // rows of this block inside the window
             Pt pi[RB + 1];
 #pragma unroll
             for (int r = 0; r <= RB; ++r)
-                if ((uint32_t)r <= nr) pi[r] = rec[i0 + r]; // i0 + nr <= last_row + 1
+                if ((uint32_t)r <= nr) pi[r] = P.load(i0 + r); // i0 + nr <= last_row + 1
             bool cand[RB];
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
@@ -316,7 +351,7 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
         } else {
             ni = ci + W;
             nj = ni + 2;
-            nw_rows = min(W * 4u, n);
+            nw_rows = min(W * (uint32_t)TL_REFP_GROW, n);
             __syncthreads(); // (the found branch's barrier: the steps stay symmetric)
         }
         if (ni > last_row) { // end of a pass over the triangle
@@ -345,7 +380,7 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
 
     if (rank == 0) {
         for (uint32_t q = tid; q < n; q += kRefPThreads)
-            reinterpret_cast<float4 *>(pts)[q] = reinterpret_cast<const float4 *>(rec)[q];
+            reinterpret_cast<float4 *>(pts)[q] = make_float4(P.x[q], P.y[q], __int_as_float(P.cty[q]), P.spl[q]);
         if (tid == 0) {
             state->moves = moves;
             state->passes = passes;
@@ -460,7 +495,7 @@ void launch_ref_persistent(const Src &src, uint32_t n, DevState *state, tl_move 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)csize);
     cfg.blockDim = dim3(kRefPThreads);
-    cfg.dynamicSmemBytes = (size_t)n * sizeof(Pt);
+    cfg.dynamicSmemBytes = (size_t)((n + 3u) & ~3u) * sizeof(Pt);
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = 1;

@@ -299,6 +299,62 @@ def test_mode_r_1k_random_start(T, ctx):
     check_mode_r(T, ctx, x, y, O.shuffle_tour(1000, 5))
 
 
+def test_mode_r_move_budgets_resume_where_they_stopped(T, ctx):
+    """The persistent cluster kernel keeps cursor, window and pass bookkeeping in registers and hands
+    them back through DevState: a search cut into budgeted runs applies the oracle's moves in the
+    oracle's order and ends in the oracle's tour."""
+    n = 2000
+    x, y = O.gen_uniform(n, 77)
+    P = O.Problem(x, y)
+    start = O.nn_tour(P, 3)
+    want_t, want_st, want_mv = O.two_opt_ref(P, start, log_cap=1 << 16)
+    p = T.Problem.euc2d(ctx, x, y)
+    s = p.session(T.ALGO_TWO_OPT_REF, start)
+    prefix = np.asarray(start, dtype=np.int64).copy()
+    done = 0
+    for budget in (1, 7, 8, want_st.moves // 2, want_st.moves - 1):
+        s.run(max_moves=budget)
+        for m in want_mv[done:budget]:
+            prefix[m[1] + 1:m[2] + 1] = prefix[m[1] + 1:m[2] + 1][::-1].copy()
+        done = budget
+        assert int(s.stats().moves) == budget and s.stats().converged == 0
+        assert (s.tour().astype(np.int64) == prefix).all(), f"after {budget} moves"
+    s.run()
+    st = s.stats()
+    assert (s.tour().astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals)
+    assert st.converged == 1
+    s.close()
+
+
+def test_mode_r_beyond_one_sm_of_shared_memory_uses_the_per_step_kernel(T, ctx):
+    """n = 14 500: the tour records no longer fit one SM's shared memory (k2_two_opt_ref.cu:
+    kRefPersistMaxN), so the launch-per-step kernel runs the chain -- same moves, same tour."""
+    n = 14500
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    start = O.nn_tour(P, 3)
+    want_t, want_st, want_mv = O.two_opt_ref(P, start, log_cap=1 << 16)
+    got_t, st, mv = T.Problem.euc2d(ctx, x, y).local_search(T.ALGO_TWO_OPT_REF, start, log_cap=1 << 16)
+    assert int(st.launches) > 1000  # one launch per cursor step
+    assert [(m[1], m[2]) for m in mv] == [(m[1], m[2]) for m in want_mv]
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals)
+
+
+def test_mode_r_largest_persistent_size(T, ctx):
+    """n = 14 000 = kRefPersistMaxN: 224 000 B of records per CTA, a handful of launches."""
+    n = 14000
+    x, y = O.gen_uniform(n, n)
+    P = O.Problem(x, y)
+    start = O.nn_tour(P, 3)
+    want_t, want_st, _ = O.two_opt_ref(P, start)
+    got_t, st, _ = T.Problem.euc2d(ctx, x, y).local_search(T.ALGO_TWO_OPT_REF, start)
+    assert int(st.launches) < 16
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals)
+
+
 # ---- K5 k-NN and the nearest-neighbour constructor ---------------------------------------------
 
 def test_knn_reference_ordered_vector(T, ctx):  # tests/test_kdtree_and_distance_matrix.rs:199-243
