@@ -12,9 +12,9 @@ _lib = _capi.load()
 _prof = getattr(_lib, "tl_debug_refp", None)  # tuning builds (-DTL_REFP_PROF) only
 if _prof is not None:
     _prof.argtypes = [C.POINTER(C.c_double), C.c_int]
-for n in (52, 1000, 5000, 10000, 14000):
-    x, y = bench.instance(n, n, "f32")
-    p = T.Problem.euc2d(ctx, x, y, T.DIST_F32_EXACT)
+for n, dist in ((52, "f32"), (1000, "f32"), (5000, "f32"), (10000, "f32"), (14000, "f32"), (1000, "nint"), (10000, "nint"), (11000, "nint")):
+    x, y = bench.instance(n, n, dist)
+    p = T.Problem.euc2d(ctx, x, y, T.DIST_F32_EXACT if dist == "f32" else T.DIST_NINT_I32)
     nn = p.nn_tour(3)
     p.local_search(T.ALGO_TWO_OPT_REF, nn, max_moves=5)
     walls = []
@@ -33,7 +33,7 @@ for n in (52, 1000, 5000, 10000, 14000):
         walls.append(time.perf_counter() - t0)
     h = hashlib.sha1(np.asarray(t, dtype=np.int64).tobytes()).hexdigest()[:12]
     hm = hashlib.sha1(repr([(m[1], m[2]) for m in mv]).encode()).hexdigest()[:12]
-    print(f"[{tag}] n={n}: wall {1e3*min(walls):.2f} ms device {st.device_ms:.2f} ms moves {int(st.moves)} passes {int(st.passes)} "
+    print(f"[{tag}] n={n} {dist}: wall {1e3*min(walls):.2f} ms device {st.device_ms:.2f} ms moves {int(st.moves)} passes {int(st.passes)} "
           f"launches {int(st.launches)} tour {h} log {hm}", flush=True)
     # budgeted + resumed run must give the same tour (cursor state survives a launch boundary)
     s = p.session(T.ALGO_TWO_OPT_REF, nn)

@@ -34,6 +34,7 @@
 #include "two_opt_apply.cuh"
 
 #include <cooperative_groups.h>
+#include <type_traits>
 
 namespace tl {
 
@@ -182,41 +183,64 @@ __device__ __forceinline__ void cluster_barrier()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// Tour records in shared memory as four arrays (x, y, city, entering-edge length): a warp's column
-// loads and the reversal's stores touch consecutive words (conflict-free; 16-byte records would
-// put the 4-byte field stores of consecutive lanes 4 ways onto the same banks), and a load that needs
-// only some fields costs only those.  Same interface as EucPol (policy.cuh).
-template <bool FAST>
+// Tour records in shared memory as arrays (x, y, city, entering-edge length [, matrix slot]): a warp's
+// column loads and the reversal's stores touch consecutive words (conflict-free), and a load that
+// needs only some fields costs only those.  Same interface as EucPol / MatPol (policy.cuh).
+// METRIC: 0 = f32 guarded fast sqrt, 1 = f32 safe sqrt, 2 = TSPLIB nint for integer coordinates
+// (FP64-free, common.cuh: dist_nint_grid), 3 = TSPLIB nint in double.  The nint metrics belong to
+// matrix sessions: the kernel recomputes the matrix entries from the coordinates (bit-equal by K1's
+// construction) and carries every city's matrix slot along so that the Cs records can be restored.
+template <int METRIC>
 struct SmemSoaPol {
-    using V = float;
-    using Rec = Pt;
-    float *x, *y, *spl;
-    int32_t *cty;
-    __device__ __forceinline__ Rec load(uint32_t q) const { return Pt{x[q], y[q], cty[q], spl[q]}; }
+    static constexpr bool kInt = METRIC >= 2;
+    using V = typename std::conditional<kInt, int32_t, float>::type;
+    struct Rec {
+        float x, y;
+        int32_t city, slot;
+        V sp;
+    };
+    float *x, *y;
+    int32_t *cty, *spl, *slt;
+    __device__ __forceinline__ Rec load(uint32_t q) const
+    {
+        return Rec{x[q], y[q], cty[q], kInt ? slt[q] : 0, Val<V>::from_bits(spl[q])};
+    }
     static __device__ __forceinline__ V sp(const Rec &r) { return r.sp; }
-    __device__ __forceinline__ V dist(const Rec &a, const Rec &b) const { return dist_f32<FAST>(a.x, a.y, b.x, b.y); }
+    __device__ __forceinline__ V dist(const Rec &a, const Rec &b) const
+    {
+        if constexpr (METRIC == 0) return dist_f32<true>(a.x, a.y, b.x, b.y);
+        else if constexpr (METRIC == 1) return dist_f32<false>(a.x, a.y, b.x, b.y);
+        else if constexpr (METRIC == 2) return dist_nint_grid(a.x, a.y, b.x, b.y);
+        else return dist_nint(a.x, a.y, b.x, b.y);
+    }
     __device__ __forceinline__ void store_id(uint32_t q, const Rec &from) const
     {
         x[q] = from.x;
         y[q] = from.y;
         cty[q] = from.city;
+        if constexpr (kInt) slt[q] = from.slot;
     }
-    __device__ __forceinline__ void store_sp(uint32_t q, V v) const { spl[q] = v; }
+    __device__ __forceinline__ void store_sp(uint32_t q, V v) const { spl[q] = Val<V>::bits(v); }
 };
 
 // max_steps cursor steps (or until done).  Window unit = (block of RB rows, 32 consecutive columns):
 // a warp loads the 32 column records once and evaluates RB pairs per lane.  key = (row in window) << 14 | column orders the window's pairs lexicographically; the
 // cluster-wide minimum key is the reference's next move.
-template <bool FAST, bool SCREEN>
+template <int METRIC, bool SCREEN>
 __global__ void __launch_bounds__(kRefPThreads, 1)
-    ref_persistent_kernel(Pt *__restrict__ pts, uint32_t n, DevState *state, tl_move *__restrict__ log,
-                          uint64_t log_cap, uint32_t max_steps, float margin)
+    ref_persistent_kernel(Pt *__restrict__ pts, Cs *__restrict__ cs, const float2 *__restrict__ xy, uint32_t n,
+                          DevState *state, tl_move *__restrict__ log, uint64_t log_cap, uint32_t max_steps,
+                          float margin)
 {
+    using Pol = SmemSoaPol<METRIC>;
+    using V = typename Pol::V;
+    using Rec = typename Pol::Rec;
+    constexpr bool kInt = Pol::kInt;
     extern __shared__ __align__(16) unsigned char ref_smem[];
     const uint32_t na = (n + 3u) & ~3u; // array pitch (words)
-    const SmemSoaPol<FAST> P{reinterpret_cast<float *>(ref_smem), reinterpret_cast<float *>(ref_smem) + na,
-                             reinterpret_cast<float *>(ref_smem) + 3 * (size_t)na,
-                             reinterpret_cast<int32_t *>(ref_smem) + 2 * (size_t)na};
+    const Pol P{reinterpret_cast<float *>(ref_smem), reinterpret_cast<float *>(ref_smem) + na,
+                reinterpret_cast<int32_t *>(ref_smem) + 2 * (size_t)na, reinterpret_cast<int32_t *>(ref_smem) + 3 * (size_t)na,
+                reinterpret_cast<int32_t *>(ref_smem) + 4 * (size_t)na};
     // [step parity]: the smallest hit key of the step known so far, CLUSTER-wide -- a warp that finds a
     // hit pushes it into every CTA's copy with a remote atomicMin (DSMEM), so every warp of the cluster
     // stops evaluating pairs behind it, and after the step's cluster barrier every copy holds the move
@@ -230,11 +254,21 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
 
     if (*reinterpret_cast<const volatile int *>(&state->done)) return; // cluster-uniform
     for (uint32_t q = tid; q < n; q += kRefPThreads) {
-        const float4 v = __ldcg(reinterpret_cast<const float4 *>(pts) + q); // Pt = {x, y, city, sp}
-        P.x[q] = v.x;
-        P.y[q] = v.y;
-        P.cty[q] = __float_as_int(v.z);
-        P.spl[q] = v.w;
+        if constexpr (kInt) {
+            const int4 v = __ldcg(reinterpret_cast<const int4 *>(cs) + q); // Cs = {slot, sp bits, city, pad}
+            const float2 c = __ldg(&xy[v.z]);
+            P.x[q] = c.x;
+            P.y[q] = c.y;
+            P.cty[q] = v.z;
+            P.spl[q] = v.y;
+            P.slt[q] = v.x;
+        } else {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(pts) + q); // Pt = {x, y, city, sp}
+            P.x[q] = v.x;
+            P.y[q] = v.y;
+            P.cty[q] = __float_as_int(v.z);
+            P.spl[q] = __float_as_int(v.w);
+        }
     }
     if (tid == 0) s_min[0] = s_min[1] = kNoHit;
     // replicated loop state
@@ -281,16 +315,20 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
             const uint32_t i0 = ci + w0;
             const uint32_t j = i0 + 2 + c * 32 + lane;
             const bool jin = j <= last_col;
-            Pt pj{}, pj1{};
+            Rec pj{}, pj1{};
             if (jin) {
                 pj = P.load(j);
                 pj1 = P.load(j + 1);
             }
             const uint32_t nr = min((uint32_t)RB, rows - w0); // rows of this block inside the window
-            Pt pi[RB + 1];
+            Rec pi[RB + 1];
 #pragma unroll
             for (int r = 0; r <= RB; ++r)
                 if ((uint32_t)r <= nr) pi[r] = P.load(i0 + r); // i0 + nr <= last_row + 1
+            // screened comparison: new < cur  =>  screened new < cur + margin (the margin covers the
+            // screened distances' error and, for the nint metrics, the two roundings to integers)
+            float spj1f = 0.f;
+            if constexpr (SCREEN) spj1f = (float)pj1.sp;
             bool cand[RB];
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
@@ -298,14 +336,13 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
                 // row i0 + r starts at column i + 2, the cursor's own row at cur_j
                 const uint32_t jfirst = (w0 + r == 0) ? cj : i0 + r + 2;
                 if ((uint32_t)r < nr && jin && j >= jfirst) {
-                    const float cur = __fadd_rn(pi[r + 1].sp, pj1.sp);
-                    if (SCREEN) { // cheap distances; anything within the error margin is re-checked exactly
+                    if constexpr (SCREEN) { // cheap distances; anything within the error margin is re-checked exactly
                         const float nws = __fadd_rn(dist_f32_screen(pi[r].x, pi[r].y, pj.x, pj.y),
                                                     dist_f32_screen(pi[r + 1].x, pi[r + 1].y, pj1.x, pj1.y));
-                        cand[r] = nws < __fadd_rn(cur, margin);
+                        cand[r] = nws < __fadd_rn(__fadd_rn((float)pi[r + 1].sp, spj1f), margin);
                     } else {
                         // two separately rounded sums, compared directly (two_opt.rs:35-49)
-                        cand[r] = __fadd_rn(P.dist(pi[r], pj), P.dist(pi[r + 1], pj1)) < cur;
+                        cand[r] = Val<V>::add(P.dist(pi[r], pj), P.dist(pi[r + 1], pj1)) < Val<V>::add(pi[r + 1].sp, pj1.sp);
                     }
                 }
             }
@@ -316,7 +353,7 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
                 if (SCREEN && bal && !hit_here) { // warp-uniform: the exact comparison for this row's candidates
                     bool hit = false;
                     if (cand[r])
-                        hit = __fadd_rn(P.dist(pi[r], pj), P.dist(pi[r + 1], pj1)) < __fadd_rn(pi[r + 1].sp, pj1.sp);
+                        hit = Val<V>::add(P.dist(pi[r], pj), P.dist(pi[r + 1], pj1)) < Val<V>::add(pi[r + 1].sp, pj1.sp);
                     bal = __ballot_sync(0xffffffffu, hit);
                 }
                 if (bal && !hit_here) { // the block's rows in order: the first row with a hit holds its smallest key
@@ -379,8 +416,13 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
     REFP_ADD(6, REFP_CLK() - tk0);
 
     if (rank == 0) {
-        for (uint32_t q = tid; q < n; q += kRefPThreads)
-            reinterpret_cast<float4 *>(pts)[q] = make_float4(P.x[q], P.y[q], __int_as_float(P.cty[q]), P.spl[q]);
+        for (uint32_t q = tid; q < n; q += kRefPThreads) {
+            if constexpr (kInt)
+                reinterpret_cast<int4 *>(cs)[q] = make_int4(P.slt[q], P.spl[q], P.cty[q], 0);
+            else
+                reinterpret_cast<float4 *>(pts)[q] =
+                    make_float4(P.x[q], P.y[q], __int_as_float(P.cty[q]), __int_as_float(P.spl[q]));
+        }
         if (tid == 0) {
             state->moves = moves;
             state->passes = passes;
@@ -438,21 +480,44 @@ namespace tl {
 #endif
 
 // The persistent form: one cluster of `csize` CTAs (16 needs the non-portable opt-in; 8 otherwise).
-// Returns the cluster size this device can run for n records, 0 if the form does not apply.
-int ref_persistent_cluster_size(const Src &src, uint32_t n)
+namespace {
+using RefPFn = void (*)(Pt *, Cs *, const float2 *, uint32_t, DevState *, tl_move *, uint64_t, uint32_t, float);
+RefPFn refp_fn(int metric, bool screen)
 {
-    if (src.kind > SRC_EUC_SAFE || n < 4 || n > (uint32_t)kRefPersistMaxN) return 0;
-    static int cached_size[2] = {-1, -1}; // by FAST; the answer for the largest n holds for every n
-    const int fast = src.kind == SRC_EUC_FAST ? 1 : 0;
-    if (cached_size[fast] >= 0) return cached_size[fast];
-    const void *fn = fast ? (const void *)ref_persistent_kernel<true, false> : (const void *)ref_persistent_kernel<false, false>;
-    const size_t smem = (size_t)kRefPersistMaxN * sizeof(Pt);
+    switch (metric) {
+    case 0: return screen ? ref_persistent_kernel<0, true> : ref_persistent_kernel<0, false>;
+    case 1: return ref_persistent_kernel<1, false>; // no screening outside the fast-sqrt domain
+    case 2: return screen ? ref_persistent_kernel<2, true> : ref_persistent_kernel<2, false>;
+    default: return screen ? ref_persistent_kernel<3, true> : ref_persistent_kernel<3, false>;
+    }
+}
+// 0/1: f32 coordinate sessions; 2/3: nint matrix sessions of coordinate problems (xy given); -1: none
+int refp_metric(const Src &src, const float2 *xy, int nint_mode)
+{
+    if (src.kind == SRC_EUC_FAST) return 0;
+    if (src.kind == SRC_EUC_SAFE) return 1;
+    if (src.kind == SRC_MAT_I32 && xy && nint_mode == 2) return 2;
+    if (src.kind == SRC_MAT_I32 && xy && nint_mode == 1) return 3;
+    return -1;
+}
+size_t refp_smem_bytes(int metric, uint32_t n) { return (size_t)((n + 3u) & ~3u) * (metric >= 2 ? 20 : 16); }
+} // namespace
+
+// Returns the cluster size this device can run for n records, 0 if the form does not apply.
+int ref_persistent_cluster_size(const Src &src, const float2 *xy, int nint_mode, uint32_t n)
+{
+    const int metric = refp_metric(src, xy, nint_mode);
+    if (metric < 0 || n < 4 || n > (uint32_t)(metric >= 2 ? kRefPersistMaxNInt : kRefPersistMaxN)) return 0;
+    static int cached_size = -1; // every instantiation has the same shape; the answer for the largest n holds for every n
+    if (cached_size >= 0) return cached_size;
+    const size_t smem = (size_t)kRefPersistMaxN * 16;
+    static_assert((size_t)kRefPersistMaxNInt * 20 <= (size_t)kRefPersistMaxN * 16, "one shared-memory opt-in for all");
     int best = 0;
     bool ok = true;
-    for (const void *f : {(const void *)ref_persistent_kernel<true, true>, (const void *)ref_persistent_kernel<true, false>,
-                          (const void *)ref_persistent_kernel<false, false>})
-        ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
-             cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    for (int m = 0; m < 4; ++m)
+        for (int sc = 0; sc < 2; ++sc)
+            ok = ok && cudaFuncSetAttribute((const void *)refp_fn(m, sc != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                 cudaFuncSetAttribute((const void *)refp_fn(m, sc != 0), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
     if (ok) {
         for (int cs : {16, 8, 4, 2}) {
             cudaLaunchAttribute attr[1];
@@ -467,7 +532,7 @@ int ref_persistent_cluster_size(const Src &src, uint32_t n)
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) == cudaSuccess && nclusters >= 1) {
+            if (cudaOccupancyMaxActiveClusters(&nclusters, (const void *)refp_fn(2, true), &cfg) == cudaSuccess && nclusters >= 1) {
                 best = cs;
                 break;
             }
@@ -480,13 +545,16 @@ int ref_persistent_cluster_size(const Src &src, uint32_t n)
         if (want <= 0) best = 0;
         else if (want < best) best = want;
     }
-    cached_size[fast] = best;
+    cached_size = best;
     return best;
 }
 
-void launch_ref_persistent(const Src &src, uint32_t n, DevState *state, tl_move *log, uint64_t log_cap,
-                           uint32_t max_steps, int csize, float screen_margin, cudaStream_t st)
+// screen_margin >= 0 (fast-sqrt domain only, common.cuh: kScreenMarginScale): screened distances first;
+// the nint metrics add the two roundings to integers (1.0) to it
+void launch_ref_persistent(const Src &src, const float2 *xy, int nint_mode, uint32_t n, DevState *state, tl_move *log,
+                           uint64_t log_cap, uint32_t max_steps, int csize, float screen_margin, cudaStream_t st)
 {
+    const int metric = refp_metric(src, xy, nint_mode);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)csize;
@@ -495,17 +563,13 @@ void launch_ref_persistent(const Src &src, uint32_t n, DevState *state, tl_move 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)csize);
     cfg.blockDim = dim3(kRefPThreads);
-    cfg.dynamicSmemBytes = (size_t)((n + 3u) & ~3u) * sizeof(Pt);
+    cfg.dynamicSmemBytes = refp_smem_bytes(metric, n);
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    // screen_margin >= 0 (fast-sqrt domain only, common.cuh: kScreenMarginScale): screened distances first
-    if (src.kind == SRC_EUC_FAST && screen_margin >= 0.0f)
-        cudaLaunchKernelEx(&cfg, ref_persistent_kernel<true, true>, src.pts, n, state, log, (uint64_t)log_cap, max_steps, screen_margin);
-    else if (src.kind == SRC_EUC_FAST)
-        cudaLaunchKernelEx(&cfg, ref_persistent_kernel<true, false>, src.pts, n, state, log, (uint64_t)log_cap, max_steps, -1.0f);
-    else
-        cudaLaunchKernelEx(&cfg, ref_persistent_kernel<false, false>, src.pts, n, state, log, (uint64_t)log_cap, max_steps, -1.0f);
+    const bool screen = screen_margin >= 0.0f && metric != 1;
+    const float margin = screen ? (metric >= 2 ? screen_margin + 1.0009765625f : screen_margin) : -1.0f;
+    cudaLaunchKernelEx(&cfg, refp_fn(metric, screen), src.pts, src.cs, xy, n, state, log, (uint64_t)log_cap, max_steps, margin);
 }
 
 void launch_apply_two_opt(const Src &src, const void *cand, int ncand, DevState *state, unsigned int *ticket,

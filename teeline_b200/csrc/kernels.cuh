@@ -128,11 +128,14 @@ void launch_extract_tour(const Src &src, uint32_t n, uint32_t *tour, cudaStream_
 constexpr int kRefWindow0 = 8; // rows scanned per launch right after a hit
 void launch_ref_step(const Src &src, uint32_t n, DevState *state, unsigned int *ticket, tl_move *log,
                      uint64_t log_cap, int grid, cudaStream_t st);
-// persistent form: one thread-block cluster runs up to max_steps cursor steps from shared memory
-constexpr int kRefPersistMaxN = 14000; // 16-byte records of the whole tour in one SM's shared memory
-int ref_persistent_cluster_size(const Src &src, uint32_t n);
-void launch_ref_persistent(const Src &src, uint32_t n, DevState *state, tl_move *log, uint64_t log_cap,
-                           uint32_t max_steps, int csize, float screen_margin, cudaStream_t st);
+// persistent form: one thread-block cluster runs up to max_steps cursor steps from shared memory.
+// f32 coordinate sessions, and nint matrix sessions of coordinate problems (xy = city-ordered
+// coordinates, nint_mode as tl_problem::nint_mode(): the entries are recomputed, bit-equal to K1's)
+constexpr int kRefPersistMaxN = 14000;    // 16 bytes per position of the whole tour in one SM's shared memory
+constexpr int kRefPersistMaxNInt = 11000; // 20 bytes per position (the matrix slot travels with the city)
+int ref_persistent_cluster_size(const Src &src, const float2 *xy, int nint_mode, uint32_t n);
+void launch_ref_persistent(const Src &src, const float2 *xy, int nint_mode, uint32_t n, DevState *state, tl_move *log,
+                           uint64_t log_cap, uint32_t max_steps, int csize, float screen_margin, cudaStream_t st);
 
 // K3 Or-opt (recompute path)
 constexpr int kOrR = 8;          // columns per lane

@@ -382,10 +382,11 @@ tl_status enqueue_steps(tl_session *s, uint32_t steps)
     if (s->algo == TL_ALGO_TWO_OPT_REF) {
         // coordinate problems whose records fit one SM's shared memory: the whole chain of `steps`
         // cursor steps in ONE launch of a thread-block cluster (k2_two_opt_ref.cu, persistent form)
-        if (const int csize = ref_persistent_cluster_size(s->src, s->n)) {
+        if (const int csize = ref_persistent_cluster_size(s->src, s->p->d_xy, s->p->nint_mode(), s->n)) {
             const float m = s->p->dmax * kScreenMarginScale;
             const float margin = (s->p->fast_sqrt && std::isfinite(m) && s->p->dmax >= kScreenMinDmax && !getenv("TL_NO_SCREEN")) ? m : -1.0f;
-            launch_ref_persistent(s->src, s->n, s->state.p, s->log.p, s->log_cap, steps, csize, margin, st);
+            launch_ref_persistent(s->src, s->p->d_xy, s->p->nint_mode(), s->n, s->state.p, s->log.p, s->log_cap, steps, csize,
+                                  margin, st);
             s->c->launches += 1;
             TL_CUDA_TRY(cudaGetLastError());
             return TL_OK;
@@ -887,7 +888,7 @@ tl_status tl_session_run(tl_session *s, int64_t max_moves)
         uint32_t batch = s->algo == TL_ALGO_TWO_OPT_REF ? 64 : 32;
         // Mode R, persistent form: a batch is one launch, so make it long (the kernel stops by itself
         // at convergence or at the move budget)
-        if (s->algo == TL_ALGO_TWO_OPT_REF && ref_persistent_cluster_size(s->src, s->n)) batch = 1u << 20;
+        if (s->algo == TL_ALGO_TWO_OPT_REF && ref_persistent_cluster_size(s->src, s->p->d_xy, s->p->nint_mode(), s->n)) batch = 1u << 20;
         if (budgeted) {
             batch = (uint32_t)std::min<int64_t>(256, budget);
             budget -= batch;

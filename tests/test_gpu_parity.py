@@ -565,6 +565,49 @@ def test_nint_i32_matrix_path(T, ctx, algo):
     assert st.path_used == T.PATH_MATRIX
 
 
+def test_mode_r_nint_on_fractional_coordinates(T, ctx):
+    """TSPLIB nint of non-integer coordinates (evaluated in double, common.cuh: dist_nint): Mode R's
+    persistent kernel recomputes the matrix entries from the coordinates -- same moves as the oracle
+    on the packed matrix."""
+    n = 400
+    x, y = O.gen_uniform(n, 91)
+    x, y = (x * np.float32(37.3)).astype(np.float32), (y * np.float32(37.3)).astype(np.float32)
+    P = O.Problem(tri=O.matrix_packed_nint(x, y), n=n)
+    prob = T.Problem.euc2d(ctx, x, y, T.DIST_NINT_I32)
+    st = run_both(T, prob, P, "ref", O.shuffle_tour(n, 9), T.PATH_AUTO)
+    assert st.path_used == T.PATH_MATRIX and st.converged == 1
+
+
+def test_mode_r_10k_nint_matches_oracle(T, ctx):
+    """BASELINE config 3 (10k cities, int32 TSPLIB-nint matrix), reference-exact first improvement:
+    the whole search against the CPU oracle on the packed nint matrix; the Or-opt stage that follows
+    still finds the session's Cs records and matrix consistent."""
+    n = 10000
+    gx, gy = O.gen_grid(n, n)
+    P = O.Problem(tri=O.matrix_packed_nint(gx, gy), n=n)
+    start = O.nn_tour(P, 3)
+    want_t, want_st, want_mv = O.two_opt_ref(P, start, log_cap=1 << 16)
+    prob = T.Problem.euc2d(ctx, gx, gy, T.DIST_NINT_I32)
+    got_t, st, mv = prob.local_search(T.ALGO_TWO_OPT_REF, start, log_cap=1 << 16)
+    assert st.path_used == T.PATH_MATRIX
+    assert [m[1:3] for m in mv] == [m[1:3] for m in want_mv]
+    assert [np.float32(m[0]) for m in mv] == [np.float32(m[0]) for m in want_mv]
+    assert (got_t.astype(np.int64) == want_t).all()
+    assert (int(st.moves), int(st.passes), int(st.evals)) == (want_st.moves, want_st.passes, want_st.evals)
+    # a budgeted run stops in the middle of the chain and hands the records back to the matrix kernels
+    s = prob.session(T.ALGO_TWO_OPT_REF, start)
+    s.run(max_moves=100)
+    mid = s.tour()
+    s.close()
+    want_mid = np.asarray(start, dtype=np.int64).copy()
+    for m in want_mv[:100]:
+        want_mid[m[1] + 1:m[2] + 1] = want_mid[m[1] + 1:m[2] + 1][::-1].copy()
+    assert (mid.astype(np.int64) == want_mid).all()
+    want_b = O.two_opt_best(P, mid, max_moves=3, nthreads=8, log_cap=8)
+    got_b = prob.local_search(T.ALGO_TWO_OPT_BEST, mid, max_moves=3, log_cap=8)
+    assert [m[:3] for m in got_b[2]] == [m[:3] for m in want_b[2]]
+
+
 def test_nint_berlin52_known_optimum(T, ctx, berlin52, golden_dir):
     ids, x, y = berlin52
     P = O.Problem(tri=O.matrix_packed_nint(x, y), n=52)
