@@ -304,23 +304,34 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
         unsigned int mine = kNoHit;
         const uint32_t dq = nwarps / cpr, dr = nwarps - dq * cpr; // unit stride in (block, chunk) form
         uint32_t b = gwarp / cpr, c = gwarp - b * cpr;            // one division per step
-        for (uint32_t u = gwarp; u < units; u += nwarps) {
+        auto next_unit = [&]() { // (block, chunk) of the warp's next unit
+            c += dr;
+            b += dq;
+            if (c >= cpr) { c -= cpr; b += 1; }
+        };
+        for (uint32_t u = gwarp; u < units; u += nwarps, next_unit()) {
+            const uint32_t w0 = b * RB;
+            const uint32_t i0 = ci + w0;
+            const uint32_t jw = i0 + 2 + c * 32; // the warp's first column
+            if (jw > last_col) continue;         // the chunk lies beyond the end of these (shorter) rows
             // every key of this and of the warp's later units is at least (first row of the block) << 14:
-            // stop once a smaller hit is known (this warp's, or any in this CTA -- one read per warp)
+            // stop once a smaller hit is known (this warp's, or any in the cluster -- one read per warp)
             unsigned int known = 0;
             if (lane == 0) known = *reinterpret_cast<volatile unsigned int *>(&s_min[par]);
             known = min(mine, __shfl_sync(0xffffffffu, known, 0));
-            const uint32_t w0 = b * RB;
             if ((w0 << 14) > known) break;
-            const uint32_t i0 = ci + w0;
-            const uint32_t j = i0 + 2 + c * 32 + lane;
+            REFP_ADD(2, 1);
+            const uint32_t j = jw + lane;
+            const uint32_t nr = min((uint32_t)RB, rows - w0); // rows of this block inside the window
+            // FULL: every (row, lane) of the unit is a pair of the window -- no per-pair range tests
+            const bool full = nr == (uint32_t)RB && w0 != 0 && c != 0 && jw + 31 <= last_col;
+            static_assert(RB <= 33, "chunk 1 starts right of every row's first column");
             const bool jin = j <= last_col;
             Rec pj{}, pj1{};
             if (jin) {
                 pj = P.load(j);
                 pj1 = P.load(j + 1);
             }
-            const uint32_t nr = min((uint32_t)RB, rows - w0); // rows of this block inside the window
             Rec pi[RB + 1];
 #pragma unroll
             for (int r = 0; r <= RB; ++r)
@@ -328,24 +339,35 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
             // screened comparison: new < cur  =>  screened new < cur + margin (the margin covers the
             // screened distances' error and, for the nint metrics, the two roundings to integers)
             float spj1f = 0.f;
-            if constexpr (SCREEN) spj1f = (float)pj1.sp;
+            if constexpr (SCREEN) spj1f = __fadd_rn((float)pj1.sp, margin);
             bool cand[RB];
+            auto eval_rows = [&](auto FullC) {
+                constexpr bool FULL = decltype(FullC)::value;
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                cand[r] = false;
-                // row i0 + r starts at column i + 2, the cursor's own row at cur_j
-                const uint32_t jfirst = (w0 + r == 0) ? cj : i0 + r + 2;
-                if ((uint32_t)r < nr && jin && j >= jfirst) {
-                    if constexpr (SCREEN) { // cheap distances; anything within the error margin is re-checked exactly
-                        const float nws = __fadd_rn(dist_f32_screen(pi[r].x, pi[r].y, pj.x, pj.y),
-                                                    dist_f32_screen(pi[r + 1].x, pi[r + 1].y, pj1.x, pj1.y));
-                        cand[r] = nws < __fadd_rn(__fadd_rn((float)pi[r + 1].sp, spj1f), margin);
-                    } else {
-                        // two separately rounded sums, compared directly (two_opt.rs:35-49)
-                        cand[r] = Val<V>::add(P.dist(pi[r], pj), P.dist(pi[r + 1], pj1)) < Val<V>::add(pi[r + 1].sp, pj1.sp);
+                for (int r = 0; r < RB; ++r) {
+                    cand[r] = false;
+                    // row i0 + r starts at column i + 2, the cursor's own row at cur_j
+                    const uint32_t jfirst = (w0 + r == 0) ? cj : i0 + r + 2;
+                    if (FULL || ((uint32_t)r < nr && jin && j >= jfirst)) {
+                        if constexpr (SCREEN) { // cheap distances; anything within the error margin is re-checked exactly
+                            const float nws = __fadd_rn(dist_f32_screen(pi[r].x, pi[r].y, pj.x, pj.y),
+                                                        dist_f32_screen(pi[r + 1].x, pi[r + 1].y, pj1.x, pj1.y));
+                            cand[r] = nws < __fadd_rn((float)pi[r + 1].sp, spj1f);
+                        } else {
+                            // two separately rounded sums, compared directly (two_opt.rs:35-49)
+                            cand[r] = Val<V>::add(P.dist(pi[r], pj), P.dist(pi[r + 1], pj1)) < Val<V>::add(pi[r + 1].sp, pj1.sp);
+                        }
                     }
                 }
-            }
+            };
+            if (full)
+                eval_rows(std::true_type{});
+            else
+                eval_rows(std::false_type{});
+            bool any_cand = false;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) any_cand |= cand[r];
+            if (__ballot_sync(0xffffffffu, any_cand) == 0) continue; // the common case: one vote per unit
             bool hit_here = false;
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
@@ -358,14 +380,10 @@ __global__ void __launch_bounds__(kRefPThreads, 1)
                 }
                 if (bal && !hit_here) { // the block's rows in order: the first row with a hit holds its smallest key
                     hit_here = true;
-                    mine = min(mine, ((w0 + r) << 14) | (j - lane + (uint32_t)(__ffs(bal) - 1)));
+                    mine = min(mine, ((w0 + r) << 14) | (jw + (uint32_t)(__ffs(bal) - 1)));
                 }
             }
             if (hit_here && lane < csize) atomicMin(cluster.map_shared_rank(&s_min[par], lane), mine);
-            c += dr;
-            b += dq;
-            if (c >= cpr) { c -= cpr; b += 1; }
-            REFP_ADD(2, 1);
         }
         const long long tp1 = REFP_CLK();
         cluster_barrier(); // release/acquire: every hit of the step has landed in every copy
