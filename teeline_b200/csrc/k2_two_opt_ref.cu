@@ -224,8 +224,9 @@ struct SmemSoaPol {
 };
 
 // max_steps cursor steps (or until done).  Window unit = (block of RB rows, 32 consecutive columns):
-// a warp loads the 32 column records once and evaluates RB pairs per lane.  key = (row in window) << 14 | column orders the window's pairs lexicographically; the
-// cluster-wide minimum key is the reference's next move.
+// a warp loads the 32 column records once and evaluates RB pairs per lane.
+// key = (row in window) << 14 | column orders the window's pairs lexicographically; the cluster-wide
+// minimum key is the reference's next move.
 template <int METRIC, bool SCREEN>
 __global__ void __launch_bounds__(kRefPThreads, 1)
     ref_persistent_kernel(Pt *__restrict__ pts, Cs *__restrict__ cs, const float2 *__restrict__ xy, uint32_t n,
