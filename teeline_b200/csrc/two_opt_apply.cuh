@@ -30,9 +30,13 @@ __device__ __forceinline__ void reverse_segment_inplace(const Pol &P, uint32_t m
     // round costs one memory round trip instead of U (a thread's own records never alias)
     constexpr int U = 4;
     Rec P0{}, P1{}; // the segment's outer neighbours, needed by thread 0 only: load them up front
+    V sp_first = V(); // entering edge of position mi+1 (thread 0's delta needs it).  Read here and not from
+                      // A[] below: position mi+1+t's edge length is rewritten by thread t-1, so a thread
+                      // t > 0 must not touch that field at all (array-of-fields policies then never load it)
     if (tid == 0) {
         P0 = P.load(mi);
         P1 = P.load(mj + 1);
+        sp_first = Pol::sp(P.load(mi + 1));
     }
     for (uint32_t t0 = tid; t0 < nxy; t0 += nthreads * U) {
         Rec A[U], B[U];
@@ -55,13 +59,13 @@ __device__ __forceinline__ void reverse_segment_inplace(const Pol &P, uint32_t m
                 V e1, e2;
                 if (known_e1) {
                     e1 = e1_in;
-                    e2 = Val<V>::sub(Val<V>::add(delta_in, Val<V>::add(Pol::sp(A[u]), Pol::sp(P1))), e1_in);
+                    e2 = Val<V>::sub(Val<V>::add(delta_in, Val<V>::add(sp_first, Pol::sp(P1))), e1_in);
                 } else {
                     e1 = P.dist(P0, B[u]); // new edge (p_i, p_j)
                     e2 = P.dist(A[u], P1); // new edge (p_i+1, p_j+1)
                 }
                 if (delta_out)
-                    *delta_out = (float)Val<V>::sub(Val<V>::add(e1, e2), Val<V>::add(Pol::sp(A[u]), Pol::sp(P1)));
+                    *delta_out = (float)Val<V>::sub(Val<V>::add(e1, e2), Val<V>::add(sp_first, Pol::sp(P1)));
                 P.store_sp(a, e1);
                 P.store_sp(mj + 1, e2);
             }
